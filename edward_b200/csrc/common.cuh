@@ -1,0 +1,182 @@
+// common.cuh — shared device-side definitions: kernel argument block, likelihood families,
+// Philox4x32-10, deterministic block reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace edhmc {
+
+constexpr int kWarpsPerCta = 8;            // consumer warps per CTA (each owns a private TMA ring)
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kMaxStages = 8;
+constexpr int kMaxFeatures = 2048;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Scalars of the chain that live in global memory between launches.
+struct ChainScalars {
+  double logp_cur;   // log joint of the current state (cached across transitions and launches)
+  double logp_new;   // stepwise plan: log joint at the proposal
+  double k_old;      // stepwise plan: kinetic energy of the drawn momentum
+  double log_u;      // stepwise plan
+  long long n_accept;
+  int valid;         // 1: (zcur, gcur, logp_cur) describe params[max(t-1,0)]
+  int need_init;     // stepwise plan: the initial evaluation pass is live
+  int nonfinite;     // debug: set if a log joint / gradient went NaN/Inf
+  int pad;
+};
+
+struct KArgs {
+  // ---- problem (edhmc_cfg + bound data) ----
+  const float* X;
+  const void* y;
+  long long n_rows;
+  long long ldx;
+  int D;
+  int P;
+  int has_bias;
+  int family;
+  int y_dtype;
+  float lik_scale;
+  const float* prior_loc;
+  const float* prior_scale;
+  double prior_const;  // sum_c (0.5*log(2*pi) + log(scale_c)), float64, computed once on the host
+  // ---- streaming plan ----
+  int Kact;          // active vector chunks per lane
+  int J;             // row groups per tile
+  int RT;            // rows per tile = (32/G)*J
+  int S;             // ring stages per warp
+  int stage_floats;  // ring stage stride in floats (x tile + y slice + pad)
+  int y_off;         // float offset of the y slice inside a stage
+  int wpad;          // padded length of theta in shared memory (G*KMAX*V)
+  int zigzag;        // 1: odd passes walk a warp's tiles backwards (L2 reuse)
+  int l2_hint;       // 0 none, 1 evict_last on all X tiles
+  int n_shard_ctas;  // CTAs that share the rows (== gridDim.x)
+  // ---- scratch ----
+  double* partials;            // [2][grid][P+1]
+  unsigned long long* bar;     // grid barrier counter (persistent plan)
+  unsigned int* ticket;        // last-arriver ticket (stepwise plan)
+  double* sums;                // [P+1] shard sums → all-reduced in place (stepwise plan)
+  // ---- chain state ----
+  ChainScalars* sc;
+  float* zcur;  // [P]
+  float* gcur;  // [P]
+  float* z;     // [P] stepwise plan working position (also theta of edhmc_logp_grad)
+  float* r;     // [P] stepwise plan working momentum
+  // ---- run ----
+  float* params;
+  long long ldp;
+  long long t0;
+  long long n_iter;
+  float eps;
+  float half_eps;
+  int L;
+  const float* r0;
+  const float* u;
+  unsigned long long seed;
+  double* trace_scalars;
+  float* trace_pos;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Likelihood families. Returns log p(y|eta) and d/deta log p(y|eta), float32, in the op order of
+// the TensorFlow path the reference executes (see oracle/hmc_oracle.py for the citations).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void row_terms(int family, float eta, float yv, float lik_scale, float& lp, float& r) {
+  if (family == 0) {
+    // -(where(l>=0,l,0) - l*y + log1p(exp(-|l|)));  gradient y - sigmoid(l), piecewise as autodiff does
+    const bool pos = eta >= 0.0f;
+    const float e = expf(pos ? -eta : eta);
+    const float relu = pos ? eta : 0.0f;
+    lp = -__fadd_rn(__fsub_rn(relu, __fmul_rn(eta, yv)), log1pf(e));
+    const float q = __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(1.0f, e)), e);
+    r = pos ? __fadd_rn(__fsub_rn(yv, 1.0f), q) : __fsub_rn(yv, q);
+  } else if (family == 1) {
+    const float zz = __fdiv_rn(__fsub_rn(yv, eta), lik_scale);
+    lp = __fsub_rn(__fmul_rn(-0.5f, __fmul_rn(zz, zz)), __fadd_rn(0.9189385332046727f, logf(lik_scale)));
+    r = __fdiv_rn(zz, lik_scale);
+  } else {
+    const float mu = expf(eta);
+    lp = __fsub_rn(__fsub_rn(__fmul_rn(yv, eta), mu), lgammaf(yv + 1.0f));
+    r = __fsub_rn(yv, mu);
+  }
+}
+
+__device__ __forceinline__ float load_y(const void* y, int y_dtype, long long i) {
+  if (y_dtype == 0) return static_cast<float>(__ldg(reinterpret_cast<const int*>(y) + i));
+  if (y_dtype == 1) return __ldg(reinterpret_cast<const float*>(y) + i);
+  return static_cast<float>(__ldg(reinterpret_cast<const unsigned char*>(y) + i));
+}
+__device__ __forceinline__ float y_from_bits(uint32_t bits, int y_dtype) {
+  return y_dtype == 0 ? static_cast<float>(static_cast<int>(bits)) : __uint_as_float(bits);
+}
+
+// Normal prior, float64: log density without the constant, and its gradient.
+__device__ __forceinline__ double prior_quad(float zc, float loc, float scale) {
+  const double t = (static_cast<double>(zc) - static_cast<double>(loc)) / static_cast<double>(scale);
+  return -0.5 * t * t;
+}
+__device__ __forceinline__ double prior_grad(float zc, float loc, float scale) {
+  const double s = static_cast<double>(scale);
+  return -((static_cast<double>(zc) - static_cast<double>(loc)) / s) / s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: draws are a pure function of
+// (seed, transition index, element index), so every CTA and every rank generates the same numbers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]);
+    const uint32_t lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]);
+    const uint32_t lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0;
+    const uint32_t n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0;
+    c[1] = lo1;
+    c[2] = n2;
+    c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ float u01_open(uint32_t x) {  // (0,1)
+  return (static_cast<float>(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+// Standard normal for element `idx` of transition `t` (Box–Muller on two Philox words).
+__device__ __forceinline__ float philox_normal(unsigned long long seed, long long t, int idx) {
+  uint32_t c[4] = {static_cast<uint32_t>(idx), static_cast<uint32_t>(t), static_cast<uint32_t>(t >> 32), 0x4e6f726du};
+  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const float u1 = u01_open(c[0]);
+  const float u2 = u01_open(c[1]);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+__device__ __forceinline__ float philox_uniform(unsigned long long seed, long long t) {
+  uint32_t c[4] = {0u, static_cast<uint32_t>(t), static_cast<uint32_t>(t >> 32), 0x556e6966u};
+  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  return u01_open(c[0]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic reductions (fixed tree, float64).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+  return v;
+}
+// Block-wide sum; every thread gets the result. `scratch` holds >= 32 doubles. Contains barriers.
+__device__ __forceinline__ double block_sum_f64(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum_f64(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < nw; ++w) t += scratch[w];
+  return t;
+}
+
+}  // namespace edhmc

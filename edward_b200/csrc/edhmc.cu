@@ -1,0 +1,625 @@
+// edhmc.cu — host side of libedhmc.so: execution planner, kernel dispatch, the C ABI of include/edhmc.h,
+// and NCCL (loaded lazily with dlopen so the library has no link-time NCCL dependency).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/edhmc.h"
+#include "chain.cuh"
+
+using namespace edhmc;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(EDHMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen
+// ------------------------------------------------------------------------------------------------
+struct NcclUid {
+  char internal[128];
+};
+typedef int (*fn_ncclGetUniqueId)(NcclUid*);
+typedef int (*fn_ncclCommInitRank)(void**, int, NcclUid, int);
+typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(void*);
+typedef const char* (*fn_ncclGetErrorString)(int);
+
+struct NcclApi {
+  void* lib = nullptr;
+  fn_ncclGetUniqueId GetUniqueId = nullptr;
+  fn_ncclCommInitRank CommInitRank = nullptr;
+  fn_ncclAllReduce AllReduce = nullptr;
+  fn_ncclCommDestroy CommDestroy = nullptr;
+  fn_ncclGetErrorString GetErrorString = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // reuse the copy torch already mapped
+    if (lib) break;
+  }
+  if (!lib)
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+  if (!lib) return fail(EDHMC_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (fn_ncclGetUniqueId)dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (fn_ncclCommInitRank)dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (fn_ncclAllReduce)dlsym(lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (fn_ncclCommDestroy)dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (fn_ncclGetErrorString)dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail(EDHMC_ERR_COMM, "libnccl is missing required symbols");
+  g_nccl.lib = lib;
+  return 0;
+}
+#define NCCL_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    int r__ = (expr);                                                                                    \
+    if (r__ != 0)                                                                                        \
+      return fail(EDHMC_ERR_COMM, "%s failed: %s", #expr,                                                \
+                  g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error");                    \
+  } while (0)
+static const int kNcclFloat64 = 8, kNcclSum = 0;
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct Plan {
+  int G = 0, V = 0, KMAX = 0, Kact = 0, J = 0, RT = 0, S = 0, stage_floats = 0, y_off = 0, wpad = 0;
+  int grid = 0;
+  size_t smem_persist = 0, smem_pass = 0;
+  const void* fn_persist = nullptr;
+  const void* fn_pass = nullptr;
+  bool persistent_ok = false;
+};
+
+struct edhmc_handle {
+  edhmc_cfg cfg;
+  int P = 0;
+  int num_sms = 0;
+  int smem_optin = 0;
+  bool bound = false;
+  const float* X = nullptr;
+  const void* y = nullptr;
+  int y_dtype = 0;
+  int* y_owned = nullptr;  // int32 copy when the caller's y is uint8
+  Plan plan;
+  int zigzag = 1;
+  int l2_hint = 0;
+  // device buffers
+  float* d_prior_loc = nullptr;
+  float* d_prior_scale = nullptr;
+  double prior_const = 0.0;
+  ChainScalars* d_sc = nullptr;
+  float* d_zcur = nullptr;
+  float* d_gcur = nullptr;
+  float* d_z = nullptr;
+  float* d_r = nullptr;
+  float* d_g = nullptr;
+  double* d_partials = nullptr;
+  size_t partials_cap = 0;
+  unsigned long long* d_bar = nullptr;
+  unsigned int* d_ticket = nullptr;
+  double* d_sums = nullptr;
+  unsigned long long* d_bad = nullptr;
+  uint64_t seed = 0x243F6A8885A308D3ull;
+  double* trace_scalars = nullptr;
+  float* trace_pos = nullptr;
+  // nccl
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
+  // stats
+  long long passes_last = 0, launches_last = 0;
+  int plan_in_use = 0;
+};
+
+template <int G, int V>
+static void plan_fns(Plan& p) {
+  constexpr int KMAX = 64 / V;
+  p.fn_persist = reinterpret_cast<const void*>(&k_hmc_persistent<G, V, KMAX>);
+  p.fn_pass = reinterpret_cast<const void*>(&k_pass<G, V, KMAX>);
+}
+
+static long long gcdll(long long a, long long b) { return b ? gcdll(b, a % b) : a; }
+
+static int make_plan(edhmc_handle* h) {
+  const edhmc_cfg& c = h->cfg;
+  Plan p;
+  const int D = c.n_features;
+  const long long ldx = c.ldx;
+  p.V = (ldx % 4 == 0) ? 4 : (ldx % 2 == 0 ? 2 : 1);
+  p.KMAX = 64 / p.V;
+  const int chunks = (D + p.V - 1) / p.V;
+  const int gs[3] = {1, 4, 32};
+  p.G = 0;
+  for (int g : gs)
+    if ((chunks + g - 1) / g <= p.KMAX) {
+      p.G = g;
+      break;
+    }
+  if (!p.G)
+    return fail(EDHMC_ERR_INVALID, "n_features=%d exceeds the supported maximum of %d", D, kMaxFeatures);
+  p.Kact = (chunks + p.G - 1) / p.G;
+  p.wpad = p.G * p.KMAX * p.V;
+  const int RPS = 32 / p.G;
+  const long long row_bytes = ldx * 4;
+  long long J = 7168 / (RPS * row_bytes);
+  if (J < 1) J = 1;
+  if (J > 8) J = 8;
+  // tiles must start on 16-byte boundaries: RT*ldx*4 % 16 == 0
+  const long long AU = 4 / gcdll(ldx, 4);
+  const long long jstep = AU / gcdll(RPS, AU);
+  J = (J + jstep - 1) / jstep * jstep;
+  p.J = static_cast<int>(J);
+  p.RT = RPS * p.J;
+  long long x_floats = static_cast<long long>(p.RT - 1) * ldx + static_cast<long long>(p.Kact) * p.G * p.V;
+  if (x_floats < static_cast<long long>(p.RT) * ldx) x_floats = static_cast<long long>(p.RT) * ldx;
+  x_floats = (x_floats + 3) / 4 * 4;
+  p.y_off = static_cast<int>(x_floats);
+  long long sf = x_floats + p.RT;
+  sf = (sf + 31) / 32 * 32;
+  p.stage_floats = static_cast<int>(sf);
+
+  const size_t budget = static_cast<size_t>(h->smem_optin) - 1024;
+  size_t offs[7];
+  int S = kMaxStages;
+  for (; S >= 1; --S)
+    if (smem_layout_bytes(S, p.stage_floats, h->P, p.wpad, true, offs) <= budget) break;
+  if (S < 2) {
+    // state arrays do not fit next to a 2-deep ring: persistent plan unavailable, try stepwise sizing
+    int S2 = kMaxStages;
+    for (; S2 >= 1; --S2)
+      if (smem_layout_bytes(S2, p.stage_floats, h->P, p.wpad, false, offs) <= budget) break;
+    if (S2 < 1) return fail(EDHMC_ERR_INVALID, "row of %lld bytes does not fit the shared-memory ring", row_bytes);
+    p.S = S2;
+    p.persistent_ok = false;
+  } else {
+    p.S = S;
+    p.persistent_ok = true;
+  }
+  p.smem_persist = smem_layout_bytes(p.S, p.stage_floats, h->P, p.wpad, true, offs);
+  p.smem_pass = smem_layout_bytes(p.S, p.stage_floats, h->P, p.wpad, false, offs);
+
+  switch (p.G * 10 + p.V) {
+    case 11: plan_fns<1, 1>(p); break;
+    case 12: plan_fns<1, 2>(p); break;
+    case 14: plan_fns<1, 4>(p); break;
+    case 41: plan_fns<4, 1>(p); break;
+    case 42: plan_fns<4, 2>(p); break;
+    case 44: plan_fns<4, 4>(p); break;
+    case 321: plan_fns<32, 1>(p); break;
+    case 322: plan_fns<32, 2>(p); break;
+    case 324: plan_fns<32, 4>(p); break;
+    default: return fail(EDHMC_ERR_INVALID, "internal: no kernel for G=%d V=%d", p.G, p.V);
+  }
+  if (p.persistent_ok) {
+    cudaError_t e = cudaFuncSetAttribute(p.fn_persist, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(p.smem_persist));
+    if (e != cudaSuccess) return fail(EDHMC_ERR_CUDA, "cudaFuncSetAttribute(persist, %zu): %s", p.smem_persist, cudaGetErrorString(e));
+  }
+  {
+    cudaError_t e = cudaFuncSetAttribute(p.fn_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(p.smem_pass));
+    if (e != cudaSuccess) return fail(EDHMC_ERR_CUDA, "cudaFuncSetAttribute(pass, %zu): %s", p.smem_pass, cudaGetErrorString(e));
+  }
+  // grid: one CTA per SM, fewer when there are not enough rows to give every warp two tiles
+  long long want = (c.n_rows + static_cast<long long>(kWarpsPerCta) * 2 * p.RT - 1) /
+                   (static_cast<long long>(kWarpsPerCta) * 2 * p.RT);
+  if (want < 1) want = 1;
+  int per_sm = 1;
+  if (p.persistent_ok) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p.fn_persist, kThreads, p.smem_persist);
+    if (e != cudaSuccess) return fail(EDHMC_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+    if (per_sm < 1) return fail(EDHMC_ERR_CUDA, "persistent kernel does not fit on an SM (smem %zu)", p.smem_persist);
+    per_sm = 1;  // the ring is sized for one CTA per SM
+  }
+  const long long cap = static_cast<long long>(h->num_sms) * per_sm;
+  p.grid = static_cast<int>(want < cap ? want : cap);
+  h->plan = p;
+  return 0;
+}
+
+static void fill_args(edhmc_handle* h, KArgs& a) {
+  memset(&a, 0, sizeof(a));
+  const edhmc_cfg& c = h->cfg;
+  a.X = h->X;
+  a.y = h->y;
+  a.n_rows = c.n_rows;
+  a.ldx = c.ldx;
+  a.D = c.n_features;
+  a.P = h->P;
+  a.has_bias = c.has_bias;
+  a.family = c.family;
+  a.y_dtype = h->y_dtype;
+  a.lik_scale = c.lik_scale;
+  a.prior_loc = h->d_prior_loc;
+  a.prior_scale = h->d_prior_scale;
+  a.prior_const = h->prior_const;
+  const Plan& p = h->plan;
+  a.Kact = p.Kact;
+  a.J = p.J;
+  a.RT = p.RT;
+  a.S = p.S;
+  a.stage_floats = p.stage_floats;
+  a.y_off = p.y_off;
+  a.wpad = p.wpad;
+  a.zigzag = h->zigzag;
+  a.l2_hint = h->l2_hint;
+  a.n_shard_ctas = p.grid;
+  a.partials = h->d_partials;
+  a.bar = h->d_bar;
+  a.ticket = h->d_ticket;
+  a.sums = h->d_sums;
+  a.sc = h->d_sc;
+  a.zcur = h->d_zcur;
+  a.gcur = h->d_gcur;
+  a.z = h->d_z;
+  a.r = h->d_r;
+  a.seed = h->seed;
+  a.trace_scalars = h->trace_scalars;
+  a.trace_pos = h->trace_pos;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int edhmc_version(void) { return EDHMC_VERSION_MAJOR * 1000 + EDHMC_VERSION_MINOR; }
+
+const char* edhmc_last_error(void) { return g_last_error.c_str(); }
+
+int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
+  if (!out || !cfg) return fail(EDHMC_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->n_rows < 0 || cfg->n_rows_global < cfg->n_rows) return fail(EDHMC_ERR_INVALID, "bad n_rows / n_rows_global");
+  if (cfg->n_features < 1 || cfg->n_features > kMaxFeatures)
+    return fail(EDHMC_ERR_INVALID, "n_features must be in [1, %d], got %d", kMaxFeatures, cfg->n_features);
+  if (cfg->ldx < cfg->n_features) return fail(EDHMC_ERR_INVALID, "ldx (%lld) < n_features (%d)", (long long)cfg->ldx, cfg->n_features);
+  if (cfg->ldx > (1 << 20)) return fail(EDHMC_ERR_INVALID, "ldx too large");
+  if (cfg->family < 0 || cfg->family > 2) return fail(EDHMC_ERR_INVALID, "unknown family %d", cfg->family);
+  if (cfg->y_dtype < 0 || cfg->y_dtype > 2) return fail(EDHMC_ERR_INVALID, "unknown y_dtype %d", cfg->y_dtype);
+  if (cfg->family == EDHMC_NORMAL_IDENTITY && !(cfg->lik_scale > 0.0f))
+    return fail(EDHMC_ERR_INVALID, "lik_scale must be > 0 for the Normal family");
+  if (!cfg->prior_loc_host || !cfg->prior_scale_host) return fail(EDHMC_ERR_INVALID, "prior arrays are required");
+  for (int i = 0; i < 5; ++i)
+    if (cfg->reserved[i] != 0) return fail(EDHMC_ERR_INVALID, "reserved fields must be zero");
+  const int P = cfg->n_features + (cfg->has_bias ? 1 : 0);
+  double pc = 0.0;
+  for (int i = 0; i < P; ++i) {
+    if (!(cfg->prior_scale_host[i] > 0.0f) || !isfinite(cfg->prior_scale_host[i]) || !isfinite(cfg->prior_loc_host[i]))
+      return fail(EDHMC_ERR_INVALID, "prior_scale[%d] must be finite and > 0, prior_loc finite", i);
+    pc += 0.5 * log(2.0 * M_PI) + log(static_cast<double>(cfg->prior_scale_host[i]));
+  }
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(EDHMC_ERR_INVALID, "device %d out of range (%d CUDA devices visible)", cfg->device, ndev);
+  CUDA_TRY(cudaSetDevice(cfg->device));
+
+  edhmc_handle* h = new edhmc_handle();
+  h->cfg = *cfg;
+  h->cfg.prior_loc_host = nullptr;
+  h->cfg.prior_scale_host = nullptr;
+  h->P = P;
+  h->prior_const = pc;
+  if (const char* e = getenv("EDHMC_ZIGZAG")) h->zigzag = atoi(e);
+  if (const char* e = getenv("EDHMC_L2_HINT")) h->l2_hint = atoi(e);
+  cudaError_t e1 = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  cudaError_t e2 = cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    delete h;
+    return fail(EDHMC_ERR_CUDA, "cudaDeviceGetAttribute failed");
+  }
+  int rc = make_plan(h);
+  if (rc) {
+    delete h;
+    return rc;
+  }
+#define ALLOC(ptr, bytes)                                                                    \
+  do {                                                                                       \
+    cudaError_t e__ = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes));                 \
+    if (e__ != cudaSuccess) {                                                                \
+      edhmc_destroy(h);                                                                      \
+      return fail(EDHMC_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e__)); \
+    }                                                                                        \
+  } while (0)
+  const size_t pb = static_cast<size_t>(P) * sizeof(float);
+  ALLOC(h->d_prior_loc, pb);
+  ALLOC(h->d_prior_scale, pb);
+  ALLOC(h->d_sc, sizeof(ChainScalars));
+  ALLOC(h->d_zcur, pb);
+  ALLOC(h->d_gcur, pb);
+  ALLOC(h->d_z, pb);
+  ALLOC(h->d_r, pb);
+  ALLOC(h->d_g, pb);
+  h->partials_cap = static_cast<size_t>(2) * h->num_sms * (P + 1);
+  ALLOC(h->d_partials, h->partials_cap * sizeof(double));
+  ALLOC(h->d_bar, sizeof(unsigned long long));
+  ALLOC(h->d_ticket, sizeof(unsigned int));
+  ALLOC(h->d_sums, static_cast<size_t>(P + 1) * sizeof(double));
+  ALLOC(h->d_bad, sizeof(unsigned long long));
+#undef ALLOC
+  cudaMemcpy(h->d_prior_loc, cfg->prior_loc_host, pb, cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_prior_scale, cfg->prior_scale_host, pb, cudaMemcpyHostToDevice);
+  cudaMemset(h->d_sc, 0, sizeof(ChainScalars));
+  cudaMemset(h->d_zcur, 0, pb);
+  cudaMemset(h->d_gcur, 0, pb);
+  cudaMemset(h->d_bar, 0, sizeof(unsigned long long));
+  cudaMemset(h->d_ticket, 0, sizeof(unsigned int));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    edhmc_destroy(h);
+    return fail(EDHMC_ERR_CUDA, "initialisation failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return 0;
+}
+
+int edhmc_destroy(edhmc_t* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  cudaFree(h->d_prior_loc);
+  cudaFree(h->d_prior_scale);
+  cudaFree(h->d_sc);
+  cudaFree(h->d_zcur);
+  cudaFree(h->d_gcur);
+  cudaFree(h->d_z);
+  cudaFree(h->d_r);
+  cudaFree(h->d_g);
+  cudaFree(h->d_partials);
+  cudaFree(h->d_bar);
+  cudaFree(h->d_ticket);
+  cudaFree(h->d_sums);
+  cudaFree(h->d_bad);
+  cudaFree(h->y_owned);
+  delete h;
+  return 0;
+}
+
+int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite, void* stream_) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (h->cfg.n_rows > 0 && (!X || !y)) return fail(EDHMC_ERR_INVALID, "X and y are required");
+  if (reinterpret_cast<uintptr_t>(X) % 16 != 0) return fail(EDHMC_ERR_INVALID, "X must be 16-byte aligned");
+  if (h->cfg.y_dtype != EDHMC_Y_U8 && reinterpret_cast<uintptr_t>(y) % 4 != 0)
+    return fail(EDHMC_ERR_INVALID, "y must be 4-byte aligned");
+  h->X = X;
+  h->y = y;
+  h->y_dtype = h->cfg.y_dtype;
+  if (h->cfg.y_dtype == EDHMC_Y_U8 && h->cfg.n_rows > 0) {
+    if (!h->y_owned) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->y_owned), static_cast<size_t>(h->cfg.n_rows) * 4));
+    k_u8_to_i32<<<h->num_sms * 4, 256, 0, stream>>>(reinterpret_cast<const unsigned char*>(y), h->y_owned, h->cfg.n_rows);
+    CUDA_TRY(cudaGetLastError());
+    h->y = h->y_owned;
+    h->y_dtype = EDHMC_Y_I32;
+  }
+  h->bound = true;
+  // data changed: the cached log joint / gradient no longer apply
+  CUDA_TRY(cudaMemsetAsync(&h->d_sc->valid, 0, sizeof(int), stream));
+  if (check_finite && h->cfg.n_rows > 0) {
+    CUDA_TRY(cudaMemsetAsync(h->d_bad, 0, sizeof(unsigned long long), stream));
+    k_check_finite<<<h->num_sms * 8, 256, 0, stream>>>(X, h->cfg.n_rows, h->cfg.ldx, h->cfg.n_features, h->y,
+                                                        h->y_dtype, h->d_bad);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, h->d_bad, sizeof(bad), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (bad) {
+      h->bound = false;
+      return fail(EDHMC_ERR_NONFINITE, "Tensor had NaN or Inf values (%llu non-finite entries in X/y)", bad);
+    }
+  }
+  return 0;
+}
+
+static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int gate, cudaStream_t stream) {
+  KArgs aa = a;
+  const float* th = theta;
+  int gt = gate;
+  void* params[] = {&aa, &th, &gt};
+  CUDA_TRY(cudaLaunchKernel(h->plan.fn_pass, dim3(h->plan.grid), dim3(kThreads), params, h->plan.smem_pass, stream));
+  ++h->launches_last;
+  return 0;
+}
+
+static int allreduce_sums(edhmc_handle* h, cudaStream_t stream) {
+  if (h->nranks > 1) {
+    NCCL_TRY(g_nccl.AllReduce(h->d_sums, h->d_sums, static_cast<size_t>(h->P + 1), kNcclFloat64, kNcclSum, h->comm, stream));
+    ++h->launches_last;
+  }
+  return 0;
+}
+
+int edhmc_logp_grad(edhmc_t* h, const float* theta, double* logp, float* grad, void* stream_) {
+  if (!h || !theta || !logp || !grad) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data has not been called");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  h->launches_last = 0;
+  h->passes_last = 1;
+  KArgs a;
+  fill_args(h, a);
+  int rc = launch_pass(h, a, theta, 0, stream);
+  if (rc) return rc;
+  rc = allreduce_sums(h, stream);
+  if (rc) return rc;
+  k_logp_grad_finish<<<1, kThreads, 0, stream>>>(a, theta, logp, grad);
+  CUDA_TRY(cudaGetLastError());
+  ++h->launches_last;
+  return 0;
+}
+
+int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int64_t n_iter, float step_size,
+              int32_t n_steps, const float* r0, const float* u, void* stream_) {
+  if (!h || !params) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data has not been called");
+  if (ldp < h->P) return fail(EDHMC_ERR_INVALID, "ldp (%lld) < number of latent dimensions (%d)", (long long)ldp, h->P);
+  if (n_steps < 0 || n_iter < 0 || t0 < 0) return fail(EDHMC_ERR_INVALID, "negative n_steps / n_iter / t0");
+  if (t0 + n_iter > T)
+    return fail(EDHMC_ERR_RANGE, "indices[0] = %lld is not in [0, %lld)", (long long)(t0 + n_iter - 1), (long long)T);
+  if (n_iter == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  KArgs a;
+  fill_args(h, a);
+  a.params = params;
+  a.ldp = ldp;
+  a.t0 = t0;
+  a.n_iter = n_iter;
+  a.eps = step_size;
+  a.half_eps = 0.5f * step_size;
+  a.L = n_steps;
+  a.r0 = r0;
+  a.u = u;
+  h->launches_last = 0;
+  h->passes_last = n_iter * n_steps;
+
+  bool persistent = h->plan.persistent_ok && h->nranks == 1;
+  if (h->cfg.plan == EDHMC_PLAN_STEPWISE) persistent = false;
+  if (h->cfg.plan == EDHMC_PLAN_PERSISTENT && !persistent)
+    return fail(EDHMC_ERR_INVALID, "persistent plan unavailable (row shards or shared memory)");
+  h->plan_in_use = persistent ? EDHMC_PLAN_PERSISTENT : EDHMC_PLAN_STEPWISE;
+
+  if (persistent) {
+    CUDA_TRY(cudaMemsetAsync(h->d_bar, 0, sizeof(unsigned long long), stream));
+    void* kp[] = {&a};
+    CUDA_TRY(cudaLaunchCooperativeKernel(h->plan.fn_persist, dim3(h->plan.grid), dim3(kThreads), kp, h->plan.smem_persist, stream));
+    ++h->launches_last;
+  } else {
+    int rc;
+    k_chain_check<<<1, kThreads, 0, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = launch_pass(h, a, h->d_zcur, 1, stream))) return rc;
+    if ((rc = allreduce_sums(h, stream))) return rc;
+    k_chain_init_finish<<<1, kThreads, 0, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    h->launches_last += 2;
+    for (int64_t it = 0; it < n_iter; ++it) {
+      k_chain_begin<<<1, kThreads, 0, stream>>>(a, it, h->d_g);
+      CUDA_TRY(cudaGetLastError());
+      ++h->launches_last;
+      for (int s = 0; s < n_steps; ++s) {
+        if ((rc = launch_pass(h, a, h->d_z, 0, stream))) return rc;
+        if ((rc = allreduce_sums(h, stream))) return rc;
+        k_chain_leap<<<1, kThreads, 0, stream>>>(a, it, s, h->d_g);
+        CUDA_TRY(cudaGetLastError());
+        ++h->launches_last;
+      }
+    }
+  }
+  if (h->cfg.debug) {
+    ChainScalars sc;
+    CUDA_TRY(cudaMemcpyAsync(&sc, h->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (sc.nonfinite) return fail(EDHMC_ERR_NONFINITE, "log joint density had NaN or Inf values");
+  }
+  return 0;
+}
+
+int edhmc_set_trace(edhmc_t* h, double* trace_scalars, float* trace_pos) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  h->trace_scalars = trace_scalars;
+  h->trace_pos = trace_pos;
+  return 0;
+}
+
+int edhmc_read_state(edhmc_t* h, int64_t* n_accept_host, double* logp_host, void* stream_) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ChainScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(&sc, h->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (n_accept_host) *n_accept_host = sc.n_accept;
+  if (logp_host) *logp_host = sc.logp_cur;
+  return 0;
+}
+
+int edhmc_reset(edhmc_t* h, void* stream_) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemsetAsync(h->d_sc, 0, sizeof(ChainScalars), stream));
+  return 0;
+}
+
+int edhmc_seed(edhmc_t* h, uint64_t seed) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  h->seed = seed;
+  return 0;
+}
+
+int edhmc_comm_unique_id(void* id128_host) {
+  if (!id128_host) return fail(EDHMC_ERR_INVALID, "null argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  NCCL_TRY(g_nccl.GetUniqueId(reinterpret_cast<NcclUid*>(id128_host)));
+  return 0;
+}
+
+int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t rank) {
+  if (!h || !id128_host) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(EDHMC_ERR_INVALID, "bad nranks/rank");
+  int rc = nccl_load();
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  NcclUid id;
+  memcpy(&id, id128_host, sizeof(id));
+  NCCL_TRY(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+  h->nranks = nranks;
+  h->rank = rank;
+  return 0;
+}
+
+int edhmc_plan_info(edhmc_t* h, int64_t* out, int32_t cap) {
+  if (!h || !out) return fail(EDHMC_ERR_INVALID, "null argument");
+  const int64_t v[10] = {h->plan.grid,
+                         kWarpsPerCta,
+                         h->plan.S,
+                         h->plan.RT,
+                         h->plan.G,
+                         h->plan.V,
+                         static_cast<int64_t>(h->plan.persistent_ok ? h->plan.smem_persist : h->plan.smem_pass),
+                         h->plan_in_use,
+                         h->passes_last,
+                         h->launches_last};
+  int n = cap < 10 ? cap : 10;
+  for (int i = 0; i < n; ++i) out[i] = v[i];
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+"""GLMSampler — owns one libedhmc handle: the device-resident data, the chain state and the HMC loop.
+
+This is the object `ed.HMC` builds in `initialize()` in place of the reference's TensorFlow graph
+(edward/inferences/hmc.py:61-130). torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _C
+
+
+@dataclass
+class GLMSpec:
+  """theta = [w(D), b?] ~ Normal(prior_loc, prior_scale);  y ~ family(X w + b)."""
+  n_features: int
+  has_bias: bool = False
+  family: int = _C.BERNOULLI_LOGIT
+  prior_loc: Optional[np.ndarray] = None
+  prior_scale: Optional[np.ndarray] = None
+  lik_scale: float = 1.0
+
+  @property
+  def n_params(self) -> int:
+    return self.n_features + (1 if self.has_bias else 0)
+
+
+def _require_cuda(device) -> torch.device:
+  if not torch.cuda.is_available():
+    raise _C.EdhmcError(_C.ERR_CUDA, "no CUDA device: edward_b200 runs its HMC path only on the GPU "
+                        "(there is no CPU fallback)")
+  dev = torch.device(device if device is not None else "cuda")
+  if dev.type != "cuda":
+    raise _C.EdhmcError(_C.ERR_INVALID, "device must be a CUDA device, got %s" % dev)
+  if dev.index is None:
+    dev = torch.device("cuda", torch.cuda.current_device())
+  return dev
+
+
+def _stream_ptr(dev) -> int:
+  return torch.cuda.current_stream(dev).cuda_stream
+
+
+_Y_DTYPES = {torch.int32: _C.Y_I32, torch.float32: _C.Y_F32, torch.uint8: _C.Y_U8}
+
+
+class GLMSampler:
+  """One chain of HMC over a GLM. Row-sharded when `comm` (a torch.distributed group spec) is given."""
+
+  def __init__(self, spec: GLMSpec, X, y, device=None, plan: int = _C.PLAN_AUTO, debug: bool = False,
+               check_finite: bool = True, n_rows_global: Optional[int] = None):
+    self.lib = _C.lib()
+    self.dev = _require_cuda(device)
+    self.spec = spec
+    P = spec.n_params
+    loc = np.zeros(P, np.float32) if spec.prior_loc is None else np.ascontiguousarray(spec.prior_loc, np.float32).reshape(P)
+    scale = np.ones(P, np.float32) if spec.prior_scale is None else np.ascontiguousarray(spec.prior_scale, np.float32).reshape(P)
+    self.X = self._to_device(X, torch.float32)
+    if self.X.dim() != 2 or self.X.shape[1] != spec.n_features:
+      raise TypeError("X must have shape [N, %d], got %s" % (spec.n_features, tuple(self.X.shape)))
+    if self.X.stride(1) != 1 or self.X.data_ptr() % 16 != 0:
+      self.X = self.X.contiguous()
+    yt = y if isinstance(y, torch.Tensor) else torch.as_tensor(np.asarray(y))
+    if yt.dtype not in _Y_DTYPES:
+      # the reference casts observed data to the random variable's dtype (inference.py:88-95)
+      yt = yt.to(torch.int32 if spec.family != _C.NORMAL_IDENTITY else torch.float32)
+    self.y = yt.to(self.dev).contiguous()
+    if self.y.dim() != 1 or self.y.shape[0] != self.X.shape[0]:
+      raise TypeError("y must have shape [%d], got %s" % (self.X.shape[0], tuple(self.y.shape)))
+    self.n_rows = int(self.X.shape[0])
+    self.P = P
+
+    cfg = _C.Cfg()
+    cfg.n_rows = self.n_rows
+    cfg.n_rows_global = int(n_rows_global if n_rows_global is not None else self.n_rows)
+    cfg.n_features = spec.n_features
+    cfg.ldx = int(self.X.stride(0)) if self.n_rows > 1 else max(int(self.X.stride(0)), spec.n_features)
+    cfg.has_bias = 1 if spec.has_bias else 0
+    cfg.family = int(spec.family)
+    cfg.y_dtype = _Y_DTYPES[self.y.dtype]
+    cfg.lik_scale = float(spec.lik_scale)
+    cfg.prior_loc_host = loc.ctypes.data_as(C.POINTER(C.c_float))
+    cfg.prior_scale_host = scale.ctypes.data_as(C.POINTER(C.c_float))
+    cfg.device = self.dev.index
+    cfg.plan = int(plan)
+    cfg.debug = 1 if debug else 0
+    self._h = C.c_void_p()
+    _C.check(self.lib.edhmc_create(C.byref(self._h), C.byref(cfg)))
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_bind_data(self._h, self.X.data_ptr(), self.y.data_ptr(), 1 if check_finite else 0,
+                                        _stream_ptr(self.dev)))
+    self._trace = None
+    self.nranks = 1
+
+  def _to_device(self, a, dtype):
+    t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
+    return t.to(device=self.dev, dtype=dtype)
+
+  # ---- row shards (extension) -----------------------------------------------------------------
+  def init_comm(self, nranks: int, rank: int, group=None):
+    """Creates the NCCL communicator of this handle; the unique id travels over torch.distributed."""
+    import torch.distributed as dist
+    buf = (C.c_char * 128)()
+    if rank == 0:
+      _C.check(self.lib.edhmc_comm_unique_id(C.cast(buf, C.c_void_p)))
+    ids = [bytes(buf)]
+    dist.broadcast_object_list(ids, src=0, group=group)
+    idbuf = C.create_string_buffer(ids[0], 128)
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_comm_init(self._h, C.cast(idbuf, C.c_void_p), int(nranks), int(rank)))
+    self.nranks = int(nranks)
+
+  # ---- evaluation ------------------------------------------------------------------------------
+  def logp_grad(self, theta):
+    """log p(y, theta) (float64 scalar tensor) and its gradient (float32 [P]) — hmc.py:161-192,199."""
+    th = self._to_device(theta, torch.float32).contiguous().reshape(self.P)
+    logp = torch.empty(1, dtype=torch.float64, device=self.dev)
+    grad = torch.empty(self.P, dtype=torch.float32, device=self.dev)
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_logp_grad(self._h, th.data_ptr(), logp.data_ptr(), grad.data_ptr(), _stream_ptr(self.dev)))
+    return logp, grad
+
+  def run(self, params: torch.Tensor, t0: int, n_iter: int, step_size: float, n_steps: int,
+          r0: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None):
+    """n_iter transitions in place on `params` [T, >=P] (device, float32, row-major)."""
+    if params.device != self.dev or params.dtype != torch.float32:
+      raise TypeError("params must be a float32 tensor on %s" % self.dev)
+    if params.dim() == 1:
+      params = params.view(-1, 1)
+    if params.stride(1) != 1:
+      raise TypeError("params rows must be contiguous")
+    r0p = up = None
+    if r0 is not None:
+      r0 = self._to_device(r0, torch.float32).contiguous()
+      if r0.numel() < n_iter * self.P:
+        raise ValueError("r0 must hold n_iter*P momentum draws")
+      r0p = r0.data_ptr()
+    if u is not None:
+      u = self._to_device(u, torch.float32).contiguous()
+      if u.numel() < n_iter:
+        raise ValueError("u must hold n_iter uniforms")
+      up = u.data_ptr()
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_run(self._h, params.data_ptr(), int(params.stride(0)), int(params.shape[0]), int(t0),
+                                  int(n_iter), float(step_size), int(n_steps), r0p, up, _stream_ptr(self.dev)))
+
+  def set_trace(self, n_iter: int):
+    sc = torch.zeros(n_iter, 8, dtype=torch.float64, device=self.dev)
+    pos = torch.zeros(n_iter, self.P, dtype=torch.float32, device=self.dev)
+    self._trace = (sc, pos)
+    _C.check(self.lib.edhmc_set_trace(self._h, sc.data_ptr(), pos.data_ptr()))
+    return sc, pos
+
+  def clear_trace(self):
+    self._trace = None
+    _C.check(self.lib.edhmc_set_trace(self._h, None, None))
+
+  def read_state(self):
+    n = C.c_int64(0)
+    lp = C.c_double(0.0)
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_read_state(self._h, C.byref(n), C.byref(lp), _stream_ptr(self.dev)))
+    return int(n.value), float(lp.value)
+
+  def reset(self):
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_reset(self._h, _stream_ptr(self.dev)))
+
+  def seed(self, seed: int):
+    _C.check(self.lib.edhmc_seed(self._h, C.c_uint64(int(seed) & (2**64 - 1))))
+
+  def plan_info(self) -> dict:
+    out = (C.c_int64 * 10)()
+    n = _C.check(self.lib.edhmc_plan_info(self._h, out, 10))
+    keys = ["grid_ctas", "warps_per_cta", "ring_stages", "tile_rows", "lanes_per_row", "vec_width", "smem_bytes",
+            "plan_in_use", "passes_last_run", "launches_last_run"]
+    return {k: int(out[i]) for i, k in enumerate(keys[:n])}
+
+  def close(self):
+    if getattr(self, "_h", None) is not None and self._h.value:
+      self.lib.edhmc_destroy(self._h)
+      self._h = C.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass

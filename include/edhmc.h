@@ -1,0 +1,157 @@
+/*
+ * edhmc.h — C ABI of libedhmc.so: Edward's HMC hot path for GLM-style models on B200 (sm_100a).
+ *
+ * This is the drop-in boundary. The reference (blei-lab/edward 1.3.5) has no native code: its hot
+ * path is a TensorFlow graph built by edward/inferences/hmc.py and executed by tf.Session.run. The
+ * entry points below are what a ctypes binding on the reference side would call instead of
+ * `sess.run(self.train)`; each one cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - C linkage, plain pointers and sizes. No torch / C++ types.
+ *   - Every function returns 0 on success and a negative edhmc_status on failure;
+ *     edhmc_last_error() gives a thread-local, human-readable message for the last failure.
+ *   - Pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *   - The caller owns every buffer it passes; the library owns only the handle and its scratch.
+ *   - A handle is not thread-safe. The library starts no host threads. All device work is queued on
+ *     the caller-supplied stream (`void* stream` is a cudaStream_t; NULL = legacy default stream).
+ *   - Floating point is float32 (the reference's dtype on this path); reductions are carried in
+ *     float64 on the device.
+ *
+ * Model covered (anything else is rejected by the host front-end with NotImplementedError):
+ *   latent  theta = [w[0..D), b?]         with independent Normal(loc, scale) priors
+ *   eta_n   = sum_d X[n,d] * w[d] (+ b)
+ *   y_n     ~ family(eta_n)               Bernoulli-logit (north star), Normal-identity, Poisson-log
+ */
+#ifndef EDHMC_H_
+#define EDHMC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDHMC_VERSION_MAJOR 0
+#define EDHMC_VERSION_MINOR 1
+
+typedef enum edhmc_status {
+  EDHMC_OK = 0,
+  EDHMC_ERR_INVALID = -1,    /* bad argument / unsupported configuration (reference: TypeError/ValueError) */
+  EDHMC_ERR_CUDA = -2,       /* CUDA runtime error */
+  EDHMC_ERR_NONFINITE = -3,  /* NaN/Inf in X or y (reference: ed.dot raises InvalidArgumentError,
+                                edward/util/tensorflow.py:27-36) or in log-joint/gradient when debug */
+  EDHMC_ERR_RANGE = -4,      /* update past the last Empirical row (reference: tf.scatter_update
+                                out-of-range, edward/inferences/hmc.py:125) */
+  EDHMC_ERR_STATE = -5,      /* call sequence error (e.g. run before bind_data) */
+  EDHMC_ERR_COMM = -6,       /* NCCL failure */
+  EDHMC_ERR_NOMEM = -7
+} edhmc_status;
+
+/* Likelihood families: log p(y_n | eta_n). */
+typedef enum edhmc_family {
+  EDHMC_BERNOULLI_LOGIT = 0, /* Bernoulli(logits=eta).log_prob(y): models/random_variables.py:13-25 →
+                                TF bernoulli._log_prob → -sigmoid_cross_entropy_with_logits */
+  EDHMC_NORMAL_IDENTITY = 1, /* Normal(loc=eta, scale=s).log_prob(y)   (tests/inferences/hmc_test.py:14-91) */
+  EDHMC_POISSON_LOG = 2      /* Poisson(rate=exp(eta)).log_prob(y) */
+} edhmc_family;
+
+typedef enum edhmc_ydtype {
+  EDHMC_Y_I32 = 0, /* reference dtype of Bernoulli data (inference.py:88-95 casts to key.dtype=int32) */
+  EDHMC_Y_F32 = 1,
+  EDHMC_Y_U8 = 2
+} edhmc_ydtype;
+
+/* Execution plan selector (all are CUDA paths; there is no CPU path). */
+typedef enum edhmc_plan {
+  EDHMC_PLAN_AUTO = 0,
+  EDHMC_PLAN_PERSISTENT = 1, /* one cooperative launch runs every transition of edhmc_run */
+  EDHMC_PLAN_STEPWISE = 2    /* one launch per data pass (+ NCCL all-reduce when sharded) */
+} edhmc_plan;
+
+typedef struct edhmc_cfg {
+  int64_t n_rows;          /* rows of X / y held by THIS rank (its shard) */
+  int64_t n_rows_global;   /* rows over all ranks (== n_rows when nranks == 1) */
+  int32_t n_features;      /* D: columns of X */
+  int64_t ldx;             /* row stride of X in floats (>= D) */
+  int32_t has_bias;        /* 1: a scalar latent b is added to every linear predictor */
+  int32_t family;          /* edhmc_family */
+  int32_t y_dtype;         /* edhmc_ydtype */
+  float   lik_scale;       /* Normal-identity only: likelihood scale s (> 0) */
+  const float* prior_loc_host;   /* [P] P = D + has_bias; order [w..., b] */
+  const float* prior_scale_host; /* [P] > 0 */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t plan;            /* edhmc_plan */
+  int32_t debug;           /* 1: check log-joint/gradient for NaN/Inf after every run (inference.py:279-281) */
+  int32_t reserved[5];     /* must be zero */
+} edhmc_cfg;
+
+typedef struct edhmc_handle edhmc_t;
+
+/* Library version as major*1000+minor. */
+int edhmc_version(void);
+
+/* Thread-local message for the most recent failure on this thread ("" if none). */
+const char* edhmc_last_error(void);
+
+/* Builds the sampler state for one model. Replaces the graph construction done once by
+ * HMC.initialize → MonteCarlo.initialize → HMC.build_update (hmc.py:45-130, monte_carlo.py:95-109). */
+int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg);
+int edhmc_destroy(edhmc_t* h);
+
+/* Binds the observed data (borrowed, must stay valid while the handle uses it).
+ * X: [n_rows, ldx] float32 row-major, 16-byte aligned. y: [n_rows] of cfg.y_dtype.
+ * check_finite != 0 scans X and y once and fails with EDHMC_ERR_NONFINITE — this replaces the
+ * per-evaluation CheckNumerics of ed.dot (util/tensorflow.py:33-36). Synchronises the stream when
+ * check_finite != 0. */
+int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite, void* stream);
+
+/* log p(y, theta) and its gradient at theta, exactly what one `tf.gradients(log_joint(z), z)` of
+ * hmc.py:199/206 evaluates via HMC._log_joint (hmc.py:161-192).
+ * theta: [P] float32. logp: [1] float64 (device). grad: [P] float32 (device).
+ * With row shards the result is the all-reduced global value on every rank. */
+int edhmc_logp_grad(edhmc_t* h, const float* theta, double* logp, float* grad, void* stream);
+
+/* Runs n_iter HMC transitions t = t0 .. t0+n_iter-1 with no host round-trip (n_iter == 1 is one
+ * MonteCarlo.update, monte_carlo.py:111-150; n_iter == T is Inference.run's loop, inference.py:145-147).
+ * Transition t reads row max(t-1,0) of `params` and writes row t (hmc.py:81-85,121-126).
+ *   params    [T, ldp] float32, in place; first P entries of each row are theta = [w..., b]
+ *   step_size, n_steps: leapfrog step size and count (hmc.py:45)
+ *   r0        [n_iter, P] float32 momentum draws, or NULL → device Philox N(0,1)      (hmc.py:88-91)
+ *   u         [n_iter]    float32 accept uniforms in (0,1), or NULL → device Philox   (hmc.py:108)
+ * Accept rule: log(u) < K(r0) - K(rL) + logp(zL) - logp(z0), strict (hmc.py:100-109).
+ * Fails with EDHMC_ERR_RANGE if t0 + n_iter > T. */
+int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int64_t n_iter,
+              float step_size, int32_t n_steps, const float* r0, const float* u, void* stream);
+
+/* Optional per-transition trace for parity tests. Both may be NULL (default).
+ *   trace_scalars [n_iter, 8] float64: {logp_old, logp_new, K_old, K_new, ratio, log_u, accept, reserved}
+ *   trace_pos     [n_iter, P] float32: proposed position z_L of each transition. */
+int edhmc_set_trace(edhmc_t* h, double* trace_scalars, float* trace_pos);
+
+/* Counters owned by the handle: number of accepted proposals since the last reset
+ * (MonteCarlo.n_accept, monte_carlo.py:100) and the cached log-joint of the current state.
+ * Synchronises the stream. Any output pointer may be NULL. */
+int edhmc_read_state(edhmc_t* h, int64_t* n_accept_host, double* logp_host, void* stream);
+
+/* `sess.run(inference.reset)`: zero n_accept (monte_carlo.py:104) and drop the cached state. */
+int edhmc_reset(edhmc_t* h, void* stream);
+
+/* Seeds the device Philox4x32-10 streams used when r0 / u are NULL (ed.set_seed, util/graphs.py:59-73). */
+int edhmc_seed(edhmc_t* h, uint64_t seed);
+
+/* Row-sharded multi-GPU (extension; the reference is single-device). One handle per rank/GPU.
+ * edhmc_comm_unique_id fills a 128-byte ncclUniqueId on rank 0; the caller broadcasts it (e.g. with
+ * torch.distributed) and every rank calls edhmc_comm_init. Afterwards edhmc_logp_grad / edhmc_run
+ * all-reduce (sum, float64) the per-shard [grad, logp] once per data pass over NVLink. */
+int edhmc_comm_unique_id(void* id128_host);
+int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t rank);
+
+/* Introspection for benches/tests: fills up to `cap` int64 values:
+ * {grid_ctas, warps_per_cta, ring_stages, tile_rows, lanes_per_row, vec_width, smem_bytes,
+ *  plan_in_use, passes_last_run, launches_last_run}. Returns the number written. */
+int edhmc_plan_info(edhmc_t* h, int64_t* out_host, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDHMC_H_ */
