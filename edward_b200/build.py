@@ -1,22 +1,25 @@
-"""Builds edward_b200/lib/libedhmc.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds edward_b200/lib/libedhmc.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+The kernel template is instantiated in one translation unit per (lanes-per-row, vector-width) pair
+(csrc/inst_g*_v*.cu) so the units compile in parallel; objects land in csrc/_obj/.
+"""
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libedhmc.so")
-SOURCES = ["edhmc.cu"]
-HEADERS = ["ptx.cuh", "common.cuh", "stream.cuh", "chain.cuh", os.path.join("..", "..", "include", "edhmc.h")]
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc() -> str:
@@ -26,29 +29,53 @@ def _nvcc() -> str:
   raise RuntimeError("nvcc not found; libedhmc.so cannot be built")
 
 
-def is_stale() -> bool:
-  if not os.path.exists(LIB):
+def sources():
+  return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _deps():
+  return glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "edhmc.h")]
+
+
+def _stale(target, srcs) -> bool:
+  if not os.path.exists(target):
     return True
-  t = os.path.getmtime(LIB)
-  for f in SOURCES + HEADERS:
-    p = os.path.join(CSRC, f)
-    if os.path.exists(p) and os.path.getmtime(p) > t:
-      return True
-  return False
+  t = os.path.getmtime(target)
+  return any(os.path.exists(s) and os.path.getmtime(s) > t for s in srcs)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def is_stale() -> bool:
+  return _stale(LIB, sources() + _deps())
+
+
+def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -> str:
   if not force and not is_stale():
     return LIB
+  nvcc = _nvcc()
+  os.makedirs(OBJ, exist_ok=True)
   os.makedirs(LIBDIR, exist_ok=True)
-  cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-      ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+  deps = _deps()
+
+  def compile_one(src):
+    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    if not force and not _stale(obj, [src] + deps):
+      return obj, ""
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+      raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
+    return obj, res.stderr
+
+  with ThreadPoolExecutor(max_workers=jobs or min(10, os.cpu_count() or 4)) as ex:
+    results = list(ex.map(compile_one, sources()))
+  if verbose:
+    for _, log in results:
+      sys.stderr.write(log)
+  objs = [o for o, _ in results]
+  cmd = [nvcc] + ARCH_FLAGS + ["-shared", "-o", LIB] + objs + ["-ldl"]
   res = subprocess.run(cmd, capture_output=True, text=True)
   if res.returncode != 0:
-    sys.stderr.write(res.stdout + res.stderr)
-    raise RuntimeError("nvcc failed building libedhmc.so")
-  if verbose:
-    sys.stderr.write(res.stderr)
+    raise RuntimeError("link failed:\n%s%s" % (res.stdout, res.stderr))
   return LIB
 
 

@@ -1,0 +1,155 @@
+// chain_small.cuh — single-CTA kernels of the stepwise plan and bind-time utilities. Included by edhmc.cu only.
+#pragma once
+#include "chain.cuh"
+
+namespace edhmc {
+
+// ---- single-CTA chain kernels (<<<1, kThreads>>>) of the stepwise plan, on the global chain state ----
+
+__device__ __forceinline__ double finish_gradient(const KArgs& a, const float* pos, float* gout, double* red) {
+  double pl = 0.0;
+  for (int c = threadIdx.x; c < a.P; c += kThreads) {
+    const float loc = a.prior_loc[c], sc = a.prior_scale[c];
+    gout[c] = static_cast<float>(a.sums[c] + prior_grad(pos[c], loc, sc));
+    pl += prior_quad(pos[c], loc, sc);
+  }
+  return (block_sum_f64(pl, red) - a.prior_const) + a.sums[a.P];
+}
+
+// Decides whether the cached (gcur, logp_cur) still describe params[max(t0-1,0)].
+__global__ void __launch_bounds__(kThreads, 1) k_chain_check(const KArgs a) {
+  const long long t_prev = a.t0 > 0 ? a.t0 - 1 : 0;
+  bool mismatch = false;
+  for (int c = threadIdx.x; c < a.P; c += kThreads) {
+    const float v = a.params[t_prev * a.ldp + c];
+    if (__float_as_uint(v) != __float_as_uint(a.zcur[c])) mismatch = true;
+  }
+  const int need = __syncthreads_or((mismatch || !a.sc->valid) ? 1 : 0);
+  if (need)
+    for (int c = threadIdx.x; c < a.P; c += kThreads) a.zcur[c] = a.params[t_prev * a.ldp + c];
+  if (threadIdx.x == 0) a.sc->need_init = need ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_chain_init_finish(const KArgs a) {
+  __shared__ double red[64];
+  if (!a.sc->need_init) return;
+  const double lp = finish_gradient(a, a.zcur, a.gcur, red);
+  if (threadIdx.x == 0) {
+    a.sc->logp_cur = lp;
+    a.sc->valid = 1;
+    a.sc->need_init = 0;
+  }
+}
+
+__device__ __forceinline__ void chain_finish(const KArgs& a, long long it, float* gnew, double logp_new, double* red) {
+  const long long t = a.t0 + it;
+  double ks = 0.0;
+  for (int c = threadIdx.x; c < a.P; c += kThreads) ks += static_cast<double>(__fmul_rn(a.r[c], a.r[c]));
+  const double k_new = 0.5 * block_sum_f64(ks, red);
+  const double logp_cur = a.sc->logp_cur;
+  const double k_old = a.sc->k_old;
+  const AcceptResult ar = mh_accept(k_old, k_new, logp_new, logp_cur, a.sc->log_u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    write_trace(a, it, logp_cur, logp_new, k_old, k_new, ar);
+    if (!isfinite(logp_new)) a.sc->nonfinite = 1;
+    if (ar.accept) {
+      a.sc->logp_cur = logp_new;
+      a.sc->n_accept += 1;
+    }
+  }
+  for (int c = threadIdx.x; c < a.P; c += kThreads) {
+    if (a.trace_pos) a.trace_pos[it * a.P + c] = a.z[c];
+    if (ar.accept) {
+      a.zcur[c] = a.z[c];
+      a.gcur[c] = gnew[c];
+    }
+    a.params[t * a.ldp + c] = ar.accept ? a.z[c] : a.zcur[c];
+  }
+}
+
+// Start of transition `it`: draw momentum and uniform, kinetic energy, first half kick + drift.
+__global__ void __launch_bounds__(kThreads, 1) k_chain_begin(const KArgs a, long long it, float* gwork) {
+  __shared__ double red[64];
+  const long long t = a.t0 + it;
+  double ks = 0.0;
+  for (int c = threadIdx.x; c < a.P; c += kThreads) {
+    const float rv = a.r0 ? a.r0[it * a.P + c] : philox_normal(a.seed, t, c);
+    ks += static_cast<double>(__fmul_rn(rv, rv));
+    float zz = a.zcur[c];
+    float rr = rv;
+    if (a.L > 0) {
+      rr = kick(rv, a.half_eps, a.gcur[c]);
+      zz = drift(zz, a.eps, rr);
+    }
+    a.r[c] = rr;
+    a.z[c] = zz;
+    gwork[c] = a.gcur[c];
+  }
+  const double k_old = 0.5 * block_sum_f64(ks, red);
+  if (threadIdx.x == 0) {
+    const float u = a.u ? a.u[it] : philox_uniform(a.seed, t);
+    a.sc->k_old = k_old;
+    a.sc->log_u = static_cast<double>(logf(u));
+  }
+  if (a.L == 0) {
+    __syncthreads();
+    chain_finish(a, it, gwork, a.sc->logp_cur, red);
+  }
+}
+
+// After the pass (and all-reduce) of leapfrog step s: second half kick; then either the next step's
+// first half kick + drift, or the Metropolis–Hastings accept and the Empirical write.
+__global__ void __launch_bounds__(kThreads, 1) k_chain_leap(const KArgs a, long long it, int s, float* gwork) {
+  __shared__ double red[64];
+  const double logp_new = finish_gradient(a, a.z, gwork, red);
+  const bool last = (s == a.L - 1);
+  for (int c = threadIdx.x; c < a.P; c += kThreads) {
+    float rr = kick(a.r[c], a.half_eps, gwork[c]);
+    if (!last) {
+      rr = kick(rr, a.half_eps, gwork[c]);
+      a.z[c] = drift(a.z[c], a.eps, rr);
+    }
+    a.r[c] = rr;
+  }
+  if (last) {
+    __syncthreads();
+    chain_finish(a, it, gwork, logp_new, red);
+  }
+}
+
+// edhmc_logp_grad epilogue: prior + all-reduced sums → caller's buffers.
+__global__ void __launch_bounds__(kThreads, 1) k_logp_grad_finish(const KArgs a, const float* theta, double* logp_out,
+                                                                 float* grad_out) {
+  __shared__ double red[64];
+  const double lp = finish_gradient(a, theta, grad_out, red);
+  if (threadIdx.x == 0) *logp_out = lp;
+}
+
+// ---- bind-time scan: counts NaN/Inf in X (D valid columns per row) and y ----
+__global__ void k_check_finite(const float* X, long long n_rows, long long ldx, int D, const void* y, int y_dtype,
+                               unsigned long long* bad) {
+  unsigned long long local = 0;
+  const long long total = n_rows * D;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / D;
+    const int col = static_cast<int>(i - row * D);
+    if (!isfinite(X[row * ldx + col])) ++local;
+  }
+  if (y_dtype == 1) {
+    const float* yf = reinterpret_cast<const float*>(y);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_rows;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+      if (!isfinite(yf[i])) ++local;
+  }
+  if (local) atomicAdd(bad, local);
+}
+
+__global__ void k_u8_to_i32(const unsigned char* src, int* dst, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+
+}  // namespace edhmc

@@ -51,7 +51,13 @@ struct KArgs {
   int wpad;          // padded length of theta in shared memory (G*KMAX*V)
   int zigzag;        // 1: odd passes walk a warp's tiles backwards (L2 reuse)
   int l2_hint;       // 0 none, 1 evict_last on all X tiles
-  int n_shard_ctas;  // CTAs that share the rows (== gridDim.x)
+  int ldx_i;         // ldx as int
+  int tl;            // floats per full tile = RT*ldx
+  int tm;            // tl & 3: per-tile drift of the 16-byte alignment (non-zero only if ldx % 4 != 0)
+  // ---- launch mode ----
+  int mode;               // 0: run n_iter transitions (cooperative launch); 1: one data pass at theta_in
+  int gate;               // mode 1: return immediately unless sc->need_init
+  const float* theta_in;  // mode 1: [P]
   // ---- scratch ----
   double* partials;            // [2][grid][P+1]
   unsigned long long* bar;     // grid barrier counter (persistent plan)
@@ -84,12 +90,17 @@ struct KArgs {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void row_terms(int family, float eta, float yv, float lik_scale, float& lp, float& r) {
   if (family == 0) {
-    // -(where(l>=0,l,0) - l*y + log1p(exp(-|l|)));  gradient y - sigmoid(l), piecewise as autodiff does
+    // -(where(l>=0,l,0) - l*y + log1p(exp(-|l|)));  gradient y - sigmoid(l), piecewise as autodiff does.
+    // log1p(e) is evaluated as log(u) - ((u-1)-e)/u with u = 1+e (exact-to-rounding compensation), and
+    // e/(1+e) with one reciprocal: u is in (1,2], so no range checks are needed.
     const bool pos = eta >= 0.0f;
-    const float e = expf(pos ? -eta : eta);
+    const float e = expf(-fabsf(eta));
+    const float u = __fadd_rn(1.0f, e);
+    const float inv = __fdividef(1.0f, u);
+    const float l1p = __fsub_rn(logf(u), __fmul_rn(__fsub_rn(__fsub_rn(u, 1.0f), e), inv));
     const float relu = pos ? eta : 0.0f;
-    lp = -__fadd_rn(__fsub_rn(relu, __fmul_rn(eta, yv)), log1pf(e));
-    const float q = __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(1.0f, e)), e);
+    lp = -__fadd_rn(__fsub_rn(relu, __fmul_rn(eta, yv)), l1p);
+    const float q = __fmul_rn(e, inv);
     r = pos ? __fadd_rn(__fsub_rn(yv, 1.0f), q) : __fsub_rn(yv, q);
   } else if (family == 1) {
     const float zz = __fdiv_rn(__fsub_rn(yv, eta), lik_scale);

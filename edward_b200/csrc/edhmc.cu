@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "../../include/edhmc.h"
-#include "chain.cuh"
+#include "chain_small.cuh"
 
 using namespace edhmc;
 
@@ -96,13 +96,23 @@ static const int kNcclFloat64 = 8, kNcclSum = 0;
 // plan
 // ------------------------------------------------------------------------------------------------
 struct Plan {
-  int G = 0, V = 0, KMAX = 0, Kact = 0, J = 0, RT = 0, S = 0, stage_floats = 0, y_off = 0, wpad = 0;
+  int G = 0, V = 0, K = 0, Kact = 0, J = 0, RT = 0, S = 0, stage_floats = 0, y_off = 0, wpad = 0, tl = 0, tm = 0;
   int grid = 0;
-  size_t smem_persist = 0, smem_pass = 0;
-  const void* fn_persist = nullptr;
-  const void* fn_pass = nullptr;
-  bool persistent_ok = false;
+  size_t smem = 0;
+  const void* fn = nullptr;
 };
+
+namespace edhmc {
+const void* lookup_g1_v1(int K);
+const void* lookup_g1_v2(int K);
+const void* lookup_g1_v4(int K);
+const void* lookup_g4_v1(int K);
+const void* lookup_g4_v2(int K);
+const void* lookup_g4_v4(int K);
+const void* lookup_g32_v1(int K);
+const void* lookup_g32_v2(int K);
+const void* lookup_g32_v4(int K);
+}  // namespace edhmc
 
 struct edhmc_handle {
   edhmc_cfg cfg;
@@ -144,47 +154,69 @@ struct edhmc_handle {
   int plan_in_use = 0;
 };
 
-template <int G, int V>
-static void plan_fns(Plan& p) {
-  constexpr int KMAX = 64 / V;
-  p.fn_persist = reinterpret_cast<const void*>(&k_hmc_persistent<G, V, KMAX>);
-  p.fn_pass = reinterpret_cast<const void*>(&k_pass<G, V, KMAX>);
+static const void* lookup_kernel(int G, int V, int K) {
+  switch (G * 10 + V) {
+    case 11: return lookup_g1_v1(K);
+    case 12: return lookup_g1_v2(K);
+    case 14: return lookup_g1_v4(K);
+    case 41: return lookup_g4_v1(K);
+    case 42: return lookup_g4_v2(K);
+    case 44: return lookup_g4_v4(K);
+    case 321: return lookup_g32_v1(K);
+    case 322: return lookup_g32_v2(K);
+    case 324: return lookup_g32_v4(K);
+  }
+  return nullptr;
 }
 
 static long long gcdll(long long a, long long b) { return b ? gcdll(b, a % b) : a; }
 
+// Chooses the streaming geometry: V = widest vector the row stride allows, G = fewest lanes per row
+// whose per-lane chunk count fits 64 floats, K = smallest compiled tier >= chunks per lane, tiles of
+// about 7 KB, and as many ring stages as shared memory holds next to the chain state.
 static int make_plan(edhmc_handle* h) {
   const edhmc_cfg& c = h->cfg;
   Plan p;
   const int D = c.n_features;
   const long long ldx = c.ldx;
   p.V = (ldx % 4 == 0) ? 4 : (ldx % 2 == 0 ? 2 : 1);
-  p.KMAX = 64 / p.V;
+  const int kmax = 64 / p.V;
   const int chunks = (D + p.V - 1) / p.V;
   const int gs[3] = {1, 4, 32};
   p.G = 0;
   for (int g : gs)
-    if ((chunks + g - 1) / g <= p.KMAX) {
+    if ((chunks + g - 1) / g <= kmax) {
       p.G = g;
       break;
     }
-  if (!p.G)
-    return fail(EDHMC_ERR_INVALID, "n_features=%d exceeds the supported maximum of %d", D, kMaxFeatures);
+  if (!p.G) return fail(EDHMC_ERR_INVALID, "n_features=%d exceeds the supported maximum of %d", D, kMaxFeatures);
   p.Kact = (chunks + p.G - 1) / p.G;
-  p.wpad = p.G * p.KMAX * p.V;
+  static const int tiers4[] = {1, 2, 4, 8, 12, 16}, tiers2[] = {1, 2, 4, 8, 16, 24, 27, 32}, tiers1[] = {1, 2, 4, 8, 16, 32, 64};
+  const int* tiers = p.V == 4 ? tiers4 : (p.V == 2 ? tiers2 : tiers1);
+  const int ntier = p.V == 4 ? 6 : (p.V == 2 ? 8 : 7);
+  p.K = 0;
+  for (int i = 0; i < ntier; ++i)
+    if (tiers[i] >= p.Kact) {
+      p.K = tiers[i];
+      break;
+    }
+  if (!p.K) return fail(EDHMC_ERR_INVALID, "internal: no tier for %d chunks", p.Kact);
+  p.fn = lookup_kernel(p.G, p.V, p.K);
+  if (!p.fn) return fail(EDHMC_ERR_INVALID, "internal: no kernel for G=%d V=%d K=%d", p.G, p.V, p.K);
+  p.wpad = p.G * p.K * p.V;
   const int RPS = 32 / p.G;
   const long long row_bytes = ldx * 4;
   long long J = 7168 / (RPS * row_bytes);
   if (J < 1) J = 1;
   if (J > 8) J = 8;
-  // tiles must start on 16-byte boundaries: RT*ldx*4 % 16 == 0
-  const long long AU = 4 / gcdll(ldx, 4);
-  const long long jstep = AU / gcdll(RPS, AU);
-  J = (J + jstep - 1) / jstep * jstep;
   p.J = static_cast<int>(J);
   p.RT = RPS * p.J;
-  long long x_floats = static_cast<long long>(p.RT - 1) * ldx + static_cast<long long>(p.Kact) * p.G * p.V;
-  if (x_floats < static_cast<long long>(p.RT) * ldx) x_floats = static_cast<long long>(p.RT) * ldx;
+  p.tl = static_cast<int>(p.RT * ldx);
+  p.tm = p.tl & 3;
+  // x region: up to 3 floats of alignment skew + the tile + the over-read of the padded chunks / 16-byte round-up
+  long long x_floats = 3 + static_cast<long long>(p.RT - 1) * ldx + p.wpad;
+  const long long copy_floats = 3 + static_cast<long long>(p.RT) * ldx + 4;
+  if (x_floats < copy_floats) x_floats = copy_floats;
   x_floats = (x_floats + 3) / 4 * 4;
   p.y_off = static_cast<int>(x_floats);
   long long sf = x_floats + p.RT;
@@ -195,57 +227,21 @@ static int make_plan(edhmc_handle* h) {
   size_t offs[7];
   int S = kMaxStages;
   for (; S >= 1; --S)
-    if (smem_layout_bytes(S, p.stage_floats, h->P, p.wpad, true, offs) <= budget) break;
-  if (S < 2) {
-    // state arrays do not fit next to a 2-deep ring: persistent plan unavailable, try stepwise sizing
-    int S2 = kMaxStages;
-    for (; S2 >= 1; --S2)
-      if (smem_layout_bytes(S2, p.stage_floats, h->P, p.wpad, false, offs) <= budget) break;
-    if (S2 < 1) return fail(EDHMC_ERR_INVALID, "row of %lld bytes does not fit the shared-memory ring", row_bytes);
-    p.S = S2;
-    p.persistent_ok = false;
-  } else {
-    p.S = S;
-    p.persistent_ok = true;
-  }
-  p.smem_persist = smem_layout_bytes(p.S, p.stage_floats, h->P, p.wpad, true, offs);
-  p.smem_pass = smem_layout_bytes(p.S, p.stage_floats, h->P, p.wpad, false, offs);
-
-  switch (p.G * 10 + p.V) {
-    case 11: plan_fns<1, 1>(p); break;
-    case 12: plan_fns<1, 2>(p); break;
-    case 14: plan_fns<1, 4>(p); break;
-    case 41: plan_fns<4, 1>(p); break;
-    case 42: plan_fns<4, 2>(p); break;
-    case 44: plan_fns<4, 4>(p); break;
-    case 321: plan_fns<32, 1>(p); break;
-    case 322: plan_fns<32, 2>(p); break;
-    case 324: plan_fns<32, 4>(p); break;
-    default: return fail(EDHMC_ERR_INVALID, "internal: no kernel for G=%d V=%d", p.G, p.V);
-  }
-  if (p.persistent_ok) {
-    cudaError_t e = cudaFuncSetAttribute(p.fn_persist, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(p.smem_persist));
-    if (e != cudaSuccess) return fail(EDHMC_ERR_CUDA, "cudaFuncSetAttribute(persist, %zu): %s", p.smem_persist, cudaGetErrorString(e));
-  }
-  {
-    cudaError_t e = cudaFuncSetAttribute(p.fn_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(p.smem_pass));
-    if (e != cudaSuccess) return fail(EDHMC_ERR_CUDA, "cudaFuncSetAttribute(pass, %zu): %s", p.smem_pass, cudaGetErrorString(e));
-  }
+    if (smem_layout_bytes(S, p.stage_floats, h->P, p.wpad, offs) <= budget) break;
+  if (S < 2) return fail(EDHMC_ERR_INVALID, "row of %lld bytes does not fit the shared-memory ring", row_bytes);
+  p.S = S;
+  p.smem = smem_layout_bytes(p.S, p.stage_floats, h->P, p.wpad, offs);
+  cudaError_t e = cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem));
+  if (e != cudaSuccess) return fail(EDHMC_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", p.smem, cudaGetErrorString(e));
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p.fn, kThreads, p.smem);
+  if (e != cudaSuccess) return fail(EDHMC_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+  if (per_sm < 1) return fail(EDHMC_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", p.smem);
   // grid: one CTA per SM, fewer when there are not enough rows to give every warp two tiles
   long long want = (c.n_rows + static_cast<long long>(kWarpsPerCta) * 2 * p.RT - 1) /
                    (static_cast<long long>(kWarpsPerCta) * 2 * p.RT);
   if (want < 1) want = 1;
-  int per_sm = 1;
-  if (p.persistent_ok) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p.fn_persist, kThreads, p.smem_persist);
-    if (e != cudaSuccess) return fail(EDHMC_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
-    if (per_sm < 1) return fail(EDHMC_ERR_CUDA, "persistent kernel does not fit on an SM (smem %zu)", p.smem_persist);
-    per_sm = 1;  // the ring is sized for one CTA per SM
-  }
-  const long long cap = static_cast<long long>(h->num_sms) * per_sm;
-  p.grid = static_cast<int>(want < cap ? want : cap);
+  p.grid = static_cast<int>(want < h->num_sms ? want : h->num_sms);
   h->plan = p;
   return 0;
 }
@@ -276,7 +272,9 @@ static void fill_args(edhmc_handle* h, KArgs& a) {
   a.wpad = p.wpad;
   a.zigzag = h->zigzag;
   a.l2_hint = h->l2_hint;
-  a.n_shard_ctas = p.grid;
+  a.ldx_i = static_cast<int>(c.ldx);
+  a.tl = p.tl;
+  a.tm = p.tm;
   a.partials = h->d_partials;
   a.bar = h->d_bar;
   a.ticket = h->d_ticket;
@@ -448,10 +446,11 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
 
 static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int gate, cudaStream_t stream) {
   KArgs aa = a;
-  const float* th = theta;
-  int gt = gate;
-  void* params[] = {&aa, &th, &gt};
-  CUDA_TRY(cudaLaunchKernel(h->plan.fn_pass, dim3(h->plan.grid), dim3(kThreads), params, h->plan.smem_pass, stream));
+  aa.mode = 1;
+  aa.gate = gate;
+  aa.theta_in = theta;
+  void* params[] = {&aa};
+  CUDA_TRY(cudaLaunchKernel(h->plan.fn, dim3(h->plan.grid), dim3(kThreads), params, h->plan.smem, stream));
   ++h->launches_last;
   return 0;
 }
@@ -508,16 +507,17 @@ int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int
   h->launches_last = 0;
   h->passes_last = n_iter * n_steps;
 
-  bool persistent = h->plan.persistent_ok && h->nranks == 1;
+  bool persistent = h->nranks == 1;
   if (h->cfg.plan == EDHMC_PLAN_STEPWISE) persistent = false;
   if (h->cfg.plan == EDHMC_PLAN_PERSISTENT && !persistent)
-    return fail(EDHMC_ERR_INVALID, "persistent plan unavailable (row shards or shared memory)");
+    return fail(EDHMC_ERR_INVALID, "persistent plan unavailable with row shards");
   h->plan_in_use = persistent ? EDHMC_PLAN_PERSISTENT : EDHMC_PLAN_STEPWISE;
 
   if (persistent) {
     CUDA_TRY(cudaMemsetAsync(h->d_bar, 0, sizeof(unsigned long long), stream));
     void* kp[] = {&a};
-    CUDA_TRY(cudaLaunchCooperativeKernel(h->plan.fn_persist, dim3(h->plan.grid), dim3(kThreads), kp, h->plan.smem_persist, stream));
+    a.mode = 0;
+    CUDA_TRY(cudaLaunchCooperativeKernel(h->plan.fn, dim3(h->plan.grid), dim3(kThreads), kp, h->plan.smem, stream));
     ++h->launches_last;
   } else {
     int rc;
@@ -613,7 +613,7 @@ int edhmc_plan_info(edhmc_t* h, int64_t* out, int32_t cap) {
                          h->plan.RT,
                          h->plan.G,
                          h->plan.V,
-                         static_cast<int64_t>(h->plan.persistent_ok ? h->plan.smem_persist : h->plan.smem_pass),
+                         static_cast<int64_t>(h->plan.smem),
                          h->plan_in_use,
                          h->passes_last,
                          h->launches_last};

@@ -1,0 +1,16 @@
+// Instantiates k_hmc<G=32, V=4, K> for every K tier (one translation unit per (G,V) so they build in parallel).
+#include "chain.cuh"
+
+namespace edhmc {
+const void* lookup_g32_v4(int K) {
+  switch (K) {
+    case 1: return reinterpret_cast<const void*>(&k_hmc<32, 4, 1>);
+    case 2: return reinterpret_cast<const void*>(&k_hmc<32, 4, 2>);
+    case 4: return reinterpret_cast<const void*>(&k_hmc<32, 4, 4>);
+    case 8: return reinterpret_cast<const void*>(&k_hmc<32, 4, 8>);
+    case 12: return reinterpret_cast<const void*>(&k_hmc<32, 4, 12>);
+    case 16: return reinterpret_cast<const void*>(&k_hmc<32, 4, 16>);
+    default: return nullptr;
+  }
+}
+}  // namespace edhmc

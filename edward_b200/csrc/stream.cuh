@@ -13,27 +13,40 @@
 // while the grid synchronises on the current pass's reduction.
 //
 // Work decomposition inside a warp: a row is handled by G lanes (G = 1, 4 or 32); lane `lg` of the
-// group owns vector chunks k*G+lg (k < Kact) of V floats each, i.e. 128-/64-/32-bit shared loads.
-// theta sits zero-padded in shared memory, so padded columns contribute 0 to the dot product.
+// group owns vector chunks k*G+lg (k < K, K a compile-time tier) of V floats each, i.e. 128-/64-/32-bit
+// shared loads, and the arithmetic is packed FFMA2 (two fp32 FMAs per instruction) when V >= 2.
+// theta is zero-padded to G*K*V entries, so padded columns contribute 0 to the dot product and their
+// gradient accumulators are simply never written out.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace edhmc {
 
-struct WarpRows {
-  long long begin, end;  // rows [begin, end) of this warp
-  int nt;                // tiles per pass
+// Per-warp description of its rows, in registers.
+struct WarpTiles {
+  const float* x0;  // first float of the warp's first row
+  const char* y0;   // first y byte of the warp's first row
+  int nt;           // tiles per pass
+  int rows_last;    // rows in tile nt-1
+  int tail;         // 1: tile nt-1 ends at the last row of X (must not read past its D-th float)
 };
 
-__device__ __forceinline__ WarpRows warp_rows(const KArgs& a, int gw, int total_w) {
-  const long long units = (a.n_rows + 3) >> 2;  // 4-row units keep every tile start 16-byte aligned
+__device__ __forceinline__ WarpTiles warp_tiles(const KArgs& a, int gw, int total_w) {
+  const long long units = (a.n_rows + 3) >> 2;  // 4-row units keep every warp's first row 16-byte aligned
   const long long u0 = units * gw / total_w, u1 = units * (gw + 1) / total_w;
-  WarpRows w;
-  w.begin = u0 * 4;
-  w.end = u1 * 4 < a.n_rows ? u1 * 4 : a.n_rows;
-  if (w.end < w.begin) w.end = w.begin;
-  w.nt = static_cast<int>((w.end - w.begin + a.RT - 1) / a.RT);
+  long long begin = u0 * 4;
+  long long end = u1 * 4 < a.n_rows ? u1 * 4 : a.n_rows;
+  if (end < begin) end = begin;
+  WarpTiles w;
+  w.x0 = a.X + begin * a.ldx;
+  w.y0 = reinterpret_cast<const char*>(a.y) + begin * 4;
+  const long long n = end - begin;
+  w.nt = static_cast<int>((n + a.RT - 1) / a.RT);
+  w.rows_last = w.nt ? static_cast<int>(n - static_cast<long long>(w.nt - 1) * a.RT) : 0;
+  w.tail = (n > 0 && end == a.n_rows) ? 1 : 0;
   return w;
 }
 
@@ -49,49 +62,6 @@ struct Ring {
   int ipass, ik, istage;
 };
 
-__device__ __forceinline__ void tile_geometry(const KArgs& a, const WarpRows& wr, int pass, int kt, long long& row0,
-                                              int& rows) {
-  const int kk = (a.zigzag && (pass & 1)) ? (wr.nt - 1 - kt) : kt;
-  row0 = wr.begin + static_cast<long long>(kk) * a.RT;
-  const long long left = wr.end - row0;
-  rows = left < a.RT ? static_cast<int>(left) : a.RT;
-}
-
-// Issues the next tile of this warp's sequence into stage `istage`. Called by ALL lanes of the warp
-// (converged): every lane copies its share of the y slice, lane 0 launches the bulk copy of X.
-__device__ __forceinline__ void ring_issue(const KArgs& a, const WarpRows& wr, Ring& ring, int lane, uint64_t policy) {
-  long long row0;
-  int rows;
-  tile_geometry(a, wr, ring.ipass, ring.ik, row0, rows);
-  float* sb = ring.base + static_cast<size_t>(ring.istage) * a.stage_floats;
-  uint64_t* bar = ring.bars + ring.istage;
-  const char* ysrc = reinterpret_cast<const char*>(a.y) + row0 * 4;
-  for (int e = lane; e < rows; e += 32) cp_async4(sb + a.y_off + e, ysrc + static_cast<size_t>(e) * 4);
-  cp_async_mbar_arrive_noinc(bar);
-  if (lane == 0) {
-    const float* src = a.X + row0 * a.ldx;
-    // never read past the last valid float of X (the last row has only D valid floats)
-    const long long nfl = (row0 + rows == a.n_rows) ? static_cast<long long>(rows - 1) * a.ldx + a.D
-                                                    : static_cast<long long>(rows) * a.ldx;
-    const uint32_t b16 = static_cast<uint32_t>((nfl * 4) & ~15LL);
-    for (long long i = b16 >> 2; i < nfl; ++i) sb[i] = __ldg(src + i);
-    fence_proxy_async_smem();
-    mbar_arrive_expect_tx(bar, b16);
-    if (b16) {
-      if (a.l2_hint)
-        bulk_g2s_hint(sb, src, b16, bar, policy);
-      else
-        bulk_g2s(sb, src, b16, bar);
-    }
-  }
-  ++ring.qi;
-  if (++ring.ik == wr.nt) {
-    ring.ik = 0;
-    ++ring.ipass;
-  }
-  if (++ring.istage == a.S) ring.istage = 0;
-}
-
 __device__ __forceinline__ void ring_init(Ring& ring, float* base, uint64_t* bars) {
   ring.base = base;
   ring.bars = bars;
@@ -105,87 +75,186 @@ __device__ __forceinline__ void ring_init(Ring& ring, float* base, uint64_t* bar
   ring.istage = 0;
 }
 
-// Fills the ring at the start of a launch (all lanes).
-__device__ __forceinline__ void ring_prologue(const KArgs& a, const WarpRows& wr, Ring& ring, long long n_passes, int lane,
-                                              uint64_t policy) {
-  ring.q_total = n_passes * wr.nt;
-  for (int s = 0; s < a.S && ring.qi < ring.q_total; ++s) ring_issue(a, wr, ring, lane, policy);
+// Issues the next tile of this warp's sequence into stage `istage`. Called by ALL lanes of the warp
+// (converged): every lane copies its share of the y slice, lane 0 launches the bulk copy of X.
+// A tile whose first float is not 16-byte aligned (possible only when ldx % 4 != 0) is copied from the
+// aligned address below it; the consumer skips the same `m` leading floats.
+__device__ __forceinline__ void ring_issue(const KArgs& a, const WarpTiles& wt, Ring& ring, int lane, uint64_t policy) {
+  const int kk = (a.zigzag && (ring.ipass & 1)) ? (wt.nt - 1 - ring.ik) : ring.ik;
+  const bool last = (kk == wt.nt - 1);
+  const int rows = last ? wt.rows_last : a.RT;
+  float* sb = ring.base + ring.istage * a.stage_floats;
+  uint64_t* bar = ring.bars + ring.istage;
+  const char* ysrc = wt.y0 + static_cast<long long>(kk) * (a.RT * 4);
+  for (int e = lane; e < rows; e += 32) cp_async4(sb + a.y_off + e, ysrc + e * 4);
+  cp_async_mbar_arrive_noinc(bar);
+  if (lane == 0) {
+    const int m = (kk * a.tm) & 3;
+    const float* src = wt.x0 + static_cast<long long>(kk) * a.tl - m;
+    uint32_t bytes;
+    if (last && wt.tail) {
+      // never read past the last valid float of X: bulk-copy the 16-byte multiple, finish with scalar copies
+      const int nfl = m + (rows - 1) * a.ldx_i + a.D;
+      bytes = static_cast<uint32_t>(nfl * 4) & ~15u;
+      for (int i = bytes >> 2; i < nfl; ++i) sb[i] = __ldg(src + i);
+    } else {
+      bytes = (static_cast<uint32_t>((m + rows * a.ldx_i) * 4) + 15u) & ~15u;
+    }
+    fence_proxy_async_smem();
+    mbar_arrive_expect_tx(bar, bytes);
+    if (bytes) {
+      if (a.l2_hint)
+        bulk_g2s_hint(sb, src, bytes, bar, policy);
+      else
+        bulk_g2s(sb, src, bytes, bar);
+    }
+  }
+  ++ring.qi;
+  if (++ring.ik == wt.nt) {
+    ring.ik = 0;
+    ++ring.ipass;
+  }
+  if (++ring.istage == a.S) ring.istage = 0;
 }
 
+// Fills the ring at the start of a launch (all lanes).
+__device__ __forceinline__ void ring_prologue(const KArgs& a, const WarpTiles& wt, Ring& ring, long long n_passes, int lane,
+                                              uint64_t policy) {
+  ring.q_total = n_passes * wt.nt;
+  for (int s = 0; s < a.S && ring.qi < ring.q_total; ++s) ring_issue(a, wt, ring, lane, policy);
+}
+
+// ---- packed helpers -------------------------------------------------------------------------------
 template <int V>
-__device__ __forceinline__ void lds_vec(const float* p, float* out) {
+struct Acc {
+  using type = float2;
+};
+template <>
+struct Acc<1> {
+  using type = float;
+};
+
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// Loads K chunks of V floats starting at p with a chunk stride of `cstride` floats into packed registers.
+template <int V, int K>
+__device__ __forceinline__ void load_chunks(const float* p, int cstride, typename Acc<V>::type* out) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    if constexpr (V == 1) {
+      out[k] = p[k * cstride];
+    } else if constexpr (V == 2) {
+      out[k] = *reinterpret_cast<const float2*>(p + k * cstride);
+    } else {
+      const float4 t = *reinterpret_cast<const float4*>(p + k * cstride);
+      out[2 * k] = make_float2(t.x, t.y);
+      out[2 * k + 1] = make_float2(t.z, t.w);
+    }
+  }
+}
+
+template <int V, int NA>
+__device__ __forceinline__ float flat(const typename Acc<V>::type* g, int i) {
   if constexpr (V == 1) {
-    out[0] = *p;
-  } else if constexpr (V == 2) {
-    const float2 t = *reinterpret_cast<const float2*>(p);
-    out[0] = t.x;
-    out[1] = t.y;
+    return g[i];
   } else {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    out[0] = t.x;
-    out[1] = t.y;
-    out[2] = t.z;
-    out[3] = t.w;
+    return (i & 1) ? g[i >> 1].y : g[i >> 1].x;
   }
 }
 
 // One pass of this CTA over its rows. On return cta_acc[0..D) = Σ r_n·X[n,:], cta_acc[D] = Σ r_n (if
 // has_bias), cta_acc[P] = Σ log p(y_n|eta_n) over the CTA's rows, all float64, reduced in a fixed
 // order (bitwise reproducible). Ends with a __syncthreads().
-template <int G, int V, int KMAX>
-__device__ __forceinline__ void stream_pass(const KArgs& a, const WarpRows& wr, Ring& ring, const float* theta_s,
+template <int G, int V, int K>
+__device__ __forceinline__ void stream_pass(const KArgs& a, const WarpTiles& wt, Ring& ring, const float* theta_s,
                                             float bias, uint64_t policy, double* cta_acc) {
   constexpr int RPS = 32 / G;  // rows processed concurrently by a warp
-  constexpr int KV = KMAX * V;
+  constexpr int KV = K * V;
+  constexpr int NA = (V == 1) ? KV : KV / 2;  // packed accumulators per lane
+  constexpr bool WREG = (KV <= 56);           // theta slice held in registers
+  using acc_t = typename Acc<V>::type;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lg = lane % G, grp = lane / G;
-  const int ldx = static_cast<int>(a.ldx);
-  const int Kact = a.Kact;
+  const int lg = lane & (G - 1), grp = lane / G;
+  const int ldx = a.ldx_i;
+  const int family = a.family;
+  const float lik_scale = a.lik_scale;
 
-  float g[KV];
+  acc_t g[NA];
+  acc_t w[WREG ? NA : 1];
 #pragma unroll
-  for (int i = 0; i < KV; ++i) g[i] = 0.0f;
+  for (int i = 0; i < NA; ++i) {
+    if constexpr (V == 1)
+      g[i] = 0.0f;
+    else
+      g[i] = make_float2(0.0f, 0.0f);
+  }
+  if constexpr (WREG) load_chunks<V, K>(theta_s + lg * V, G * V, w);
   float gb = 0.0f;
   double lp = 0.0;
 
-  for (int kt = 0; kt < wr.nt; ++kt) {
-    long long row0;
-    int rows;
-    tile_geometry(a, wr, ring.cpass, kt, row0, rows);
-    const float* sb = ring.base + static_cast<size_t>(ring.stage) * a.stage_floats;
+  const bool backward = a.zigzag && (ring.cpass & 1);
+  for (int kt = 0; kt < wt.nt; ++kt) {
+    const int kk = backward ? (wt.nt - 1 - kt) : kt;
+    const int rows = (kk == wt.nt - 1) ? wt.rows_last : a.RT;
+    const int m = (kk * a.tm) & 3;
+    const float* sb = ring.base + ring.stage * a.stage_floats;
     mbar_wait(ring.bars + ring.stage, ring.parity);
     const uint32_t* ys = reinterpret_cast<const uint32_t*>(sb + a.y_off);
+    const float* xbase = sb + m + grp * ldx + lg * V;
 
-    for (int j = 0; j < a.J; ++j) {
-      if (j * RPS >= rows) break;  // warp-uniform
-      const int lr = j * RPS + grp;
-      const float* xr = sb + lr * ldx + lg * V;
-      float x[KV];
+    for (int j0 = 0; j0 < rows; j0 += RPS) {  // warp-uniform
+      const int lr = j0 + grp;
+      acc_t x[NA];
+      load_chunks<V, K>(xbase + j0 * ldx, G * V, x);
+      float dotv;
+      if constexpr (V == 1) {
+        float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < Kact) lds_vec<V>(xr + k * G * V, &x[k * V]);
-      float acc0 = 0.0f, acc1 = 0.0f;
+        for (int i = 0; i < NA; ++i) {
+          float wi;
+          if constexpr (WREG)
+            wi = w[i];
+          else
+            wi = theta_s[(i * G + lg)];
+          if (i & 1)
+            a1 = fmaf(x[i], wi, a1);
+          else
+            a0 = fmaf(x[i], wi, a0);
+        }
+        dotv = a0 + a1;
+      } else {
+        float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+        if constexpr (WREG) {
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < Kact) {
-          float wv[V];
-          lds_vec<V>(theta_s + (k * G + lg) * V, wv);
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            if (((k * V + v) & 1) == 0)
-              acc0 = fmaf(x[k * V + v], wv[v], acc0);
+          for (int i = 0; i < NA; ++i) {
+            if (i & 1)
+              a1 = fma2(x[i], w[i], a1);
             else
-              acc1 = fmaf(x[k * V + v], wv[v], acc1);
+              a0 = fma2(x[i], w[i], a0);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            acc_t wk[V / 2];
+            load_chunks<V, 1>(theta_s + (k * G + lg) * V, 0, wk);
+#pragma unroll
+            for (int q = 0; q < V / 2; ++q) {
+              if (q & 1)
+                a1 = fma2(x[k * (V / 2) + q], wk[q], a1);
+              else
+                a0 = fma2(x[k * (V / 2) + q], wk[q], a0);
+            }
           }
         }
-      float dotv = acc0 + acc1;
+        dotv = (a0.x + a0.y) + (a1.x + a1.y);
+      }
 #pragma unroll
       for (int off = G / 2; off > 0; off >>= 1) dotv += __shfl_xor_sync(kFull, dotv, off);
       const float eta = dotv + bias;
       const bool valid = lr < rows;
       const float yv = y_from_bits(ys[valid ? lr : 0], a.y_dtype);
       float lpv, rv;
-      row_terms(a.family, eta, yv, a.lik_scale, lpv, rv);
+      row_terms(family, eta, yv, lik_scale, lpv, rv);
       if (!valid) {
         lpv = 0.0f;
         rv = 0.0f;
@@ -194,51 +263,59 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const WarpRows& wr, 
         lp += static_cast<double>(lpv);
         gb += rv;
       }
+      if constexpr (V == 1) {
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < Kact) {
+        for (int i = 0; i < NA; ++i) g[i] = fmaf(rv, x[i], g[i]);
+      } else {
+        const float2 r2 = make_float2(rv, rv);
 #pragma unroll
-          for (int v = 0; v < V; ++v) g[k * V + v] = fmaf(rv, x[k * V + v], g[k * V + v]);
-        }
+        for (int i = 0; i < NA; ++i) g[i] = fma2(r2, x[i], g[i]);
+      }
     }
     __syncwarp();
     if (++ring.stage == a.S) {
       ring.stage = 0;
       ring.parity ^= 1u;
     }
-    if (ring.qi < ring.q_total) ring_issue(a, wr, ring, lane, policy);
+    if (ring.qi < ring.q_total) ring_issue(a, wt, ring, lane, policy);
   }
   ++ring.cpass;
 
-  // ---- reduce across the row groups of the warp (lanes with equal lg) ----
+  // ---- reduce across the RPS row groups of the warp with a halving butterfly: after stage `st` a lane
+  //      keeps the half of the accumulators selected by its own bit, so 32+16+8+4+2 shuffles sum 64
+  //      accumulators over 32 lanes (instead of 64*5). ----
+  constexpr int NST = (RPS == 32) ? 5 : (RPS == 8 ? 3 : 0);
+  constexpr int LP = (KV + RPS - 1) / RPS * RPS;  // padded length, divisible by RPS = 2^NST
+  constexpr int LPF = LP / RPS;                   // accumulators a lane ends up owning
+  float h[LP];
 #pragma unroll
-  for (int off = G; off < 32; off <<= 1) {
+  for (int i = 0; i < LP; ++i) h[i] = (i < KV) ? flat<V, NA>(g, i) : 0.0f;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      if (k < Kact) {
+  for (int st = 0; st < NST; ++st) {
+    const int off = 16 >> st;
+    const int half = LP >> (st + 1);
+    const bool upper = (lane & off) != 0;
 #pragma unroll
-        for (int v = 0; v < V; ++v) g[k * V + v] += __shfl_xor_sync(kFull, g[k * V + v], off);
-      }
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? h[i] : h[i + half];
+      const float keep = upper ? h[i + half] : h[i];
+      h[i] = keep + __shfl_xor_sync(kFull, send, off);
+    }
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) gb += __shfl_xor_sync(kFull, gb, off);
   lp = warp_sum_f64(lp);
 
-  // ---- reduce across the warps of the CTA: fixed order, float64 ----
+  // ---- reduce across the warps of the CTA: fixed order, float64. Lane (grp, lg) owns flat accumulator
+  //      indices grp*LPF + j, i.e. chunk k = idx / V, element v = idx % V, column (k*G+lg)*V+v. ----
   for (int wq = 0; wq < kWarpsPerCta; ++wq) {
     if (warp == wq) {
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < Kact) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            // every replica of the lane group holds the same totals: spread the writes over replicas
-            if (grp == ((k * V + v) % RPS)) {
-              const int col = (k * G + lg) * V + v;
-              if (col < a.D) cta_acc[col] = (wq ? cta_acc[col] : 0.0) + static_cast<double>(g[k * V + v]);
-            }
-          }
-        }
+      for (int j = 0; j < LPF; ++j) {
+        const int idx = grp * LPF + j;
+        const int col = ((idx / V) * G + lg) * V + (idx % V);
+        if (idx < KV && col < a.D) cta_acc[col] = (wq ? cta_acc[col] : 0.0) + static_cast<double>(h[j]);
+      }
       if (lane == 0) {
         if (a.has_bias) cta_acc[a.D] = (wq ? cta_acc[a.D] : 0.0) + static_cast<double>(gb);
         cta_acc[a.P] = (wq ? cta_acc[a.P] : 0.0) + lp;
@@ -294,7 +371,7 @@ __device__ __forceinline__ void reduce_partials(const double* part, int ncta, in
   }
 }
 
-// Shared-memory carve-up common to both plans.
+// Shared-memory carve-up.
 struct SmemLayout {
   float* ring;
   uint64_t* bars;
@@ -302,13 +379,12 @@ struct SmemLayout {
   double* red;
   double* comb;
   float* theta_s;
-  float* state;  // 5 * ppad floats (persistent plan only)
+  float* state;  // 5 * ppad floats
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline size_t smem_layout_bytes(int S, int stage_floats, int P, int wpad, bool with_state,
-                                                    size_t* offs /*7*/) {
+__host__ __device__ inline size_t smem_layout_bytes(int S, int stage_floats, int P, int wpad, size_t* offs /*7*/) {
   size_t off = 0;
   offs[0] = off;
   off += static_cast<size_t>(kWarpsPerCta) * S * stage_floats * 4;
@@ -324,13 +400,13 @@ __host__ __device__ inline size_t smem_layout_bytes(int S, int stage_floats, int
   offs[5] = off;
   off += align_up(static_cast<size_t>(wpad) * 4, 16);
   offs[6] = off;
-  if (with_state) off += 5 * align_up(static_cast<size_t>(P) * 4, 16);
+  off += 5 * align_up(static_cast<size_t>(P) * 4, 16);
   return align_up(off, 128);
 }
 
-__device__ __forceinline__ SmemLayout carve_smem(unsigned char* raw, const KArgs& a, bool with_state) {
+__device__ __forceinline__ SmemLayout carve_smem(unsigned char* raw, const KArgs& a) {
   size_t offs[7];
-  smem_layout_bytes(a.S, a.stage_floats, a.P, a.wpad, with_state, offs);
+  smem_layout_bytes(a.S, a.stage_floats, a.P, a.wpad, offs);
   SmemLayout L;
   L.ring = reinterpret_cast<float*>(raw + offs[0]);
   L.bars = reinterpret_cast<uint64_t*>(raw + offs[1]);
@@ -345,8 +421,8 @@ __device__ __forceinline__ SmemLayout carve_smem(unsigned char* raw, const KArgs
 // Zero the ring (so padded / stale columns are finite), init the mbarriers, zero theta_s.
 __device__ __forceinline__ void smem_setup(const SmemLayout& L, const KArgs& a) {
   const int tid = threadIdx.x;
-  const size_t nring = static_cast<size_t>(kWarpsPerCta) * a.S * a.stage_floats;
-  for (size_t i = tid; i < nring; i += kThreads) L.ring[i] = 0.0f;
+  const int nring = kWarpsPerCta * a.S * a.stage_floats;
+  for (int i = tid; i < nring; i += kThreads) L.ring[i] = 0.0f;
   for (int i = tid; i < a.wpad; i += kThreads) L.theta_s[i] = 0.0f;
   if (tid < kWarpsPerCta * kMaxStages) mbar_init(L.bars + tid, 33);  // 32 cp.async arrivals + 1 expect_tx arrival
   fence_mbar_init();

@@ -1,0 +1,125 @@
+"""Normal, Bernoulli, Poisson — the random variables of the HMC hot path. In the reference these are
+generated wrappers over tf.contrib.distributions (edward/models/random_variables.py:13-25); only their
+constructor signatures, `support` tags (:27-58) and eager read-outs are mirrored here. The densities the
+sampler needs are evaluated by libedhmc, not by these classes."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .. import graph as _g
+from .random_variable import RandomVariable
+
+
+def _bshape(*ts):
+  shape = ()
+  for t in ts:
+    shape = np.broadcast_shapes(shape, tuple(d if d is not None else 1 for d in t.shape))
+  return shape
+
+
+class Normal(RandomVariable):
+  support = 'real'
+
+  def __init__(self, loc, scale, validate_args=False, allow_nan_stats=True, name="Normal", **kwargs):
+    self.loc = _g.convert_to_tensor(loc)
+    self.scale = _g.convert_to_tensor(scale, self.loc.dtype if not isinstance(scale, _g.Tensor) else None)
+    if self.loc.dtype != self.scale.dtype:
+      raise TypeError("loc and scale must have the same dtype: %r vs %r" % (self.loc.dtype, self.scale.dtype))
+    self._args, self._kwargs = (loc, scale), dict(kwargs)
+    super(Normal, self).__init__(_bshape(self.loc, self.scale), (), self.loc.dtype, name=name, **kwargs)
+
+  def _sample_np(self, sample_shape):
+    loc, scale = _g.evaluate(self.loc), _g.evaluate(self.scale)
+    shape = tuple(sample_shape) + tuple(self.batch_shape)
+    return (loc + scale * np.random.standard_normal(shape)).astype(self.dtype.np)
+
+  def log_prob(self, value):
+    v = _g.convert_to_tensor(value, self.dtype)
+
+    def fn():
+      x, loc, scale = _g.evaluate(v), _g.evaluate(self.loc), _g.evaluate(self.scale)
+      return -0.5 * np.square((x - loc) / scale) - (0.5 * math.log(2.0 * math.pi) + np.log(scale))
+    return _g.Lazy(fn, _bshape(v, self.loc, self.scale), self.dtype, "NormalLogProb")
+
+  def mean(self):
+    return self.loc
+
+  def stddev(self):
+    return self.scale
+
+
+class Bernoulli(RandomVariable):
+  support = 'binary'
+
+  def __init__(self, logits=None, probs=None, dtype=_g.int32, validate_args=False, allow_nan_stats=True,
+               name="Bernoulli", **kwargs):
+    if (logits is None) == (probs is None):
+      raise ValueError("Must pass probs or logits, but not both.")
+    self.logits = _g.convert_to_tensor(logits) if logits is not None else None
+    self._probs = _g.convert_to_tensor(probs) if probs is not None else None
+    self._args, self._kwargs = (), dict(kwargs, logits=logits, probs=probs)
+    param = self.logits if self.logits is not None else self._probs
+    super(Bernoulli, self).__init__(tuple(param.shape), (), dtype, name=name, **kwargs)
+
+  def _probs_np(self, feed=None):
+    if self._probs is not None:
+      return _g.evaluate(self._probs, feed)
+    return 1.0 / (1.0 + np.exp(-_g.evaluate(self.logits, feed)))
+
+  @property
+  def probs(self):
+    if self._probs is not None:
+      return self._probs
+    return _g.Lazy(self._probs_np, tuple(self.logits.shape), self.logits.dtype, "Sigmoid")
+
+  def _sample_np(self, sample_shape):
+    p = self._probs_np()
+    return (np.random.uniform(size=tuple(sample_shape) + p.shape) < p).astype(self.dtype.np)
+
+  def log_prob(self, value):
+    v = _g.convert_to_tensor(value)
+    fdt = self.logits.dtype if self.logits is not None else self._probs.dtype
+
+    def fn():
+      y = _g.evaluate(v).astype(fdt.np)
+      if self.logits is not None:
+        l = _g.evaluate(self.logits)
+        return -(np.maximum(l, 0) - l * y + np.log1p(np.exp(-np.abs(l))))
+      p = _g.evaluate(self._probs)
+      return y * np.log(p) + (1.0 - y) * np.log1p(-p)
+    return _g.Lazy(fn, tuple(self.shape), fdt, "BernoulliLogProb")
+
+  def mean(self):
+    return self.probs
+
+
+class Poisson(RandomVariable):
+  support = 'countable'
+
+  def __init__(self, rate=None, log_rate=None, validate_args=False, allow_nan_stats=True, name="Poisson", **kwargs):
+    if (rate is None) == (log_rate is None):
+      raise ValueError("Must specify exactly one of `rate` and `log_rate`.")
+    self.log_rate = _g.convert_to_tensor(log_rate) if log_rate is not None else None
+    self._rate = _g.convert_to_tensor(rate) if rate is not None else None
+    self._args, self._kwargs = (), dict(kwargs, rate=rate, log_rate=log_rate)
+    param = self.log_rate if self.log_rate is not None else self._rate
+    super(Poisson, self).__init__(tuple(param.shape), (), param.dtype, name=name, **kwargs)
+
+  def _rate_np(self):
+    return _g.evaluate(self._rate) if self._rate is not None else np.exp(_g.evaluate(self.log_rate))
+
+  def _sample_np(self, sample_shape):
+    lam = self._rate_np()
+    return np.random.poisson(lam, size=tuple(sample_shape) + lam.shape).astype(self.dtype.np)
+
+  def log_prob(self, value):
+    from scipy.special import gammaln
+    v = _g.convert_to_tensor(value)
+
+    def fn():
+      y = _g.evaluate(v).astype(self.dtype.np)
+      lam = self._rate_np()
+      return y * np.log(lam) - lam - gammaln(y + 1.0)
+    return _g.Lazy(fn, tuple(self.shape), self.dtype, "PoissonLogProb")
