@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py — HMC leapfrog steps/s for Bayesian logistic regression (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4]
+
+A bench "step" is one `inference.run(step_size, n_steps)`-sized unit of the hot path: T transitions x L
+leapfrog steps of one chain over the whole (synthetic, resident) design matrix.
+
+  --gpus 1 (default)  workload cfg2: covertype shape N=581,012 D=54, T=100, L=10, eps=0.5/N
+                      (docs/tex/iclr2017.tex:241-265), one chain, persistent plan.
+  --gpus N>1          workload cfg4: N=10,000,000 D=1,000, rows sharded over the N GPUs in blocks of 65,536
+                      rows, NCCL all-reduce of [grad, logp] per leapfrog step; strong scaling (fixed
+                      total rows).  Launched by torchrun, one rank per GPU.
+  --impl reference    the reference's CPU schedule (oracle/hmc_ref.c, OpenMP on the host cores; TensorFlow
+                      itself cannot be installed here) on the same workload, bounded sample per step.
+
+`value` times edhmc_run with CUDA events on the launching stream, inputs resident in HBM, L2 flushed
+between steps. `e2e` times the public call chain ed.HMC(...).run() from pinned host arrays, including
+the H2D copy of X and y and the D2H read of the samples. One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg2": dict(N=581012, D=54, T=100, L=10, name="cfg2: covertype-shaped N=581012 D=54, 1 chain, T=100, n_steps=10, step_size=0.5/N"),
+    "cfg4": dict(N=10_000_000, D=1000, T=4, L=10, name="cfg4: N=10000000 D=1000, 1 chain, T=4, n_steps=10, step_size=0.5/N, rows sharded"),
+}
+GEN_BLOCK = 65536
+BASE_SEED = 42
+
+
+def parse():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--workload", default=None, choices=[None, "cfg2", "cfg4"])
+  ap.add_argument("--rows", type=int, default=None, help="override the row count (debugging)")
+  ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data: X ~ N(0,1), w_true ~ N(0,1/D), y ~ Bernoulli(sigmoid(X w_true)), generated
+# in 65,536-row blocks seeded by block index so that any sharding on block boundaries gives the same data
+# ------------------------------------------------------------------------------------------------
+def gen_device_rows(torch, dev, row_start, n_rows, D):
+  assert row_start % GEN_BLOCK == 0
+  gw = torch.Generator(device=dev).manual_seed(BASE_SEED + (1 << 40))
+  w_true = torch.randn(D, device=dev, generator=gw) / D ** 0.5
+  X = torch.empty(n_rows, D, device=dev, dtype=torch.float32)
+  y = torch.empty(n_rows, device=dev, dtype=torch.int32)
+  done = 0
+  b = row_start // GEN_BLOCK
+  while done < n_rows:
+    n = min(GEN_BLOCK, n_rows - done)
+    g = torch.Generator(device=dev).manual_seed(BASE_SEED + b)
+    xb = torch.randn(n, D, device=dev, generator=g)
+    X[done:done + n] = xb
+    y[done:done + n] = (torch.rand(n, device=dev, generator=g) < torch.sigmoid(xb @ w_true)).to(torch.int32)
+    done += n
+    b += 1
+  return X, y
+
+
+def shard_bounds(N, world, rank):
+  """Contiguous shards on 65,536-row block boundaries."""
+  nblocks = (N + GEN_BLOCK - 1) // GEN_BLOCK
+  b0 = nblocks * rank // world
+  b1 = nblocks * (rank + 1) // world
+  return min(b0 * GEN_BLOCK, N), min(b1 * GEN_BLOCK, N)
+
+
+class ClockSampler(object):
+  """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+  def __init__(self, index):
+    self.rows = []
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
+                                    "--format=csv,noheader,nounits", "-lms", "100"],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.th = threading.Thread(target=self._read, daemon=True)
+      self.th.start()
+    except Exception:
+      self.proc = None
+    self.mark = 0
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append((time.time(), line.strip()))
+
+  def start(self):
+    self.t0 = time.time()
+
+  def stop(self):
+    self.t1 = time.time()
+    if self.proc:
+      self.proc.terminate()
+    sm, smmax, reasons = [], 0.0, set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ts, line in self.rows:
+      if not (self.t0 - 0.05 <= ts <= self.t1 + 0.15):
+        continue
+      f = [x.strip() for x in line.split(",")]
+      try:
+        sm.append(float(f[0]))
+        smmax = max(smmax, float(f[1]))
+        for nm, v in zip(names, f[3:7]):
+          if v.lower().startswith("active"):
+            reasons.add(nm)
+      except Exception:
+        pass
+    sm.sort()
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smmax or None, "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+def measured_peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    with open(p) as f:
+      d = json.load(f)
+    return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+  return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's schedule in C/OpenMP (oracle/hmc_ref.c)
+# ------------------------------------------------------------------------------------------------
+def cpu_rows(wl, rows_cap):
+  """Host copy of the first rows of the workload (numpy Philox stream; values differ from the device
+  generator's, the shapes and distributions are the same — only the time matters here)."""
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  import hmc_oracle as o
+  n = min(wl["N"], rows_cap)
+  X, y, _ = o.synth_data(n, wl["D"])
+  return o, X, y
+
+
+def time_reference(wl, n_transitions, rows_cap, repeats=1):
+  import numpy as np
+  o, X, y = cpu_rows(wl, rows_cap)
+  import ref_c
+  spec = o.GLMSpec(wl["D"])
+  r0, u = o.synth_draws(n_transitions, wl["D"])
+  params = np.zeros((n_transitions, wl["D"]), np.float32)
+  best = None
+  for _ in range(repeats):
+    t = time.perf_counter()
+    ref_c.run(X, y, params, r0, u, 0.5 / wl["N"], wl["L"], spec, trace=False)
+    dt = time.perf_counter() - t
+    best = dt if best is None else min(best, dt)
+  scale = wl["N"] / float(X.shape[0])  # linear extrapolation when a row subsample is timed
+  return best * scale, X.shape[0], ref_c.num_threads()
+
+
+def run_reference(args, wl, wl_key):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  rows_cap = wl["N"] if wl_key == "cfg2" else wl["N"] // 64
+  n_tr = 2
+  for _ in range(args.warmup):
+    time_reference(wl, 1, rows_cap)
+  times = []
+  for _ in range(args.steps):
+    dt, nrows, threads = time_reference(wl, n_tr, rows_cap)
+    times.append(dt)
+  total = sum(times)
+  steps_per_s = args.steps * n_tr * wl["L"] / total
+  sample = "%d transitions x (L+1 gradient + 2 forward evaluations) per step on %d of %d rows%s" % (
+      n_tr, nrows, wl["N"], "" if nrows == wl["N"] else " (time scaled linearly to all rows)")
+  line = {
+      "impl": "reference", "metric": "hmc_leapfrog_steps_per_s", "value": steps_per_s, "unit": "leapfrog steps/s",
+      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+      "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+      "data": "synthetic",
+      "config": {"workload": wl["name"], "note": "CPU restatement of the reference's TF schedule (not TensorFlow)"},
+      "cpu_baseline": {"value": steps_per_s, "unit": "leapfrog steps/s", "cores": threads, "kind": "port", "sample": sample},
+      "e2e": {"value": steps_per_s, "unit": "leapfrog steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+  args = parse()
+  wl_key = args.workload or ("cfg2" if args.gpus == 1 else "cfg4")
+  wl = dict(WORKLOADS[wl_key])
+  if args.rows:
+    wl["N"] = args.rows
+  if args.impl == "reference":
+    run_reference(args, wl, wl_key)
+    return
+
+  import numpy as np
+  import torch
+  import torch.distributed as dist
+  from edward_b200 import engine
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if args.gpus > 1 and world != args.gpus:
+    raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d)" % (args.gpus, args.gpus, world))
+  dev = torch.device("cuda", local_rank)
+  torch.cuda.set_device(dev)
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+
+  N, D, T, L = wl["N"], wl["D"], wl["T"], wl["L"]
+  eps = 0.5 / N
+  r_lo, r_hi = shard_bounds(N, world, rank)
+  X, y = gen_device_rows(torch, dev, r_lo, r_hi - r_lo, D)
+  s = engine.GLMSampler(engine.GLMSpec(D), X, y, device=dev, n_rows_global=N,
+                        plan=engine._C.PLAN_STEPWISE if world > 1 else engine._C.PLAN_AUTO)
+  if world > 1:
+    s.init_comm(world, rank)
+  s.seed(1234)
+  params = torch.zeros(T, D, device=dev)
+  flush = torch.empty(512 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize(dev)
+
+  def one_step(timed):
+    flush.fill_(1.0)  # flush L2 between steps (outside the timed events)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s.run(params, 0, T, eps, L)
+    e1.record()
+    return e0, e1
+
+  for _ in range(max(args.warmup, 3)):
+    one_step(False)
+  barrier()
+  sampler = ClockSampler(local_rank) if rank == 0 else None
+  if sampler:
+    time.sleep(0.25)
+    sampler.start()
+  barrier()
+  wall0 = time.perf_counter()
+  evs = [one_step(True) for _ in range(args.steps)]
+  barrier()
+  wall = time.perf_counter() - wall0
+  clocks = sampler.stop() if sampler else None
+  dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+  t_ms = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+  dev_ms = float(t_ms.item())
+  info = s.plan_info()
+  n_accept, _ = s.read_state()
+  steps_total = args.steps * T * L
+  value = steps_total / (dev_ms * 1e-3)
+  launches = info["launches_last_run"] * args.steps
+
+  # ---- strong-scaling reference: the same workload on rank 0 alone (only when sharded) ----
+  n1_same = None
+  if world > 1:
+    if rank == 0:
+      try:
+        X1, y1 = gen_device_rows(torch, dev, 0, N, D)
+        s1 = engine.GLMSampler(engine.GLMSpec(D), X1, y1, device=dev)
+        s1.seed(1234)
+        p1 = torch.zeros(T, D, device=dev)
+        s1.run(p1, 0, T, eps, L)
+        torch.cuda.synchronize(dev)
+        ms1 = 0.0
+        for _ in range(2):
+          flush.fill_(1.0)
+          a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          a.record()
+          s1.run(p1, 0, T, eps, L)
+          b.record()
+          torch.cuda.synchronize(dev)
+          ms1 += a.elapsed_time(b)
+        n1_same = {"value": 2 * T * L / (ms1 * 1e-3), "unit": "leapfrog steps/s", "plan": "persistent, 1 GPU, same job"}
+        s1.close()
+        del X1, y1
+      except Exception as e:  # noqa: BLE001
+        n1_same = {"error": str(e)[:200]}
+    dist.barrier()
+
+  # ---- end to end through the public API: host arrays -> ed.HMC(...).run() -> samples on the host ----
+  e2e = None
+  if not args.no_e2e and world == 1:
+    import edward_b200 as ed
+    from edward_b200 import graph as g
+    from edward_b200 import tfshim as tf
+    from edward_b200.models import Bernoulli, Empirical, Normal
+    Xh = X.cpu().pin_memory()
+    yh = y.cpu().pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    times = []
+    h2d = Xh.numel() * 4 + yh.numel() * 4
+    d2h = T * D * 4 + 16
+    for i in range(e2e_steps + 1):
+      g.reset_default_graph()
+      flush.fill_(1.0)
+      torch.cuda.synchronize(dev)
+      t0 = time.perf_counter()
+      xs = tf.placeholder(tf.float32, [N, D])
+      beta = Normal(loc=tf.zeros(D), scale=tf.ones(D))
+      ys = Bernoulli(logits=ed.dot(xs, beta))
+      qbeta = Empirical(params=tf.Variable(tf.zeros([T, D])))
+      inference = ed.HMC({beta: qbeta}, data={xs: Xh, ys: yh})
+      inference.run(step_size=eps, n_steps=L, n_print=0, device=dev)
+      samples = qbeta.params.eval()  # D2H read of the result
+      n_acc = int(inference.n_accept.eval())
+      dt = time.perf_counter() - t0
+      if i > 0:
+        times.append(dt)
+      assert samples.shape == (T, D) and 0 <= n_acc <= T
+    e2e = {"value": e2e_steps * T * L / sum(times), "unit": "leapfrog steps/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "call": "ed.HMC({beta: qbeta}, data={X: pinned host array, y: ...}).run(step_size, n_steps) + qbeta.params.eval()"}
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  peak, peak_src = measured_peaks()
+  alg_bytes_step = 4.0 * (r_hi - r_lo) * D + 4.0 * (r_hi - r_lo)  # this rank's shard: X once + y once per leapfrog step
+  launch_ms = dev_ms / args.steps if info["plan_in_use"] == 1 else None
+  achieved = alg_bytes_step * T * L / (dev_ms / args.steps * 1e-3) / 1e9
+  roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+              "traffic": None, "peak_source": peak_src,
+              "kernel": "edhmc::k_hmc (one persistent launch = T*L passes)" if info["plan_in_use"] == 1
+              else "edhmc::k_hmc mode 1 (one pass per launch) + NCCL all-reduce + chain kernels",
+              "algorithmic_bytes_per_launch": alg_bytes_step * T * L if info["plan_in_use"] == 1 else alg_bytes_step,
+              "launch_ms": launch_ms}
+
+  cpu = None
+  if world == 1 and not args.no_cpu_baseline:
+    rows_cap = N if wl_key == "cfg2" else N // 64
+    probe, nrows, threads = time_reference(wl, 1, rows_cap)
+    n_tr = int(max(2, min(60, 12.0 / max(probe * nrows / N, 1e-3))))
+    dt, nrows, threads = time_reference(wl, n_tr, rows_cap)
+    cpu = {"value": n_tr * L / dt, "unit": "leapfrog steps/s", "cores": threads, "kind": "port",
+           "sample": "%d transitions x (L+1 gradient + 2 forward evaluations, CheckNumerics on) on %d of %d rows%s; "
+                     "C/OpenMP restatement of the reference's TensorFlow schedule (oracle/hmc_ref.c), host has %d logical CPUs"
+                     % (n_tr, nrows, N, "" if nrows == N else ", time scaled linearly", os.cpu_count())}
+
+  line = {
+      "metric": "hmc_leapfrog_steps_per_s", "value": value, "unit": "leapfrog steps/s", "n_gpus": world,
+      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+      "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+      "data": "synthetic",
+      "config": {"workload": wl["name"], "rows": N, "features": D, "transitions_per_step": T, "leapfrog_per_transition": L,
+                 "chains": 1, "plan": {1: "persistent", 2: "stepwise"}[info["plan_in_use"]],
+                 "parallelism": "rows sharded over %d GPUs, NCCL all-reduce per leapfrog step" % world if world > 1 else "1 GPU",
+                 "l2": "L2 flushed between steps (512 MiB write); within a step X (%.1f MB) is re-streamed every leapfrog step" % (4e-6 * (r_hi - r_lo) * D),
+                 "rng": "device Philox", "grid_ctas": info["grid_ctas"], "ring_stages": info["ring_stages"], "tile_rows": info["tile_rows"]},
+      "rows_steps_per_s": value * N,
+      "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+      "clocks": clocks, "n_accept_last_step": n_accept, "wall_s": wall,
+  }
+  if n1_same is not None:
+    line["n1_same_workload"] = n1_same
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -156,6 +156,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
     in_init = __syncthreads_or((mismatch || !valid) ? 1 : 0) != 0;
     n_passes = (in_init ? 1 : 0) + a.n_iter * a.L;
   }
+  // Zig-zag direction = parity of the pass's global leapfrog-step index t*L + s (the initial evaluation
+  // counts as step -1), so the accumulation order does not depend on how transitions are chunked into
+  // launches.
+  {
+    const int par0 = single ? (a.par0 & 1) : static_cast<int>((a.t0 * a.L - (in_init ? 1 : 0)) & 1);
+    ring.cpass = par0;
+    ring.ipass = par0;
+  }
   ring_prologue(a, wt, ring, n_passes, lane, policy);
   if (!single) {
     if (in_init) {

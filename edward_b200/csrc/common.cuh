@@ -57,6 +57,7 @@ struct KArgs {
   // ---- launch mode ----
   int mode;               // 0: run n_iter transitions (cooperative launch); 1: one data pass at theta_in
   int gate;               // mode 1: return immediately unless sc->need_init
+  int par0;               // mode 1: parity of this pass's global leapfrog-step index (zig-zag direction)
   const float* theta_in;  // mode 1: [P]
   // ---- scratch ----
   double* partials;            // [2][grid][P+1]

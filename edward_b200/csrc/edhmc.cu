@@ -444,10 +444,11 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
   return 0;
 }
 
-static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int gate, cudaStream_t stream) {
+static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int gate, long long gsi, cudaStream_t stream) {
   KArgs aa = a;
   aa.mode = 1;
   aa.gate = gate;
+  aa.par0 = static_cast<int>(gsi & 1);
   aa.theta_in = theta;
   void* params[] = {&aa};
   CUDA_TRY(cudaLaunchKernel(h->plan.fn, dim3(h->plan.grid), dim3(kThreads), params, h->plan.smem, stream));
@@ -472,7 +473,7 @@ int edhmc_logp_grad(edhmc_t* h, const float* theta, double* logp, float* grad, v
   h->passes_last = 1;
   KArgs a;
   fill_args(h, a);
-  int rc = launch_pass(h, a, theta, 0, stream);
+  int rc = launch_pass(h, a, theta, 0, 0, stream);
   if (rc) return rc;
   rc = allreduce_sums(h, stream);
   if (rc) return rc;
@@ -523,7 +524,7 @@ int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int
     int rc;
     k_chain_check<<<1, kThreads, 0, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
-    if ((rc = launch_pass(h, a, h->d_zcur, 1, stream))) return rc;
+    if ((rc = launch_pass(h, a, h->d_zcur, 1, t0 * n_steps - 1, stream))) return rc;
     if ((rc = allreduce_sums(h, stream))) return rc;
     k_chain_init_finish<<<1, kThreads, 0, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -533,7 +534,7 @@ int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int
       CUDA_TRY(cudaGetLastError());
       ++h->launches_last;
       for (int s = 0; s < n_steps; ++s) {
-        if ((rc = launch_pass(h, a, h->d_z, 0, stream))) return rc;
+        if ((rc = launch_pass(h, a, h->d_z, 0, (t0 + it) * n_steps + s, stream))) return rc;
         if ((rc = allreduce_sums(h, stream))) return rc;
         k_chain_leap<<<1, kThreads, 0, stream>>>(a, it, s, h->d_g);
         CUDA_TRY(cudaGetLastError());

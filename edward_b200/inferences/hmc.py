@@ -1,0 +1,169 @@
+"""ed.HMC — Hamiltonian Monte Carlo over Empirical posteriors, edward/inferences/hmc.py:14-210, with the
+transition executed by libedhmc on the GPU instead of a TensorFlow graph.
+
+    inference = ed.HMC({w: qw, b: qb}, data={X: X_train, y: y_train})
+    inference.run(step_size=0.6)          # or initialize() + update() loop
+
+keeps the reference's surface: `initialize(step_size=0.25, n_steps=2, ...)` (hmc.py:45), `update()` →
+{'t', 'accept_rate'} (monte_carlo.py:111-150), `run()` (inference.py:97-154), attributes `t`, `n_accept`,
+`n_accept_over_t`, `n_iter`, `n_print`, `step_size`, `n_steps`, `latent_vars`, `data`, `reset`, `progbar`,
+`train`. Transition t reads row max(t-1,0) of each Empirical's params and writes row t (hmc.py:81-85,121-126).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .. import _C
+from .. import graph as _g
+from ..glm import recognize
+from ..util.graphs import get_seed
+from .monte_carlo import MonteCarlo
+
+
+class HMC(MonteCarlo):
+  def __init__(self, *args, **kwargs):
+    super(HMC, self).__init__(*args, **kwargs)
+    self._sampler = None
+
+  def initialize(self, step_size=0.25, n_steps=2, *args, **kwargs):
+    """hmc.py:45-59. Extra keyword-only options of this implementation (all optional):
+    `device` (CUDA device, default cuda:$LOCAL_RANK or the current device), `plan` ('auto' | 'persistent' |
+    'stepwise'), `row_sharded` (data passed to this rank is one shard of the rows; defaults to True when
+    torch.distributed is initialised with world_size > 1)."""
+    self.step_size = step_size
+    self.n_steps = n_steps
+    self._device = kwargs.pop('device', None)
+    self._plan = {'auto': _C.PLAN_AUTO, 'persistent': _C.PLAN_PERSISTENT, 'stepwise': _C.PLAN_STEPWISE}[
+        kwargs.pop('plan', 'auto')]
+    self._row_sharded = kwargs.pop('row_sharded', None)
+    return super(HMC, self).initialize(*args, **kwargs)
+
+  # ------------------------------------------------------------------------------------------
+  def build_update(self):
+    """hmc.py:61-130, built as a device-resident sampler rather than a graph."""
+    try:
+      self.latent_vars_unconstrained
+    except AttributeError:
+      raise ValueError("This implementation of HMC requires that all "
+                       "variables have unconstrained support. Please "
+                       "initialize with auto_transform=True to ensure "
+                       "this. (if your variables already have unconstrained "
+                       "support then doing this is a no-op).")
+    import torch
+    from ..engine import GLMSampler
+
+    model = recognize(self.latent_vars, self.data)
+    self._model = model
+    y_val = self.data[model.y_rv]
+    if isinstance(y_val, _g.Tensor):
+      y_val = _g.evaluate(y_val)
+    self._x_value = self._current_x({})
+    dev = self._device
+    if dev is None:
+      dev = "cuda:%d" % int(os.environ["LOCAL_RANK"]) if "LOCAL_RANK" in os.environ else "cuda"
+
+    import torch.distributed as dist
+    sharded = self._row_sharded
+    if sharded is None:
+      sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    n_global = None
+    if sharded:
+      cnt = torch.tensor([int(np.shape(self._x_value)[0])], dtype=torch.int64,
+                         device=dev if dist.get_backend() == "nccl" else "cpu")
+      dist.all_reduce(cnt)
+      n_global = int(cnt.item())
+
+    self._sampler = GLMSampler(model.spec, self._x_value, y_val, device=dev,
+                               plan=_C.PLAN_STEPWISE if sharded else self._plan, debug=self.debug,
+                               n_rows_global=n_global)
+    if sharded:
+      self._sampler.init_comm(dist.get_world_size(), dist.get_rank())
+    seed = get_seed()
+    if seed is not None:
+      self._sampler.seed(seed)
+
+    # Re-home the Empirical stores: one packed [T, P] device buffer, each latent's Variable a view of it.
+    T = self.n_iter
+    P = model.spec.n_params
+    self._packed = torch.zeros(T, P, dtype=torch.float32, device=self._sampler.dev)
+    for slot in model.slots:
+      variables = slot.qz.get_variables()
+      if not variables:
+        raise TypeError("Empirical random variables must be directly parameterized by a tf.Variable "
+                        "for HMC to update them (hmc.py:66-70).")
+      var = variables[0]
+      rows = int(var.shape[0])
+      view = self._packed[:rows, slot.offset] if slot.scalar and len(var.shape) == 1 \
+          else self._packed[:rows, slot.offset:slot.offset + slot.size]
+      var.rebind(view)
+    return self._train
+
+  def _current_x(self, feed_dict):
+    model = self._model
+    if model.x_node is None:
+      return np.ones((model.n_rows, 1), np.float32)
+    node = model.x_node
+    if node in feed_dict:
+      return feed_dict[node]
+    if node in self.data:
+      return self.data[node]
+    if isinstance(node, _g.Variable) and node.value_tensor() is not None:
+      return node.value_tensor()
+    return _g.evaluate(node)
+
+  def _train(self, feed_dict=None):
+    """One transition at the current `t` — the op `sess.run(self.train)` executes in the reference."""
+    self._maybe_rebind(feed_dict or {})
+    self._sampler.run(self._packed, self._t, 1, self.step_size, self.n_steps)
+
+  def _maybe_rebind(self, feed_dict):
+    x = self._current_x(feed_dict)
+    if x is not self._x_value:
+      # a different design matrix was fed for the placeholder (monte_carlo.py:134-136): upload it
+      from ..engine import GLMSampler
+      old = self._sampler
+      self._x_value = x
+      self._sampler = GLMSampler(self._model.spec, x, old.y, device=old.dev, plan=self._plan, debug=self.debug)
+      n_acc, _ = old.read_state()
+      self._n_accept_base = getattr(self, "_n_accept_base", 0) + n_acc
+      old.close()
+
+  # counters ----------------------------------------------------------------------------------
+  def _get_n_accept(self):
+    if self._sampler is None:
+      return 0
+    return self._sampler.read_state()[0] + getattr(self, "_n_accept_base", 0)
+
+  def _reset_n_accept(self):
+    self._n_accept_base = 0
+    if self._sampler is not None:
+      self._sampler.reset()
+
+  # driver ------------------------------------------------------------------------------------
+  def _run_loop(self):
+    """Inference.run's loop (inference.py:145-147) with the transitions between two progress reports
+    executed as ONE device launch: the observable behaviour (params rows, t, n_accept, the progress lines
+    at t == 1 and t % n_print == 0) is unchanged, the host round-trips per transition are gone."""
+    t = self._t
+    while t < self.n_iter:
+      if self.n_print == 0:
+        nxt = self.n_iter
+      elif t == 0:
+        nxt = 1
+      else:
+        nxt = min(self.n_iter, (t // self.n_print + 1) * self.n_print)
+      self._maybe_rebind({})
+      self._sampler.run(self._packed, t, nxt - t, self.step_size, self.n_steps)
+      with np.errstate(divide='ignore', invalid='ignore'):
+        accept_rate = np.float64(self._get_n_accept()) / np.float64(nxt - 1) if self.n_print != 0 else None
+      t = nxt
+      self._t = t
+      if self.n_print != 0:
+        self.print_progress({'t': t, 'accept_rate': accept_rate})
+    if self.n_print == 0:
+      self._sampler.read_state()  # synchronise: run() returns with the samples written
+
+  def finalize(self):
+    super(HMC, self).finalize()

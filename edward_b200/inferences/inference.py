@@ -1,0 +1,145 @@
+"""Inference base class — the drop-in surface of edward/inferences/inference.py:20-338: data binding,
+`run()` driver, the `t` counter, n_print / Progbar bookkeeping, reset ops, the auto-transform identity
+map for real-valued latents."""
+from __future__ import annotations
+
+import abc
+import os
+from datetime import datetime
+
+import numpy as np
+
+from .. import graph as _g
+from ..models.random_variable import RandomVariable
+from ..util.progbar import Progbar
+from ..util.random_variables import _is_array_like, _is_placeholder, check_data, check_latent_vars
+
+
+class Counter(_g.Tensor):
+  """Integer state of the inference (`t`, `n_accept`): a tf.Variable in the reference (inference.py:211,
+  monte_carlo.py:100). `getter`/`resetter` connect it to wherever the value really lives."""
+  op_type = "VariableV2"
+
+  def __init__(self, getter, resetter, name):
+    self._getter, self._resetter, self.name = getter, resetter, name
+    super(Counter, self).__init__((), _g.int32)
+
+  def _eval(self, feed):
+    return np.int32(self._getter())
+
+  def reset(self):
+    self._resetter()
+
+  def __int__(self):
+    return int(self._getter())
+
+
+class Inference(abc.ABC):
+  def __init__(self, latent_vars=None, data=None):
+    """inference.py:54-95."""
+    if latent_vars is None:
+      latent_vars = {}
+    if data is None:
+      data = {}
+    check_latent_vars(latent_vars)
+    self.latent_vars = latent_vars
+    check_data(data)
+    self.data = {}
+    for key, value in data.items():
+      if _is_placeholder(key):
+        self.data[key] = value
+      elif isinstance(key, (RandomVariable, _g.Tensor)):
+        if isinstance(value, (RandomVariable, _g.Tensor)):
+          self.data[key] = value
+        elif _is_array_like(value):
+          # stored once with the key's dtype (inference.py:88-95: placeholder(key.dtype) → Variable)
+          if isinstance(value, (float, list, int, np.ndarray, np.number, str)):
+            self.data[key] = np.asarray(value).astype(key.dtype.np)
+          else:
+            self.data[key] = value  # torch tensor: cast on the device when the sampler binds it
+
+  def run(self, variables=None, use_coordinator=True, *args, **kwargs):
+    """inference.py:97-154: initialize, (re-)initialise variables, n_iter × (update, print_progress),
+    finalize."""
+    self.initialize(*args, **kwargs)
+    if variables is None:
+      init = _g.global_variables_initializer()
+    else:
+      init = _g.variables_initializer(variables)
+    init.run()
+    self._run_loop()
+    self.finalize()
+
+  def _run_loop(self):
+    for _ in range(self.n_iter):
+      info_dict = self.update()
+      self.print_progress(info_dict)
+
+  @abc.abstractmethod
+  def initialize(self, n_iter=1000, n_print=None, scale=None, auto_transform=True, logdir=None,
+                 log_timestamp=True, log_vars=None, debug=False):
+    """inference.py:157-285."""
+    self.n_iter = int(n_iter)
+    if n_print is None:
+      self.n_print = int(n_iter / 100)
+    else:
+      self.n_print = n_print
+    self.progbar = Progbar(self.n_iter)
+    self._t = 0
+    self.t = Counter(lambda: self._t, self._reset_t, "iteration")
+
+    if scale is None:
+      scale = {}
+    elif not isinstance(scale, dict):
+      raise TypeError("scale must be a dict object.")
+    self.scale = scale
+
+    # Latents with real support paired with Empirical ('points') posteriors need no transformation:
+    # transform(z) returns z itself (util/random_variables.py:909-910), so both maps are the identity.
+    self.transformations = {}
+    if auto_transform:
+      latent_vars = self.latent_vars.copy()
+      self.latent_vars = {}
+      self.latent_vars_unconstrained = {}
+      for z, qz in latent_vars.items():
+        if hasattr(z, 'support') and hasattr(qz, 'support') and z.support != qz.support and qz.support != 'point':
+          if z.support != 'real':
+            raise NotImplementedError("auto_transform of constrained latents (support=%r) is outside the "
+                                      "HMC/GLM path built here" % (z.support,))
+          self.transformations[z] = z
+          self.latent_vars_unconstrained[z] = qz
+          self.latent_vars[z] = qz
+        else:
+          self.latent_vars[z] = qz
+          self.latent_vars_unconstrained[z] = qz
+      del latent_vars
+
+    if logdir is not None:
+      self.logging = True
+      if log_timestamp:
+        logdir = os.path.join(os.path.expanduser(logdir), datetime.strftime(datetime.utcnow(), "%Y%m%d_%H%M%S"))
+      os.makedirs(logdir, exist_ok=True)
+      self._logfile = open(os.path.join(logdir, "scalars.jsonl"), "w")
+    else:
+      self.logging = False
+    self.debug = debug
+    self.reset = [_g.variables_initializer([self.t])]
+
+  def _reset_t(self):
+    self._t = 0
+
+  @abc.abstractmethod
+  def update(self, feed_dict=None):
+    raise NotImplementedError
+
+  def print_progress(self, info_dict):
+    """inference.py:322-332."""
+    if self.n_print != 0:
+      t = info_dict['t']
+      if t == 1 or t % self.n_print == 0:
+        self.progbar.update(t)
+
+  def finalize(self):
+    """inference.py:334-338."""
+    if self.logging:
+      self._logfile.close()

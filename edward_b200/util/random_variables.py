@@ -9,6 +9,18 @@ from .. import graph as _g
 from ..models.random_variable import RandomVariable
 
 
+def _is_array_like(v):
+  """numpy values as in the reference, plus torch tensors (host or device) so data can be handed over
+  without a detour through numpy."""
+  if isinstance(v, (float, list, int, np.ndarray, np.number, str)):
+    return True
+  try:
+    import torch
+    return isinstance(v, torch.Tensor)
+  except ImportError:
+    return False
+
+
 def _is_placeholder(t):
   return isinstance(t, _g.Tensor) and "Placeholder" in t.op_type
 
@@ -33,8 +45,8 @@ def check_data(data):
           raise TypeError("Key-value pair in data does not have same shape: {}, {}".format(key.shape, value.shape))
         elif key.dtype != value.dtype:
           raise TypeError("Key-value pair in data does not have same dtype: {}, {}".format(key.dtype, value.dtype))
-      elif isinstance(value, (float, list, int, np.ndarray, np.number, str)):
-        if not key.shape.is_compatible_with(np.shape(value)):
+      elif _is_array_like(value):
+        if not key.shape.is_compatible_with(tuple(np.shape(value))):
           raise TypeError("Key-value pair in data does not have same shape: {}, {}".format(key.shape, np.shape(value)))
         elif isinstance(value, (np.ndarray, np.number)) and \
                 not np.issubdtype(value.dtype, np.floating) and \

@@ -1,0 +1,218 @@
+"""GPU tests of the drop-in surface: the reference's own HMC tests (tests/inferences/hmc_test.py) and
+example re-expressed against edward_b200, plus parity of ed.HMC's update()/run() against the oracle's
+restatement of monte_carlo.py / inference.py semantics."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import hmc_oracle as o
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(autouse=True)
+def fresh_graph():
+  from edward_b200 import graph as g
+  g.reset_default_graph()
+  yield
+
+
+def _imports():
+  import edward_b200 as ed
+  from edward_b200 import tfshim as tf
+  from edward_b200.models import Bernoulli, Empirical, Normal
+  return ed, tf, Bernoulli, Empirical, Normal
+
+
+@pytest.mark.parametrize("default", [True, False])
+def test_normal_normal(default):
+  """hmc_test.py:14-46 (float32 cases): 50 zeros, posterior N(0, 1/sqrt(51))."""
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  sess = ed.get_session()
+  x_data = np.array([0.0] * 50, dtype=np.float32)
+  mu = Normal(loc=tf.constant(0.0), scale=tf.constant(1.0))
+  x = Normal(loc=mu, scale=tf.constant(1.0), sample_shape=50)
+  n_samples = 2000
+  if not default:
+    qmu = Empirical(params=tf.Variable(tf.ones(n_samples)))
+    inference = ed.HMC({mu: qmu}, data={x: x_data})
+  else:
+    inference = ed.HMC([mu], data={x: x_data})
+    qmu = inference.latent_vars[mu]
+  inference.run(n_print=0)
+  np.testing.assert_allclose(qmu.mean().eval(), 0, rtol=1e-1, atol=1e-1)
+  np.testing.assert_allclose(qmu.stddev().eval(), np.sqrt(1 / 51), rtol=1e-1, atol=1e-1)
+  old_t, old_n_accept = sess.run([inference.t, inference.n_accept])
+  assert old_t == (n_samples if not default else 1e4)
+  assert old_n_accept > 0.1
+  sess.run(inference.reset)
+  new_t, new_n_accept = sess.run([inference.t, inference.n_accept])
+  assert new_t == 0
+  assert new_n_accept == 0
+
+
+@pytest.mark.parametrize("default", [True, False])
+def test_linear_regression(default):
+  """hmc_test.py:48-91 (float32 cases): N=40, D=10, Normal likelihood scale 0.1, step_size=0.01."""
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  sess = ed.get_session()
+  rng = np.random.RandomState(0)
+  N, D = 40, 10
+  w_true = rng.randn(D)
+  X_train = rng.randn(N, D)
+  y_train = np.dot(X_train, w_true) + rng.normal(0, 0.1, size=N)
+  X = tf.placeholder(tf.float32, [N, D])
+  w = Normal(loc=tf.zeros(D), scale=tf.ones(D))
+  b = Normal(loc=tf.zeros(1), scale=tf.ones(1))
+  y = Normal(loc=ed.dot(X, w) + b, scale=0.1 * tf.ones(N))
+  n_samples = 2000
+  if not default:
+    qw = Empirical(tf.Variable(tf.zeros([n_samples, D])))
+    qb = Empirical(tf.Variable(tf.zeros([n_samples, 1])))
+    inference = ed.HMC({w: qw, b: qb}, data={X: X_train, y: y_train})
+  else:
+    inference = ed.HMC([w, b], data={X: X_train, y: y_train})
+    qw = inference.latent_vars[w]
+    qb = inference.latent_vars[b]
+  inference.run(step_size=0.01, n_print=0)
+  np.testing.assert_allclose(qw.mean().eval(), w_true, rtol=5e-1, atol=5e-1)
+  np.testing.assert_allclose(qb.mean().eval(), [0.0], rtol=5e-1, atol=5e-1)
+  old_t, old_n_accept = sess.run([inference.t, inference.n_accept])
+  assert old_t == (n_samples if not default else 1e4)
+  assert old_n_accept > 0.1
+  sess.run(inference.reset)
+  assert sess.run([inference.t, inference.n_accept]) == [0, 0]
+
+
+def test_update_loop_semantics_and_progress(capsys):
+  """monte_carlo.py:111-158: update() returns t (after the increment) and accept_rate = n_accept / t_before;
+  transition t reads row max(t-1,0) and writes row t; progress lines appear at t == 1 and t % n_print == 0."""
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  N, D, T = 300, 5, 20
+  Xv, yv, _ = o.synth_data(N, D)
+  X = tf.placeholder(tf.float32, [N, D])
+  w = Normal(loc=tf.zeros(D), scale=tf.ones(D))
+  y = Bernoulli(logits=ed.dot(X, w))
+  qw = Empirical(params=tf.Variable(tf.zeros([T, D])))
+  inference = ed.HMC({w: qw}, data={X: Xv, y: yv})
+  inference.initialize(step_size=0.05, n_steps=3, n_print=5)
+  assert inference.n_iter == T and inference.n_print == 5
+  tf.global_variables_initializer().run()
+  prev = None
+  for i in range(T):
+    info = inference.update()
+    assert info['t'] == i + 1
+    n_acc = int(inference.n_accept.eval())
+    if i == 0:
+      assert not np.isfinite(info['accept_rate']) or np.isnan(info['accept_rate'])
+    else:
+      assert info['accept_rate'] == n_acc / i
+    inference.print_progress(info)
+    rows = qw.params.eval()
+    if prev is not None:
+      assert np.array_equal(rows[:i], prev[:i])  # earlier rows untouched
+    prev = rows.copy()
+  out = capsys.readouterr().out
+  assert "20/20 [100%]" in out and "Acceptance Rate" in out
+  with pytest.raises(IndexError):
+    inference.update()  # past the last Empirical row (hmc.py:125 scatter_update out of range)
+  inference.finalize()
+
+
+def test_run_equals_update_loop():
+  """run() executes the transitions between two progress reports as one launch; the samples must be the
+  same as stepping update() by hand (same seed → same device Philox stream)."""
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  from edward_b200 import graph as g
+  N, D, T = 2000, 54, 30
+  Xv, yv, _ = o.synth_data(N, D)
+  outs = []
+  for mode in ("run", "update"):
+    g.reset_default_graph()
+    ed.set_seed(7)
+    X = tf.placeholder(tf.float32, [N, D])
+    w = Normal(loc=tf.zeros(D), scale=tf.ones(D))
+    y = Bernoulli(logits=ed.dot(X, w))
+    qw = Empirical(params=tf.Variable(tf.zeros([T, D])))
+    inference = ed.HMC({w: qw}, data={X: Xv, y: yv})
+    if mode == "run":
+      inference.run(step_size=0.01, n_steps=4, n_print=7)
+    else:
+      inference.initialize(step_size=0.01, n_steps=4, n_print=0)
+      tf.global_variables_initializer().run()
+      for _ in range(inference.n_iter):
+        inference.update()
+    outs.append((qw.params.eval().copy(), int(inference.n_accept.eval()), int(inference.t.eval())))
+  assert np.array_equal(outs[0][0], outs[1][0])
+  assert outs[0][1:] == outs[1][1:]
+
+
+def test_bias_model_two_latents_matches_oracle_posterior():
+  """cfg 1 model (examples/bayesian_logistic_regression.py:41-51): w[1] and scalar b with Normal(0,3) priors.
+  The chain's posterior means must agree with a long float64 oracle chain."""
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  Xv, yv = o.toy_dataset_cfg1()
+  T = 4000
+  X = tf.placeholder(tf.float32, [40, 1])
+  w = Normal(loc=tf.zeros(1), scale=3.0 * tf.ones(1))
+  b = Normal(loc=tf.zeros([]), scale=3.0 * tf.ones([]))
+  y = Bernoulli(logits=ed.dot(X, w) + b)
+  qw = Empirical(params=tf.Variable(tf.zeros([T, 1])))
+  qb = Empirical(params=tf.Variable(tf.zeros([T])))
+  inference = ed.HMC({w: qw, b: qb}, data={X: Xv, y: yv})
+  inference.run(step_size=0.6, n_print=0)
+  spec = o.GLMSpec(1, True, o.BERNOULLI_LOGIT, np.zeros(2, np.float32), np.full(2, 3.0, np.float32))
+  r0, u = o.synth_draws(T, 2, seed=5)
+  p64 = np.zeros((T, 2))
+  o.run(Xv, yv, p64, r0, u, 0.6, 2, spec)
+  burn = 500
+  got = np.array([qw.params.eval()[burn:, 0].mean(), qb.params.eval()[burn:].mean()])
+  want = p64[burn:].mean(axis=0)
+  sd = p64[burn:].std(axis=0)
+  assert np.all(np.abs(got - want) < 0.35 * sd), (got, want, sd)
+  assert qw.params.eval().shape == (T, 1) and qb.params.eval().shape == (T,)
+
+
+def test_unsupported_models_are_rejected_not_emulated():
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  X = tf.placeholder(tf.float32, [10, 2])
+  w = Normal(loc=tf.zeros(2), scale=tf.ones(2))
+  y = Bernoulli(probs=tf.sigmoid(ed.dot(X, w)))  # probs parameterisation: not the hot path
+  qw = Empirical(params=tf.Variable(tf.zeros([5, 2])))
+  inf = ed.HMC({w: qw}, data={X: np.zeros((10, 2), np.float32), y: np.zeros(10)})
+  with pytest.raises(NotImplementedError):
+    inf.initialize()
+  with pytest.raises(ValueError):
+    ed.HMC({w: qw}, data={X: np.zeros((10, 2), np.float32), y: np.zeros(10)}).initialize(auto_transform=False)
+
+
+def test_dot_nonfinite_data_raises_at_bind():
+  """ed.dot's finite check (util/tensorflow.py:33-36) is done once, when the data are bound."""
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  Xv = np.zeros((10, 2), np.float32)
+  Xv[3, 1] = np.nan
+  X = tf.placeholder(tf.float32, [10, 2])
+  w = Normal(loc=tf.zeros(2), scale=tf.ones(2))
+  y = Bernoulli(logits=ed.dot(X, w))
+  qw = Empirical(params=tf.Variable(tf.zeros([5, 2])))
+  inf = ed.HMC({w: qw}, data={X: Xv, y: np.zeros(10)})
+  with pytest.raises(ValueError):
+    inf.initialize()
+
+
+def test_example_script_runs():
+  env = dict(os.environ, PYTHONPATH=ROOT)
+  res = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "bayesian_logistic_regression.py"), "--T", "400"],
+                       capture_output=True, text=True, env=env, timeout=600)
+  assert res.returncode == 0, res.stderr[-2000:]
+  assert "400/400 [100%]" in res.stdout and "posterior mean of w" in res.stdout
+
+
+def test_smoke_entry():
+  sys.path.insert(0, ROOT)
+  import __graft_entry__ as ge
+  ge.smoke()

@@ -1,0 +1,201 @@
+"""Pins the CPU oracle (oracle/hmc_oracle.py, oracle/hmc_ref.c) — CPU only.
+
+The reference holds no golden vectors for this path and TensorFlow cannot run here ("parity unpinned"),
+so the oracle is anchored on: independent densities (scipy.stats), finite differences, the reference's
+in-tree closed forms (edward/inferences/conjugacy/conjugate_log_probs.py:21-24,134-141), np.dot
+(tests/util/dot_test.py), the reference's statistical HMC tests (tests/inferences/hmc_test.py), and the
+committed golden fixtures (regression)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import hmc_oracle as o
+import ref_c
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _spec_from(d):
+  return o.GLMSpec(d["X"].shape[1], bool(d["has_bias"]), int(d["family"]), d["prior_loc"], d["prior_scale"],
+                   float(d["lik_scale"]))
+
+
+def test_densities_match_scipy():
+  rng = np.random.default_rng(0)
+  x = rng.standard_normal(100) * 3
+  loc, scale = rng.standard_normal(100), rng.random(100) + 0.1
+  np.testing.assert_allclose(o.normal_log_prob(x, loc, scale, np.float64), stats.norm.logpdf(x, loc, scale), rtol=1e-12)
+  l = rng.standard_normal(200) * 8
+  y = rng.integers(0, 2, 200)
+  p = 1 / (1 + np.exp(-l))
+  np.testing.assert_allclose(o.bernoulli_logit_log_prob(l, y, np.float64), stats.bernoulli.logpmf(y, p), rtol=1e-9, atol=1e-12)
+  k = rng.integers(0, 9, 200)
+  np.testing.assert_allclose(o.poisson_log_log_prob(l / 4, k, np.float64), stats.poisson.logpmf(k, np.exp(l / 4)), rtol=1e-10)
+  # extreme logits stay finite (the stable form of sigmoid_cross_entropy_with_logits)
+  assert np.all(np.isfinite(o.bernoulli_logit_log_prob(np.array([-200., 200., 0.]), np.array([1, 0, 1]), np.float32)))
+
+
+def test_densities_match_reference_closed_forms():
+  """conjugate_log_probs.py:21-24: x*log(p) + (1-x)*log1p(-p);  :134-141: expanded-square Normal."""
+  rng = np.random.default_rng(1)
+  l = rng.standard_normal(50) * 3
+  y = rng.integers(0, 2, 50).astype(np.float64)
+  p = 1 / (1 + np.exp(-l))
+  np.testing.assert_allclose(o.bernoulli_logit_log_prob(l, y, np.float64), y * np.log(p) + (1 - y) * np.log1p(-p), rtol=1e-10)
+  x, loc, scale = rng.standard_normal(50), rng.standard_normal(50), rng.random(50) + 0.2
+  var = scale ** 2
+  closed = -0.5 * np.log(2 * np.pi * var) - 0.5 * loc ** 2 / var + x * loc / var - 0.5 * x ** 2 / var
+  np.testing.assert_allclose(o.normal_log_prob(x, loc, scale, np.float64), closed, rtol=1e-9, atol=1e-12)
+
+
+def test_dot_matches_numpy_and_raises_on_inf():
+  """tests/util/dot_test.py:13-31."""
+  a = np.arange(25, dtype=np.float32).reshape(5, 5) * 0.1
+  b = np.arange(5, dtype=np.float32)
+  np.testing.assert_allclose(o.dot(a, b), np.dot(a, b), rtol=1e-6)
+  np.testing.assert_allclose(o.dot(b, a), np.dot(b, a), rtol=1e-6)
+  a2 = a.copy()
+  a2[0, 0] = np.inf
+  with pytest.raises(ValueError):
+    o.dot(a2, b)
+  b2 = b.copy()
+  b2[1] = np.inf
+  with pytest.raises(ValueError):
+    o.dot(a, b2)
+
+
+@pytest.mark.parametrize("family,bias", [(o.BERNOULLI_LOGIT, True), (o.NORMAL_IDENTITY, True), (o.POISSON_LOG, False)])
+def test_gradient_matches_finite_differences(family, bias):
+  rng = np.random.default_rng(2)
+  N, D = 200, 6
+  X = rng.standard_normal((N, D)).astype(np.float32)
+  y = rng.integers(0, 2, N) if family != o.NORMAL_IDENTITY else rng.standard_normal(N).astype(np.float32)
+  P = D + int(bias)
+  spec = o.GLMSpec(D, bias, family, rng.standard_normal(P).astype(np.float32), (rng.random(P) + 0.5).astype(np.float32), 0.8)
+  th = 0.3 * rng.standard_normal(P)
+  g = o.grad_log_joint(X, y, th, spec, np.float64)
+  h = 1e-6
+  for i in range(P):
+    e = np.zeros(P)
+    e[i] = h
+    fd = (o.log_joint(X, y, th + e, spec) - o.log_joint(X, y, th - e, spec)) / (2 * h)
+    assert abs(fd - g[i]) <= 1e-6 * max(1.0, abs(g[i])), (i, fd, g[i])
+
+
+def test_leapfrog_is_reversible_and_conserves_energy():
+  X, y, _ = o.synth_data(500, 8)
+  spec = o.GLMSpec(8)
+  z0 = np.zeros(8)
+  r0 = np.random.default_rng(3).standard_normal(8)
+  z1, r1 = o.leapfrog(X, y, z0, r0, 0.005, 20, spec)
+  zb, rb = o.leapfrog(X, y, z1, -r1, 0.005, 20, spec)
+  np.testing.assert_allclose(zb, z0, atol=1e-10)
+  np.testing.assert_allclose(-rb, r0, atol=1e-10)
+  h0 = -o.log_joint(X, y, z0, spec) + 0.5 * r0 @ r0
+  h1 = -o.log_joint(X, y, z1, spec) + 0.5 * r1 @ r1
+  assert abs(h1 - h0) < 0.05
+
+
+def test_oracle_samples_reference_posterior_normal_normal():
+  """tests/inferences/hmc_test.py:14-46 on the oracle: posterior N(0, 1/sqrt(51)); reference tolerances."""
+  N, T = 50, 2000
+  X = np.ones((N, 1), np.float32)
+  y = np.zeros(N, np.float32)
+  spec = o.GLMSpec(1, False, o.NORMAL_IDENTITY, np.zeros(1, np.float32), np.ones(1, np.float32), 1.0)
+  r0, u = o.synth_draws(T, 1, seed=11)
+  params = np.ones((T, 1))
+  infos, nacc = o.run(X, y, params, r0, u, 0.25, 2, spec)
+  np.testing.assert_allclose(o.empirical_mean(params), 0, rtol=1e-1, atol=1e-1)
+  np.testing.assert_allclose(o.empirical_stddev(params), np.sqrt(1 / 51), rtol=1e-1, atol=1e-1)
+  assert nacc > 0.1
+
+
+def test_oracle_samples_reference_posterior_linear_regression():
+  """tests/inferences/hmc_test.py:48-91 on the oracle (N=40, D=10, scale 0.1, step_size 0.01)."""
+  rng = np.random.RandomState(0)
+  N, D, T = 40, 10, 2000
+  w_true = rng.randn(D)
+  X = rng.randn(N, D).astype(np.float32)
+  y = (X @ w_true + rng.normal(0, 0.1, size=N)).astype(np.float32)
+  spec = o.GLMSpec(D, True, o.NORMAL_IDENTITY, np.zeros(D + 1, np.float32), np.ones(D + 1, np.float32), 0.1)
+  r0, u = o.synth_draws(T, D + 1, seed=12)
+  params = np.zeros((T, D + 1))
+  infos, nacc = o.run(X, y, params, r0, u, 0.01, 2, spec)
+  np.testing.assert_allclose(o.empirical_mean(params)[:D], w_true, rtol=5e-1, atol=5e-1)
+  np.testing.assert_allclose(o.empirical_mean(params)[D:], [0.0], rtol=5e-1, atol=5e-1)
+  assert nacc > 0.1
+
+
+def test_transition_row_semantics():
+  """Transition t reads row max(t-1,0), writes row t (hmc.py:81-85,121-126); running past T raises."""
+  X, y, _ = o.synth_data(100, 3)
+  spec = o.GLMSpec(3)
+  r0, u = o.synth_draws(4, 3)
+  params = np.zeros((3, 3))
+  params[0] = [0.1, -0.2, 0.3]
+  start = params[0].copy()
+  info = o.transition(X, y, params, 0, r0[0], u[0], 0.05, 2, spec)
+  assert np.allclose(params[0], info.proposal if info.accept else start)
+  with pytest.raises(IndexError):
+    o.run(X, y, params, r0, u, 0.05, 2, spec, t0=0, n_iter=4)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_reproduces_golden(path):
+  d = np.load(path)
+  spec = _spec_from(d)
+  X, y, T, L, eps = d["X"], d["y"], int(d["T"]), int(d["L"]), float(d["eps"])
+  for tag, dt, tol in (("f64", np.float64, 1e-12), ("f32", np.float32, 2e-5)):
+    np.testing.assert_allclose(o.log_joint(X, y, d["theta"], spec, dt), d["logp_theta_" + tag], rtol=tol)
+    g = o.grad_log_joint(X, y, d["theta"], spec, dt)
+    assert np.max(np.abs(g - d["grad_theta_" + tag])) <= tol * np.max(np.abs(g)) + 1e-12
+  params = np.zeros((T, spec.n_params))
+  infos, nacc = o.run(X, y, params, d["r0"], d["u"], eps, L, spec, np.float64)
+  np.testing.assert_allclose(params, d["params_f64"], rtol=1e-9, atol=1e-12)
+  assert nacc == int(d["n_accept_f64"])
+  np.testing.assert_array_equal([float(i.accept) for i in infos], d["trace_f64"][:, 6])
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "poisson" not in p],
+                         ids=[os.path.basename(p)[:-4] for p in GOLDEN if "poisson" not in p])
+def test_c_port_matches_golden(path):
+  """oracle/hmc_ref.c (float32, reference schedule) against the float64 golden values."""
+  d = np.load(path)
+  spec = _spec_from(d)
+  X, y, T, L, eps = d["X"], d["y"], int(d["T"]), int(d["L"]), float(d["eps"])
+  lp, g = ref_c.logp_grad(X, y, d["theta"], spec)
+  assert abs(lp - float(d["logp_theta_f64"])) <= 2e-5 * abs(float(d["logp_theta_f64"]))
+  assert np.max(np.abs(g - d["grad_theta_f64"])) <= 2e-5 * np.max(np.abs(d["grad_theta_f64"]))
+  params = np.zeros((T, spec.n_params), np.float32)
+  nacc, tr = ref_c.run(X, y, params, d["r0"], d["u"], eps, L, spec)
+  t64 = d["trace_f64"]
+  margin = np.abs(t64[:, 5] - t64[:, 4])
+  same = tr[:, 6] == t64[:, 6]
+  assert np.all(same | (margin < 1e-2)), (tr[:, 6], t64[:, 6], margin)
+  if np.all(same):
+    assert np.max(np.abs(params - d["params_f64"])) <= 2e-4 * max(np.max(np.abs(d["params_f64"])), 1e-3)
+    assert nacc == int(d["n_accept_f64"])
+
+
+def test_c_port_checknumerics_and_range():
+  X, y, _ = o.synth_data(64, 4)
+  spec = o.GLMSpec(4)
+  r0, u = o.synth_draws(2, 4)
+  Xb = X.copy()
+  Xb[5, 2] = np.inf
+  with pytest.raises(ValueError):
+    ref_c.run(Xb, y, np.zeros((2, 4), np.float32), r0, u, 0.1, 2, spec)
+  with pytest.raises(IndexError):
+    ref_c.run(X, y, np.zeros((1, 4), np.float32), r0, u, 0.1, 2, spec, n_iter=2)
+
+
+def test_synthetic_data_is_shard_invariant():
+  """rows generated in 65,536-row blocks seeded by block index → identical under any
+  block-aligned sharding."""
+  N, D = 65536 * 2 + 1000, 5
+  X, y, w = o.synth_data(N, D)
+  X2, y2, _ = o.synth_data(N - 65536, D, row_start=65536)
+  assert np.array_equal(X[65536:], X2) and np.array_equal(y[65536:], y2)
