@@ -76,11 +76,8 @@ def gen_device_rows(torch, dev, row_start, n_rows, D):
 
 
 def shard_bounds(N, world, rank):
-  """Contiguous shards on 65,536-row block boundaries."""
-  nblocks = (N + GEN_BLOCK - 1) // GEN_BLOCK
-  b0 = nblocks * rank // world
-  b1 = nblocks * (rank + 1) // world
-  return min(b0 * GEN_BLOCK, N), min(b1 * GEN_BLOCK, N)
+  from edward_b200.sharding import shard_bounds as sb
+  return sb(N, world, rank, GEN_BLOCK)
 
 
 class ClockSampler(object):
@@ -106,6 +103,9 @@ class ClockSampler(object):
       self.rows.append((time.time(), line.strip()))
 
   def start(self):
+    deadline = time.time() + 8.0
+    while self.proc and not self.rows and time.time() < deadline:  # nvidia-smi takes a moment to emit
+      time.sleep(0.05)
     self.t0 = time.time()
 
   def stop(self):
@@ -143,7 +143,17 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the reference's schedule in C/OpenMP (oracle/hmc_ref.c)
 # ------------------------------------------------------------------------------------------------
+_CPU_ROWS = {}
+
+
 def cpu_rows(wl, rows_cap):
+  key = (wl["N"], wl["D"], rows_cap)
+  if key not in _CPU_ROWS:
+    _CPU_ROWS[key] = _cpu_rows(wl, rows_cap)
+  return _CPU_ROWS[key]
+
+
+def _cpu_rows(wl, rows_cap):
   """Host copy of the first rows of the workload (numpy Philox stream; values differ from the device
   generator's, the shapes and distributions are the same — only the time matters here)."""
   sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -256,7 +266,6 @@ def main():
   barrier()
   sampler = ClockSampler(local_rank) if rank == 0 else None
   if sampler:
-    time.sleep(0.25)
     sampler.start()
   barrier()
   wall0 = time.perf_counter()
@@ -375,7 +384,7 @@ def main():
                  "rng": "device Philox", "grid_ctas": info["grid_ctas"], "ring_stages": info["ring_stages"], "tile_rows": info["tile_rows"]},
       "rows_steps_per_s": value * N,
       "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-      "clocks": clocks, "n_accept_last_step": n_accept, "wall_s": wall,
+      "clocks": clocks, "n_accept_total": n_accept, "wall_s": wall,
   }
   if n1_same is not None:
     line["n1_same_workload"] = n1_same

@@ -104,13 +104,12 @@ class GLMSampler:
   # ---- row shards (extension) -----------------------------------------------------------------
   def init_comm(self, nranks: int, rank: int, group=None):
     """Creates the NCCL communicator of this handle; the unique id travels over torch.distributed."""
-    import torch.distributed as dist
+    from .sharding import broadcast_bytes
     buf = (C.c_char * 128)()
     if rank == 0:
       _C.check(self.lib.edhmc_comm_unique_id(C.cast(buf, C.c_void_p)))
-    ids = [bytes(buf)]
-    dist.broadcast_object_list(ids, src=0, group=group)
-    idbuf = C.create_string_buffer(ids[0], 128)
+    uid = broadcast_bytes(bytes(buf), src=0, group=group)
+    idbuf = C.create_string_buffer(uid, 128)
     with torch.cuda.device(self.dev):
       _C.check(self.lib.edhmc_comm_init(self._h, C.cast(idbuf, C.c_void_p), int(nranks), int(rank)))
     self.nranks = int(nranks)
