@@ -52,13 +52,15 @@ __device__ __forceinline__ void write_trace(const KArgs& a, long long it, double
   }
 }
 
-template <int G, int V, int K>
-__global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
+template <int G, int V, int K, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
+  constexpr int kThreads = NW * 32;
+  constexpr int CT = kChainThreads;  // O(P) chain work is owned by the first 256 threads: same reduction order for every NW
   const bool single = (a.mode == 1);
   if (single && a.gate && !a.sc->need_init) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_last;
-  const SmemLayout sm = carve_smem(smem_raw, a);
+  const SmemLayout sm = carve_smem(smem_raw, a, NW);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = a.P, D = a.D;
   const int ncta = gridDim.x;
@@ -69,9 +71,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
   float* zc = g + ppad;
   float* gc = zc + ppad;
 
-  smem_setup(sm, a);
+  smem_setup(sm, a, NW);
+  const PlanRegs pr = plan_regs(a);
   const uint64_t policy = a.l2_hint ? l2_policy_evict_last() : 0ull;
-  const WarpTiles wt = warp_tiles(a, blockIdx.x * kWarpsPerCta + warp, ncta * kWarpsPerCta);
+  const WarpTiles wt = warp_tiles(a, blockIdx.x * NW + warp, ncta * NW);
   Ring ring;
   ring_init(ring, sm.ring + warp * a.S * a.stage_floats, sm.bars + warp * kMaxStages);
 
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
   // Metropolis–Hastings accept + Empirical write for transition `it` (hmc.py:100-126).
   auto finish_transition = [&]() {
     double ks = 0.0;
-    for (int c = tid; c < P; c += kThreads) ks += static_cast<double>(__fmul_rn(r[c], r[c]));
+    for (int c = tid; c < P && tid < CT; c += CT) ks += static_cast<double>(__fmul_rn(r[c], r[c]));
     const double k_new = 0.5 * block_sum_f64(ks, sm.red);
     const AcceptResult ar = mh_accept(k_old, k_new, logp_new, logp_cur, log_u);
     if (!isfinite(logp_new)) nonfinite = 1;
@@ -93,10 +96,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
     if (blockIdx.x == 0) {
       if (tid == 0) write_trace(a, it, logp_cur, logp_new, k_old, k_new, ar);
       if (a.trace_pos)
-        for (int c = tid; c < P; c += kThreads) a.trace_pos[it * P + c] = z[c];
+        for (int c = tid; c < P && tid < CT; c += CT) a.trace_pos[it * P + c] = z[c];
     }
     if (ar.accept) {
-      for (int c = tid; c < P; c += kThreads) {
+      for (int c = tid; c < P && tid < CT; c += CT) {
         zc[c] = z[c];
         gc[c] = g[c];
       }
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
       ++n_acc;
     }
     if (blockIdx.x == 0)
-      for (int c = tid; c < P; c += kThreads) a.params[t * a.ldp + c] = zc[c];
+      for (int c = tid; c < P && tid < CT; c += CT) a.params[t * a.ldp + c] = zc[c];
   };
 
   // Starts transition `it`: momentum draw, kinetic energy, first half kick + drift, theta for the pass.
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
     while (it < a.n_iter) {
       const long long t = a.t0 + it;
       double ks = 0.0;
-      for (int c = tid; c < P; c += kThreads) {
+      for (int c = tid; c < P && tid < CT; c += CT) {
         const float rv = a.r0 ? a.r0[it * P + c] : philox_normal(a.seed, t, c);  // hmc.py:88-91
         r[c] = rv;
         z[c] = zc[c];
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
       s = 0;
       logp_new = logp_cur;
       if (a.L > 0) {
-        for (int c = tid; c < P; c += kThreads) {
+        for (int c = tid; c < P && tid < CT; c += CT) {
           const float rn = kick(r[c], a.half_eps, g[c]);
           r[c] = rn;
           const float zn = drift(z[c], a.eps, rn);
@@ -140,12 +143,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
   };
 
   if (single) {
-    for (int c = tid; c < D; c += kThreads) sm.theta_s[c] = a.theta_in[c];
+    for (int c = tid; c < D && tid < CT; c += CT) sm.theta_s[c] = a.theta_in[c];
   } else {
     // current state: row max(t0-1,0) of the Empirical store (hmc.py:81-85) + cached (grad, logp)
     const long long t_prev = a.t0 > 0 ? a.t0 - 1 : 0;
     bool mismatch = false;
-    for (int c = tid; c < P; c += kThreads) {
+    for (int c = tid; c < P && tid < CT; c += CT) {
       const float v = a.params[t_prev * a.ldp + c];
       zc[c] = v;
       gc[c] = a.gcur[c];
@@ -164,10 +167,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
     ring.cpass = par0;
     ring.ipass = par0;
   }
-  ring_prologue(a, wt, ring, n_passes, lane, policy);
+  ring_prologue(pr, wt, ring, n_passes, lane, policy);
   if (!single) {
     if (in_init) {
-      for (int c = tid; c < D; c += kThreads) sm.theta_s[c] = zc[c];
+      for (int c = tid; c < D && tid < CT; c += CT) sm.theta_s[c] = zc[c];
     } else {
       start_next();
     }
@@ -179,21 +182,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
   for (long long pass = 0; pass < n_passes; ++pass) {
     const float* pos = single ? a.theta_in : (in_init ? zc : z);
     const float bias = a.has_bias ? pos[D] : 0.0f;
-    stream_pass<G, V, K>(a, wt, ring, sm.theta_s, bias, policy, sm.cta_acc);
+    stream_pass<G, V, K, NW>(a, pr, wt, ring, sm, bias, policy);
 
     if (single) {
       // last-arriving CTA folds the partials (threadFenceReduction pattern), fixed summation order
       double* mine = a.partials + static_cast<size_t>(blockIdx.x) * (P + 1);
       for (int c = tid; c <= P; c += kThreads) mine[c] = sm.cta_acc[c];
-      __threadfence();
       __syncthreads();
       if (tid == 0) {
+        __threadfence();  // cumulative: orders the whole CTA's partial writes (bar.sync above) before the ticket
         const unsigned int ticket = atomicAdd(a.ticket, 1u);
         s_last = (ticket == static_cast<unsigned int>(ncta - 1));
+        __threadfence();
       }
       __syncthreads();
       if (s_last) {
-        __threadfence();
         reduce_partials(a.partials, ncta, P, sm.cta_acc, sm.comb);
         for (int c = tid; c <= P; c += kThreads) a.sums[c] = sm.cta_acc[c];
         if (tid == 0) *a.ticket = 0u;
@@ -204,9 +207,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
     if (ncta > 1) {
       double* mine = a.partials + (static_cast<size_t>(bufsel) * ncta + blockIdx.x) * (P + 1);
       for (int c = tid; c <= P; c += kThreads) mine[c] = sm.cta_acc[c];
-      __threadfence();
       __syncthreads();
       if (tid == 0) {
+        // release (cumulative over the CTA's writes ordered by the bar.sync above) / acquire on one counter
         red_release_add_u64(a.bar, 1ull);
         const unsigned long long target = (epoch + 1) * static_cast<unsigned long long>(ncta);
         while (ld_acquire_u64(a.bar) < target) {
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
     // gradient and log joint at `pos`: likelihood totals + Normal prior (hmc.py:183-190)
     float* gout = in_init ? gc : g;
     double pl = 0.0;
-    for (int c = tid; c < P; c += kThreads) {
+    for (int c = tid; c < P && tid < CT; c += CT) {
       const float loc = a.prior_loc[c], sc = a.prior_scale[c];
       gout[c] = static_cast<float>(sm.cta_acc[c] + prior_grad(pos[c], loc, sc));
       pl += prior_quad(pos[c], loc, sc);
@@ -236,13 +239,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
     } else {
       ++s;
       if (s == a.L) {
-        for (int c = tid; c < P; c += kThreads) r[c] = kick(r[c], a.half_eps, g[c]);
+        for (int c = tid; c < P && tid < CT; c += CT) r[c] = kick(r[c], a.half_eps, g[c]);
         finish_transition();
         ++it;
         start_next();
       } else {
         // end of step s (hmc.py:207-208) and start of step s+1 (hmc.py:201-204): two separate half kicks
-        for (int c = tid; c < P; c += kThreads) {
+        for (int c = tid; c < P && tid < CT; c += CT) {
           const float rn = kick(kick(r[c], a.half_eps, g[c]), a.half_eps, g[c]);
           r[c] = rn;
           const float zn = drift(z[c], a.eps, rn);
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_hmc(const KArgs a) {
   }
 
   if (!single && blockIdx.x == 0) {
-    for (int c = tid; c < P; c += kThreads) {
+    for (int c = tid; c < P && tid < CT; c += CT) {
       a.zcur[c] = zc[c];
       a.gcur[c] = gc[c];
     }

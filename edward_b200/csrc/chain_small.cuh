@@ -4,11 +4,11 @@
 
 namespace edhmc {
 
-// ---- single-CTA chain kernels (<<<1, kThreads>>>) of the stepwise plan, on the global chain state ----
+// ---- single-CTA chain kernels (<<<1, kChainThreads>>>) of the stepwise plan, on the global chain state ----
 
 __device__ __forceinline__ double finish_gradient(const KArgs& a, const float* pos, float* gout, double* red) {
   double pl = 0.0;
-  for (int c = threadIdx.x; c < a.P; c += kThreads) {
+  for (int c = threadIdx.x; c < a.P; c += kChainThreads) {
     const float loc = a.prior_loc[c], sc = a.prior_scale[c];
     gout[c] = static_cast<float>(a.sums[c] + prior_grad(pos[c], loc, sc));
     pl += prior_quad(pos[c], loc, sc);
@@ -17,20 +17,20 @@ __device__ __forceinline__ double finish_gradient(const KArgs& a, const float* p
 }
 
 // Decides whether the cached (gcur, logp_cur) still describe params[max(t0-1,0)].
-__global__ void __launch_bounds__(kThreads, 1) k_chain_check(const KArgs a) {
+__global__ void __launch_bounds__(kChainThreads, 1) k_chain_check(const KArgs a) {
   const long long t_prev = a.t0 > 0 ? a.t0 - 1 : 0;
   bool mismatch = false;
-  for (int c = threadIdx.x; c < a.P; c += kThreads) {
+  for (int c = threadIdx.x; c < a.P; c += kChainThreads) {
     const float v = a.params[t_prev * a.ldp + c];
     if (__float_as_uint(v) != __float_as_uint(a.zcur[c])) mismatch = true;
   }
   const int need = __syncthreads_or((mismatch || !a.sc->valid) ? 1 : 0);
   if (need)
-    for (int c = threadIdx.x; c < a.P; c += kThreads) a.zcur[c] = a.params[t_prev * a.ldp + c];
+    for (int c = threadIdx.x; c < a.P; c += kChainThreads) a.zcur[c] = a.params[t_prev * a.ldp + c];
   if (threadIdx.x == 0) a.sc->need_init = need ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_chain_init_finish(const KArgs a) {
+__global__ void __launch_bounds__(kChainThreads, 1) k_chain_init_finish(const KArgs a) {
   __shared__ double red[64];
   if (!a.sc->need_init) return;
   const double lp = finish_gradient(a, a.zcur, a.gcur, red);
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_init_finish(const KArgs a
 __device__ __forceinline__ void chain_finish(const KArgs& a, long long it, float* gnew, double logp_new, double* red) {
   const long long t = a.t0 + it;
   double ks = 0.0;
-  for (int c = threadIdx.x; c < a.P; c += kThreads) ks += static_cast<double>(__fmul_rn(a.r[c], a.r[c]));
+  for (int c = threadIdx.x; c < a.P; c += kChainThreads) ks += static_cast<double>(__fmul_rn(a.r[c], a.r[c]));
   const double k_new = 0.5 * block_sum_f64(ks, red);
   const double logp_cur = a.sc->logp_cur;
   const double k_old = a.sc->k_old;
@@ -58,7 +58,7 @@ __device__ __forceinline__ void chain_finish(const KArgs& a, long long it, float
       a.sc->n_accept += 1;
     }
   }
-  for (int c = threadIdx.x; c < a.P; c += kThreads) {
+  for (int c = threadIdx.x; c < a.P; c += kChainThreads) {
     if (a.trace_pos) a.trace_pos[it * a.P + c] = a.z[c];
     if (ar.accept) {
       a.zcur[c] = a.z[c];
@@ -69,11 +69,11 @@ __device__ __forceinline__ void chain_finish(const KArgs& a, long long it, float
 }
 
 // Start of transition `it`: draw momentum and uniform, kinetic energy, first half kick + drift.
-__global__ void __launch_bounds__(kThreads, 1) k_chain_begin(const KArgs a, long long it, float* gwork) {
+__global__ void __launch_bounds__(kChainThreads, 1) k_chain_begin(const KArgs a, long long it, float* gwork) {
   __shared__ double red[64];
   const long long t = a.t0 + it;
   double ks = 0.0;
-  for (int c = threadIdx.x; c < a.P; c += kThreads) {
+  for (int c = threadIdx.x; c < a.P; c += kChainThreads) {
     const float rv = a.r0 ? a.r0[it * a.P + c] : philox_normal(a.seed, t, c);
     ks += static_cast<double>(__fmul_rn(rv, rv));
     float zz = a.zcur[c];
@@ -100,11 +100,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_begin(const KArgs a, long
 
 // After the pass (and all-reduce) of leapfrog step s: second half kick; then either the next step's
 // first half kick + drift, or the Metropolis–Hastings accept and the Empirical write.
-__global__ void __launch_bounds__(kThreads, 1) k_chain_leap(const KArgs a, long long it, int s, float* gwork) {
+__global__ void __launch_bounds__(kChainThreads, 1) k_chain_leap(const KArgs a, long long it, int s, float* gwork) {
   __shared__ double red[64];
   const double logp_new = finish_gradient(a, a.z, gwork, red);
   const bool last = (s == a.L - 1);
-  for (int c = threadIdx.x; c < a.P; c += kThreads) {
+  for (int c = threadIdx.x; c < a.P; c += kChainThreads) {
     float rr = kick(a.r[c], a.half_eps, gwork[c]);
     if (!last) {
       rr = kick(rr, a.half_eps, gwork[c]);
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_leap(const KArgs a, long 
 }
 
 // edhmc_logp_grad epilogue: prior + all-reduced sums → caller's buffers.
-__global__ void __launch_bounds__(kThreads, 1) k_logp_grad_finish(const KArgs a, const float* theta, double* logp_out,
+__global__ void __launch_bounds__(kChainThreads, 1) k_logp_grad_finish(const KArgs a, const float* theta, double* logp_out,
                                                                  float* grad_out) {
   __shared__ double red[64];
   const double lp = finish_gradient(a, theta, grad_out, red);

@@ -7,11 +7,16 @@
 
 namespace edhmc {
 
-constexpr int kWarpsPerCta = 8;            // consumer warps per CTA (each owns a private TMA ring)
-constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kMaxWarps = 16;   // consumer warps per CTA (each owns a private TMA ring): 8, 12 or 16
+constexpr int kChainThreads = 256;  // block size of the single-CTA chain kernels (stepwise plan)
 constexpr int kMaxStages = 8;
+constexpr int kXwFloats = 2048;  // per-CTA scratch for the one-shot cross-warp reduction (8 KB)
 constexpr int kMaxFeatures = 2048;
 constexpr unsigned kFull = 0xffffffffu;
+
+// Default warps per CTA as a function of the floats each lane keeps of a row (x, theta and gradient slices
+// live in registers, ~3*KV + 40): 16 warps under 128 registers/thread, 12 under 168, else 8.
+__host__ __device__ constexpr int warps_for(int kv) { return 3 * kv + 40 <= 128 ? 16 : (3 * kv + 40 <= 168 ? 12 : 8); }
 
 // Scalars of the chain that live in global memory between launches.
 struct ChainScalars {

@@ -96,23 +96,13 @@ static const int kNcclFloat64 = 8, kNcclSum = 0;
 // plan
 // ------------------------------------------------------------------------------------------------
 struct Plan {
-  int G = 0, V = 0, K = 0, Kact = 0, J = 0, RT = 0, S = 0, stage_floats = 0, y_off = 0, wpad = 0, tl = 0, tm = 0;
+  int G = 0, V = 0, K = 0, Kact = 0, NW = 0, J = 0, RT = 0, S = 0, stage_floats = 0, y_off = 0, wpad = 0, tl = 0, tm = 0;
   int grid = 0;
   size_t smem = 0;
   const void* fn = nullptr;
 };
 
-namespace edhmc {
-const void* lookup_g1_v1(int K);
-const void* lookup_g1_v2(int K);
-const void* lookup_g1_v4(int K);
-const void* lookup_g4_v1(int K);
-const void* lookup_g4_v2(int K);
-const void* lookup_g4_v4(int K);
-const void* lookup_g32_v1(int K);
-const void* lookup_g32_v2(int K);
-const void* lookup_g32_v4(int K);
-}  // namespace edhmc
+#include "inst_table.inc"
 
 struct edhmc_handle {
   edhmc_cfg cfg;
@@ -154,46 +144,67 @@ struct edhmc_handle {
   int plan_in_use = 0;
 };
 
-static const void* lookup_kernel(int G, int V, int K) {
-  switch (G * 10 + V) {
-    case 11: return lookup_g1_v1(K);
-    case 12: return lookup_g1_v2(K);
-    case 14: return lookup_g1_v4(K);
-    case 41: return lookup_g4_v1(K);
-    case 42: return lookup_g4_v2(K);
-    case 44: return lookup_g4_v4(K);
-    case 321: return lookup_g32_v1(K);
-    case 322: return lookup_g32_v2(K);
-    case 324: return lookup_g32_v4(K);
+// Shared-memory bank-conflict degree of the row loads for G lanes per row, vectors of V floats, row stride
+// ldx floats: lanes of one LDS phase (32/V lanes) hit bank groups of V words; returns the worst multiplicity.
+static int conflict_degree(long long ldx, int V, int G) {
+  const int phase = 32 / V;  // lanes served together by one shared-memory wavefront
+  int cnt[32] = {0};
+  int worst = 0;
+  for (int lane = 0; lane < phase; ++lane) {
+    const long long word = (lane / G) * ldx + static_cast<long long>(lane % G) * V;
+    const int slot = static_cast<int>((word / V) % phase);
+    if (++cnt[slot] > worst) worst = cnt[slot];
   }
-  return nullptr;
+  return worst;
 }
 
-static long long gcdll(long long a, long long b) { return b ? gcdll(b, a % b) : a; }
-
-// Chooses the streaming geometry: V = widest vector the row stride allows, G = fewest lanes per row
-// whose per-lane chunk count fits 64 floats, K = smallest compiled tier >= chunks per lane, tiles of
-// about 7 KB, and as many ring stages as shared memory holds next to the chain state.
+// Chooses the streaming geometry (restated in csrc/gen_inst.py, which instantiates every reachable kernel):
+// V = widest vector the row stride allows; G = 1 lane per row while the row fits 64 floats per lane (measured:
+// large tiles amortise the per-tile bookkeeping best), else the fewest lanes whose slice is <= 32 floats;
+// K = smallest compiled tier >= chunks per lane; warps per CTA from the register footprint (warps_for);
+// tiles sized so that >= 3 ring stages per warp fit in shared memory.
 static int make_plan(edhmc_handle* h) {
   const edhmc_cfg& c = h->cfg;
   Plan p;
   const int D = c.n_features;
   const long long ldx = c.ldx;
   p.V = (ldx % 4 == 0) ? 4 : (ldx % 2 == 0 ? 2 : 1);
-  const int kmax = 64 / p.V;
+  const int kmax = 64 / p.V, lim = 32 / p.V;
   const int chunks = (D + p.V - 1) / p.V;
-  const int gs[3] = {1, 4, 32};
+  const int gs[5] = {2, 4, 8, 16, 32};
+  int force_g = 0, force_nw = 0;
+  if (const char* e = getenv("EDHMC_FORCE_G")) force_g = atoi(e);
+  if (const char* e = getenv("EDHMC_FORCE_NW")) force_nw = atoi(e);
   p.G = 0;
-  for (int g : gs)
-    if ((chunks + g - 1) / g <= kmax) {
-      p.G = g;
-      break;
+  if (force_g > 0) {
+    if ((chunks + force_g - 1) / force_g <= kmax) p.G = force_g;
+  } else if (chunks <= kmax) {
+    // one lane per row: the largest tiles, no shuffles, no redundant link-function work — unless the row
+    // stride makes those loads collide on the same banks (e.g. 256-byte rows: 8-way); then spread a row
+    // over the fewest lanes that bring the conflict degree down to <= 2.
+    p.G = 1;
+    if (conflict_degree(ldx, p.V, 1) >= 4) {
+      const int alt[3] = {2, 4, 8};
+      for (int g : alt)
+        if (conflict_degree(ldx, p.V, g) <= 2) {
+          p.G = g;
+          break;
+        }
     }
+  } else {
+    for (int g : gs)
+      if ((chunks + g - 1) / g <= lim) {
+        p.G = g;
+        break;
+      }
+    if (!p.G && (chunks + 31) / 32 <= kmax) p.G = 32;
+  }
   if (!p.G) return fail(EDHMC_ERR_INVALID, "n_features=%d exceeds the supported maximum of %d", D, kMaxFeatures);
   p.Kact = (chunks + p.G - 1) / p.G;
-  static const int tiers4[] = {1, 2, 4, 8, 12, 16}, tiers2[] = {1, 2, 4, 8, 16, 24, 27, 32}, tiers1[] = {1, 2, 4, 8, 16, 32, 64};
+  static const int tiers4[] = {1, 2, 3, 4, 5, 6, 7, 8, 12, 16}, tiers2[] = {1, 2, 4, 6, 8, 10, 12, 14, 16, 24, 27, 32},
+                   tiers1[] = {1, 2, 4, 8, 16, 28, 32, 64};
   const int* tiers = p.V == 4 ? tiers4 : (p.V == 2 ? tiers2 : tiers1);
-  const int ntier = p.V == 4 ? 6 : (p.V == 2 ? 8 : 7);
+  const int ntier = p.V == 4 ? 10 : (p.V == 2 ? 12 : 8);
   p.K = 0;
   for (int i = 0; i < ntier; ++i)
     if (tiers[i] >= p.Kact) {
@@ -201,12 +212,19 @@ static int make_plan(edhmc_handle* h) {
       break;
     }
   if (!p.K) return fail(EDHMC_ERR_INVALID, "internal: no tier for %d chunks", p.Kact);
-  p.fn = lookup_kernel(p.G, p.V, p.K);
-  if (!p.fn) return fail(EDHMC_ERR_INVALID, "internal: no kernel for G=%d V=%d K=%d", p.G, p.V, p.K);
+  p.NW = force_nw > 0 ? force_nw : warps_for(p.K * p.V);
+  p.fn = lookup_kernel(p.G, p.V, p.K, p.NW);
+  if (!p.fn) return fail(EDHMC_ERR_INVALID, "no kernel compiled for G=%d V=%d K=%d NW=%d", p.G, p.V, p.K, p.NW);
   p.wpad = p.G * p.K * p.V;
   const int RPS = 32 / p.G;
   const long long row_bytes = ldx * 4;
-  long long J = 7168 / (RPS * row_bytes);
+  const size_t budget = static_cast<size_t>(h->smem_optin) - 1024;
+  size_t offs[8];
+  const size_t fixed = smem_layout_bytes(p.NW, 0, 0, h->P, p.wpad, offs);
+  if (fixed + 4096 > budget) return fail(EDHMC_ERR_INVALID, "chain state does not fit shared memory");
+  long long tile_target = static_cast<long long>((budget - fixed) / (static_cast<size_t>(p.NW) * 3));
+  if (tile_target > 7168) tile_target = 7168;
+  long long J = tile_target / (RPS * row_bytes);
   if (J < 1) J = 1;
   if (J > 8) J = 8;
   p.J = static_cast<int>(J);
@@ -223,23 +241,20 @@ static int make_plan(edhmc_handle* h) {
   sf = (sf + 31) / 32 * 32;
   p.stage_floats = static_cast<int>(sf);
 
-  const size_t budget = static_cast<size_t>(h->smem_optin) - 1024;
-  size_t offs[7];
   int S = kMaxStages;
   for (; S >= 1; --S)
-    if (smem_layout_bytes(S, p.stage_floats, h->P, p.wpad, offs) <= budget) break;
+    if (smem_layout_bytes(p.NW, S, p.stage_floats, h->P, p.wpad, offs) <= budget) break;
   if (S < 2) return fail(EDHMC_ERR_INVALID, "row of %lld bytes does not fit the shared-memory ring", row_bytes);
   p.S = S;
-  p.smem = smem_layout_bytes(p.S, p.stage_floats, h->P, p.wpad, offs);
+  p.smem = smem_layout_bytes(p.NW, p.S, p.stage_floats, h->P, p.wpad, offs);
   cudaError_t e = cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem));
   if (e != cudaSuccess) return fail(EDHMC_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", p.smem, cudaGetErrorString(e));
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p.fn, kThreads, p.smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p.fn, p.NW * 32, p.smem);
   if (e != cudaSuccess) return fail(EDHMC_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
   if (per_sm < 1) return fail(EDHMC_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", p.smem);
   // grid: one CTA per SM, fewer when there are not enough rows to give every warp two tiles
-  long long want = (c.n_rows + static_cast<long long>(kWarpsPerCta) * 2 * p.RT - 1) /
-                   (static_cast<long long>(kWarpsPerCta) * 2 * p.RT);
+  long long want = (c.n_rows + static_cast<long long>(p.NW) * 2 * p.RT - 1) / (static_cast<long long>(p.NW) * 2 * p.RT);
   if (want < 1) want = 1;
   p.grid = static_cast<int>(want < h->num_sms ? want : h->num_sms);
   h->plan = p;
@@ -451,7 +466,7 @@ static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int 
   aa.par0 = static_cast<int>(gsi & 1);
   aa.theta_in = theta;
   void* params[] = {&aa};
-  CUDA_TRY(cudaLaunchKernel(h->plan.fn, dim3(h->plan.grid), dim3(kThreads), params, h->plan.smem, stream));
+  CUDA_TRY(cudaLaunchKernel(h->plan.fn, dim3(h->plan.grid), dim3(h->plan.NW * 32), params, h->plan.smem, stream));
   ++h->launches_last;
   return 0;
 }
@@ -477,7 +492,7 @@ int edhmc_logp_grad(edhmc_t* h, const float* theta, double* logp, float* grad, v
   if (rc) return rc;
   rc = allreduce_sums(h, stream);
   if (rc) return rc;
-  k_logp_grad_finish<<<1, kThreads, 0, stream>>>(a, theta, logp, grad);
+  k_logp_grad_finish<<<1, kChainThreads, 0, stream>>>(a, theta, logp, grad);
   CUDA_TRY(cudaGetLastError());
   ++h->launches_last;
   return 0;
@@ -518,25 +533,25 @@ int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int
     CUDA_TRY(cudaMemsetAsync(h->d_bar, 0, sizeof(unsigned long long), stream));
     void* kp[] = {&a};
     a.mode = 0;
-    CUDA_TRY(cudaLaunchCooperativeKernel(h->plan.fn, dim3(h->plan.grid), dim3(kThreads), kp, h->plan.smem, stream));
+    CUDA_TRY(cudaLaunchCooperativeKernel(h->plan.fn, dim3(h->plan.grid), dim3(h->plan.NW * 32), kp, h->plan.smem, stream));
     ++h->launches_last;
   } else {
     int rc;
-    k_chain_check<<<1, kThreads, 0, stream>>>(a);
+    k_chain_check<<<1, kChainThreads, 0, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     if ((rc = launch_pass(h, a, h->d_zcur, 1, t0 * n_steps - 1, stream))) return rc;
     if ((rc = allreduce_sums(h, stream))) return rc;
-    k_chain_init_finish<<<1, kThreads, 0, stream>>>(a);
+    k_chain_init_finish<<<1, kChainThreads, 0, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     h->launches_last += 2;
     for (int64_t it = 0; it < n_iter; ++it) {
-      k_chain_begin<<<1, kThreads, 0, stream>>>(a, it, h->d_g);
+      k_chain_begin<<<1, kChainThreads, 0, stream>>>(a, it, h->d_g);
       CUDA_TRY(cudaGetLastError());
       ++h->launches_last;
       for (int s = 0; s < n_steps; ++s) {
         if ((rc = launch_pass(h, a, h->d_z, 0, (t0 + it) * n_steps + s, stream))) return rc;
         if ((rc = allreduce_sums(h, stream))) return rc;
-        k_chain_leap<<<1, kThreads, 0, stream>>>(a, it, s, h->d_g);
+        k_chain_leap<<<1, kChainThreads, 0, stream>>>(a, it, s, h->d_g);
         CUDA_TRY(cudaGetLastError());
         ++h->launches_last;
       }
@@ -609,7 +624,7 @@ int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t 
 int edhmc_plan_info(edhmc_t* h, int64_t* out, int32_t cap) {
   if (!h || !out) return fail(EDHMC_ERR_INVALID, "null argument");
   const int64_t v[10] = {h->plan.grid,
-                         kWarpsPerCta,
+                         h->plan.NW,
                          h->plan.S,
                          h->plan.RT,
                          h->plan.G,

@@ -12,11 +12,13 @@
 // no CTA-wide synchronisation in the main loop, and the ring keeps prefetching the NEXT pass's tiles
 // while the grid synchronises on the current pass's reduction.
 //
-// Work decomposition inside a warp: a row is handled by G lanes (G = 1, 4 or 32); lane `lg` of the
-// group owns vector chunks k*G+lg (k < K, K a compile-time tier) of V floats each, i.e. 128-/64-/32-bit
-// shared loads, and the arithmetic is packed FFMA2 (two fp32 FMAs per instruction) when V >= 2.
+// Work decomposition inside a warp: a row is handled by G lanes (G = 1..32, power of two); lane `lg` of
+// the group owns vector chunks k*G+lg (k < K, K a compile-time tier) of V floats each, i.e. 128-/64-/
+// 32-bit shared loads, and the arithmetic is packed FFMA2 (two fp32 FMAs per instruction) when V >= 2.
 // theta is zero-padded to G*K*V entries, so padded columns contribute 0 to the dot product and their
-// gradient accumulators are simply never written out.
+// gradient accumulators are simply never written out. The planner picks the smallest G whose per-lane
+// slice (K*V floats) keeps the kernel under 128 registers, so that 16 warps per SM hide the latency of the
+// dependent FMA / MUFU chains; wide rows fall back to 12 or 8 warps.
 #pragma once
 #include <type_traits>
 
@@ -51,20 +53,20 @@ __device__ __forceinline__ WarpTiles warp_tiles(const KArgs& a, int gw, int tota
 }
 
 struct Ring {
-  float* base;     // first stage of this warp
-  uint64_t* bars;  // S mbarriers of this warp
+  uint32_t base_s;  // shared-window address of this warp's first stage
+  uint32_t bars_s;  // shared-window address of this warp's S mbarriers
   // consumer cursor
   int stage;
   uint32_t parity;
-  int cpass;  // pass index of the tile being consumed (for the zig-zag order)
+  int cpass;  // parity source of the pass being consumed (zig-zag order)
   // producer cursor
   long long qi, q_total;  // next tile to issue / tiles in this launch
   int ipass, ik, istage;
 };
 
 __device__ __forceinline__ void ring_init(Ring& ring, float* base, uint64_t* bars) {
-  ring.base = base;
-  ring.bars = bars;
+  ring.base_s = smem_u32(base);
+  ring.bars_s = smem_u32(bars);
   ring.stage = 0;
   ring.parity = 0;
   ring.cpass = 0;
@@ -75,38 +77,59 @@ __device__ __forceinline__ void ring_init(Ring& ring, float* base, uint64_t* bar
   ring.istage = 0;
 }
 
+// Loop-invariant plan constants, hoisted into registers once per kernel.
+struct PlanRegs {
+  int stage_bytes, y_off_bytes, RT, tm, tl, S, ldx, D, zigzag, l2_hint;
+};
+__device__ __forceinline__ PlanRegs plan_regs(const KArgs& a) {
+  PlanRegs p;
+  p.stage_bytes = a.stage_floats * 4;
+  p.y_off_bytes = a.y_off * 4;
+  p.RT = a.RT;
+  p.tm = a.tm;
+  p.tl = a.tl;
+  p.S = a.S;
+  p.ldx = a.ldx_i;
+  p.D = a.D;
+  p.zigzag = a.zigzag;
+  p.l2_hint = a.l2_hint;
+  return p;
+}
+
 // Issues the next tile of this warp's sequence into stage `istage`. Called by ALL lanes of the warp
 // (converged): every lane copies its share of the y slice, lane 0 launches the bulk copy of X.
 // A tile whose first float is not 16-byte aligned (possible only when ldx % 4 != 0) is copied from the
 // aligned address below it; the consumer skips the same `m` leading floats.
-__device__ __forceinline__ void ring_issue(const KArgs& a, const WarpTiles& wt, Ring& ring, int lane, uint64_t policy) {
-  const int kk = (a.zigzag && (ring.ipass & 1)) ? (wt.nt - 1 - ring.ik) : ring.ik;
+__device__ __forceinline__ void ring_issue(const PlanRegs& pr, const WarpTiles& wt, Ring& ring, int lane, uint64_t policy) {
+  const int kk = (pr.zigzag && (ring.ipass & 1)) ? (wt.nt - 1 - ring.ik) : ring.ik;
   const bool last = (kk == wt.nt - 1);
-  const int rows = last ? wt.rows_last : a.RT;
-  float* sb = ring.base + ring.istage * a.stage_floats;
-  uint64_t* bar = ring.bars + ring.istage;
-  const char* ysrc = wt.y0 + static_cast<long long>(kk) * (a.RT * 4);
-  for (int e = lane; e < rows; e += 32) cp_async4(sb + a.y_off + e, ysrc + e * 4);
-  cp_async_mbar_arrive_noinc(bar);
+  const int rows = last ? wt.rows_last : pr.RT;
+  const uint32_t sb = ring.base_s + ring.istage * pr.stage_bytes;
+  const uint32_t bar = ring.bars_s + ring.istage * 8;
+  const char* ysrc = wt.y0 + (static_cast<long long>(kk) * pr.RT + lane) * 4;
+  const uint32_t ydst = sb + pr.y_off_bytes + lane * 4;
+  if (lane < rows) cp_async4_s(ydst, ysrc);
+  for (int e = 32; lane + e < rows; e += 32) cp_async4_s(ydst + e * 4, ysrc + e * 4);
+  cp_async_mbar_arrive_noinc_s(bar);
   if (lane == 0) {
-    const int m = (kk * a.tm) & 3;
-    const float* src = wt.x0 + static_cast<long long>(kk) * a.tl - m;
+    const int m = (kk * pr.tm) & 3;
+    const float* src = wt.x0 + static_cast<long long>(kk) * pr.tl - m;
     uint32_t bytes;
     if (last && wt.tail) {
       // never read past the last valid float of X: bulk-copy the 16-byte multiple, finish with scalar copies
-      const int nfl = m + (rows - 1) * a.ldx_i + a.D;
+      const int nfl = m + (rows - 1) * pr.ldx + pr.D;
       bytes = static_cast<uint32_t>(nfl * 4) & ~15u;
-      for (int i = bytes >> 2; i < nfl; ++i) sb[i] = __ldg(src + i);
+      for (int i = bytes >> 2; i < nfl; ++i) sts_f32(sb + i * 4, __ldg(src + i));
     } else {
-      bytes = (static_cast<uint32_t>((m + rows * a.ldx_i) * 4) + 15u) & ~15u;
+      bytes = (static_cast<uint32_t>((m + rows * pr.ldx) * 4) + 15u) & ~15u;
     }
     fence_proxy_async_smem();
-    mbar_arrive_expect_tx(bar, bytes);
+    mbar_arrive_expect_tx_s(bar, bytes);
     if (bytes) {
-      if (a.l2_hint)
-        bulk_g2s_hint(sb, src, bytes, bar, policy);
+      if (pr.l2_hint)
+        bulk_g2s_hint_s(sb, src, bytes, bar, policy);
       else
-        bulk_g2s(sb, src, bytes, bar);
+        bulk_g2s_s(sb, src, bytes, bar);
     }
   }
   ++ring.qi;
@@ -114,14 +137,14 @@ __device__ __forceinline__ void ring_issue(const KArgs& a, const WarpTiles& wt, 
     ring.ik = 0;
     ++ring.ipass;
   }
-  if (++ring.istage == a.S) ring.istage = 0;
+  if (++ring.istage == pr.S) ring.istage = 0;
 }
 
 // Fills the ring at the start of a launch (all lanes).
-__device__ __forceinline__ void ring_prologue(const KArgs& a, const WarpTiles& wt, Ring& ring, long long n_passes, int lane,
-                                              uint64_t policy) {
+__device__ __forceinline__ void ring_prologue(const PlanRegs& pr, const WarpTiles& wt, Ring& ring, long long n_passes,
+                                              int lane, uint64_t policy) {
   ring.q_total = n_passes * wt.nt;
-  for (int s = 0; s < a.S && ring.qi < ring.q_total; ++s) ring_issue(a, wt, ring, lane, policy);
+  for (int s = 0; s < pr.S && ring.qi < ring.q_total; ++s) ring_issue(pr, wt, ring, lane, policy);
 }
 
 // ---- packed helpers -------------------------------------------------------------------------------
@@ -153,6 +176,28 @@ __device__ __forceinline__ void load_chunks(const float* p, int cstride, typenam
   }
 }
 
+// Same, from a 32-bit shared-window address with compile-time chunk stride CS (floats): explicit ld.shared
+// with immediate offsets, so the hot loop carries one address register per row.
+template <int V, int K, int CS>
+struct ChunkLoader {
+  template <int k>
+  static __device__ __forceinline__ void step(uint32_t addr, typename Acc<V>::type* out) {
+    if constexpr (k < K) {
+      if constexpr (V == 1) {
+        out[k] = lds_f32<k * CS * 4>(addr);
+      } else if constexpr (V == 2) {
+        out[k] = lds_f32x2<k * CS * 4>(addr);
+      } else {
+        const float4 t = lds_f32x4<k * CS * 4>(addr);
+        out[2 * k] = make_float2(t.x, t.y);
+        out[2 * k + 1] = make_float2(t.z, t.w);
+      }
+      step<k + 1>(addr, out);
+    }
+  }
+  static __device__ __forceinline__ void load(uint32_t addr, typename Acc<V>::type* out) { step<0>(addr, out); }
+};
+
 template <int V, int NA>
 __device__ __forceinline__ float flat(const typename Acc<V>::type* g, int i) {
   if constexpr (V == 1) {
@@ -162,22 +207,92 @@ __device__ __forceinline__ float flat(const typename Acc<V>::type* g, int i) {
   }
 }
 
+__host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
+
+// Shared-memory carve-up.
+struct SmemLayout {
+  float* ring;
+  uint64_t* bars;
+  double* cta_acc;
+  double* red;
+  double* comb;
+  float* theta_s;
+  float* state;  // 5 * ppad floats
+  float* xw;     // kXwFloats floats + 2*kMaxWarps doubles: one-shot cross-warp reduction scratch
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline size_t smem_layout_bytes(int nw, int S, int stage_floats, int P, int wpad, size_t* offs /*8*/) {
+  size_t off = 0;
+  offs[0] = off;
+  off += static_cast<size_t>(nw) * S * stage_floats * 4;
+  off = align_up(off, 128);
+  offs[1] = off;
+  off += static_cast<size_t>(kMaxWarps) * kMaxStages * 8;
+  offs[2] = off;
+  off += align_up(static_cast<size_t>(P + 1) * 8, 16);
+  offs[3] = off;
+  off += 64 * 8;
+  offs[4] = off;
+  off += static_cast<size_t>(kMaxWarps) * 32 * 8;
+  offs[5] = off;
+  off += align_up(static_cast<size_t>(wpad) * 4, 16);
+  offs[6] = off;
+  off += 5 * align_up(static_cast<size_t>(P) * 4, 16);
+  offs[7] = off;
+  off += static_cast<size_t>(kXwFloats) * 4 + 2 * kMaxWarps * 8;
+  return align_up(off, 128);
+}
+
+__device__ __forceinline__ SmemLayout carve_smem(unsigned char* raw, const KArgs& a, int nw) {
+  size_t offs[8];
+  smem_layout_bytes(nw, a.S, a.stage_floats, a.P, a.wpad, offs);
+  SmemLayout L;
+  L.ring = reinterpret_cast<float*>(raw + offs[0]);
+  L.bars = reinterpret_cast<uint64_t*>(raw + offs[1]);
+  L.cta_acc = reinterpret_cast<double*>(raw + offs[2]);
+  L.red = reinterpret_cast<double*>(raw + offs[3]);
+  L.comb = reinterpret_cast<double*>(raw + offs[4]);
+  L.theta_s = reinterpret_cast<float*>(raw + offs[5]);
+  L.state = reinterpret_cast<float*>(raw + offs[6]);
+  L.xw = reinterpret_cast<float*>(raw + offs[7]);
+  return L;
+}
+
+// Zero the ring (so padded / stale columns are finite), init the mbarriers, zero theta_s.
+__device__ __forceinline__ void smem_setup(const SmemLayout& L, const KArgs& a, int nw) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int nring = nw * a.S * a.stage_floats;
+  for (int i = tid; i < nring; i += nthr) L.ring[i] = 0.0f;
+  for (int i = tid; i < a.wpad; i += nthr) L.theta_s[i] = 0.0f;
+  if (tid < kMaxWarps * kMaxStages) mbar_init(L.bars + tid, 33);  // 32 cp.async arrivals + 1 expect_tx arrival
+  fence_mbar_init();
+  fence_proxy_async_smem();
+  __syncthreads();
+}
+
 // One pass of this CTA over its rows. On return cta_acc[0..D) = Σ r_n·X[n,:], cta_acc[D] = Σ r_n (if
 // has_bias), cta_acc[P] = Σ log p(y_n|eta_n) over the CTA's rows, all float64, reduced in a fixed
 // order (bitwise reproducible). Ends with a __syncthreads().
-template <int G, int V, int K>
-__device__ __forceinline__ void stream_pass(const KArgs& a, const WarpTiles& wt, Ring& ring, const float* theta_s,
-                                            float bias, uint64_t policy, double* cta_acc) {
+// Register cap per thread for NW warps of 32 threads with one CTA per SM.
+__host__ __device__ constexpr int reg_cap(int nw) { return nw >= 16 ? 128 : (nw >= 12 ? 168 : 255); }
+
+template <int G, int V, int K, int NW>
+__device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, const WarpTiles& wt, Ring& ring,
+                                            const SmemLayout& sm, float bias, uint64_t policy) {
   constexpr int RPS = 32 / G;  // rows processed concurrently by a warp
   constexpr int KV = K * V;
-  constexpr int NA = (V == 1) ? KV : KV / 2;  // packed accumulators per lane
-  constexpr bool WREG = (KV <= 56);           // theta slice held in registers
+  constexpr int NA = (V == 1) ? KV : KV / 2;          // packed accumulators per lane
+  constexpr bool WREG = (3 * KV + 40 <= reg_cap(NW));  // theta slice held in registers, else re-read from smem
   using acc_t = typename Acc<V>::type;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lg = lane & (G - 1), grp = lane / G;
-  const int ldx = a.ldx_i;
   const int family = a.family;
   const float lik_scale = a.lik_scale;
+  const int y_dtype = a.y_dtype;
+  const float* theta_s = sm.theta_s;
+  double* cta_acc = sm.cta_acc;
 
   acc_t g[NA];
   acc_t w[WREG ? NA : 1];
@@ -189,33 +304,40 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const WarpTiles& wt,
       g[i] = make_float2(0.0f, 0.0f);
   }
   if constexpr (WREG) load_chunks<V, K>(theta_s + lg * V, G * V, w);
+  const uint32_t theta_lane_s = smem_u32(theta_s) + lg * V * 4;
   float gb = 0.0f;
   double lp = 0.0;
 
-  const bool backward = a.zigzag && (ring.cpass & 1);
+  const bool backward = pr.zigzag && (ring.cpass & 1);
+  const int row_bytes = pr.ldx * 4;
+  const uint32_t lane_off = grp * row_bytes + lg * V * 4;
   for (int kt = 0; kt < wt.nt; ++kt) {
     const int kk = backward ? (wt.nt - 1 - kt) : kt;
-    const int rows = (kk == wt.nt - 1) ? wt.rows_last : a.RT;
-    const int m = (kk * a.tm) & 3;
-    const float* sb = ring.base + ring.stage * a.stage_floats;
-    mbar_wait(ring.bars + ring.stage, ring.parity);
-    const uint32_t* ys = reinterpret_cast<const uint32_t*>(sb + a.y_off);
-    const float* xbase = sb + m + grp * ldx + lg * V;
+    const int rows = (kk == wt.nt - 1) ? wt.rows_last : pr.RT;
+    const int m = (kk * pr.tm) & 3;
+    const uint32_t sb = ring.base_s + ring.stage * pr.stage_bytes;
+    mbar_wait_s(ring.bars_s + ring.stage * 8, ring.parity);
+    const uint32_t ys = sb + pr.y_off_bytes;
+    uint32_t xaddr = sb + m * 4 + lane_off;
 
-    for (int j0 = 0; j0 < rows; j0 += RPS) {  // warp-uniform
+    for (int j0 = 0; j0 < rows; j0 += RPS, xaddr += RPS * row_bytes) {  // warp-uniform
       const int lr = j0 + grp;
       acc_t x[NA];
-      load_chunks<V, K>(xbase + j0 * ldx, G * V, x);
+      ChunkLoader<V, K, G * V>::load(xaddr, x);
+      const bool valid = lr < rows;
+      const float yv = y_from_bits(lds_u32(ys + (valid ? lr : 0) * 4), y_dtype);
       float dotv;
       if constexpr (V == 1) {
         float a0 = 0.0f, a1 = 0.0f;
+        float wl[WREG ? 1 : NA];
+        if constexpr (!WREG) ChunkLoader<V, K, G * V>::load(theta_lane_s, wl);
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
           float wi;
           if constexpr (WREG)
             wi = w[i];
           else
-            wi = theta_s[(i * G + lg)];
+            wi = wl[i];
           if (i & 1)
             a1 = fmaf(x[i], wi, a1);
           else
@@ -233,16 +355,24 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const WarpTiles& wt,
               a0 = fma2(x[i], w[i], a0);
           }
         } else {
+          // theta re-read from shared memory in 4 batches (keeps the live range short)
+          constexpr int KB = (K + 3) / 4;
 #pragma unroll
-          for (int k = 0; k < K; ++k) {
-            acc_t wk[V / 2];
-            load_chunks<V, 1>(theta_s + (k * G + lg) * V, 0, wk);
+          for (int kb = 0; kb < K; kb += KB) {
+            constexpr int NB = KB * (V / 2);
+            acc_t wk[NB];
 #pragma unroll
-            for (int q = 0; q < V / 2; ++q) {
-              if (q & 1)
-                a1 = fma2(x[k * (V / 2) + q], wk[q], a1);
-              else
-                a0 = fma2(x[k * (V / 2) + q], wk[q], a0);
+            for (int k = 0; k < KB; ++k)
+              if (kb + k < K) load_chunks<V, 1>(theta_s + ((kb + k) * G + lg) * V, 0, &wk[k * (V / 2)]);
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+              const int i = kb * (V / 2) + q;
+              if (i < NA) {
+                if (q & 1)
+                  a1 = fma2(x[i], wk[q], a1);
+                else
+                  a0 = fma2(x[i], wk[q], a0);
+              }
             }
           }
         }
@@ -251,8 +381,6 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const WarpTiles& wt,
 #pragma unroll
       for (int off = G / 2; off > 0; off >>= 1) dotv += __shfl_xor_sync(kFull, dotv, off);
       const float eta = dotv + bias;
-      const bool valid = lr < rows;
-      const float yv = y_from_bits(ys[valid ? lr : 0], a.y_dtype);
       float lpv, rv;
       row_terms(family, eta, yv, lik_scale, lpv, rv);
       if (!valid) {
@@ -273,18 +401,18 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const WarpTiles& wt,
       }
     }
     __syncwarp();
-    if (++ring.stage == a.S) {
+    if (++ring.stage == pr.S) {
       ring.stage = 0;
       ring.parity ^= 1u;
     }
-    if (ring.qi < ring.q_total) ring_issue(a, wt, ring, lane, policy);
+    if (ring.qi < ring.q_total) ring_issue(pr, wt, ring, lane, policy);
   }
   ++ring.cpass;
 
   // ---- reduce across the RPS row groups of the warp with a halving butterfly: after stage `st` a lane
   //      keeps the half of the accumulators selected by its own bit, so 32+16+8+4+2 shuffles sum 64
   //      accumulators over 32 lanes (instead of 64*5). ----
-  constexpr int NST = (RPS == 32) ? 5 : (RPS == 8 ? 3 : 0);
+  constexpr int NST = ilog2(RPS);
   constexpr int LP = (KV + RPS - 1) / RPS * RPS;  // padded length, divisible by RPS = 2^NST
   constexpr int LPF = LP / RPS;                   // accumulators a lane ends up owning
   float h[LP];
@@ -308,45 +436,81 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const WarpTiles& wt,
 
   // ---- reduce across the warps of the CTA: fixed order, float64. Lane (grp, lg) owns flat accumulator
   //      indices grp*LPF + j, i.e. chunk k = idx / V, element v = idx % V, column (k*G+lg)*V+v. ----
-  for (int wq = 0; wq < kWarpsPerCta; ++wq) {
-    if (warp == wq) {
+  const int D = a.D, P = a.P;
+  double* xwd = reinterpret_cast<double*>(sm.xw + kXwFloats);  // [2][kMaxWarps]: bias-gradient and logp per warp
+  if (NW * D <= kXwFloats) {
+    // one-shot: every warp publishes its column sums, then each column is summed over the warps in order
 #pragma unroll
-      for (int j = 0; j < LPF; ++j) {
-        const int idx = grp * LPF + j;
-        const int col = ((idx / V) * G + lg) * V + (idx % V);
-        if (idx < KV && col < a.D) cta_acc[col] = (wq ? cta_acc[col] : 0.0) + static_cast<double>(h[j]);
-      }
-      if (lane == 0) {
-        if (a.has_bias) cta_acc[a.D] = (wq ? cta_acc[a.D] : 0.0) + static_cast<double>(gb);
-        cta_acc[a.P] = (wq ? cta_acc[a.P] : 0.0) + lp;
-      }
+    for (int j = 0; j < LPF; ++j) {
+      const int idx = grp * LPF + j;
+      const int col = ((idx / V) * G + lg) * V + (idx % V);
+      if (idx < KV && col < D) sm.xw[warp * D + col] = h[j];
+    }
+    if (lane == 0) {
+      xwd[warp] = static_cast<double>(gb);
+      xwd[kMaxWarps + warp] = lp;
     }
     __syncthreads();
+    for (int c = threadIdx.x; c <= P; c += NW * 32) {
+      double s = 0.0;
+      if (c < D) {
+#pragma unroll
+        for (int wq = 0; wq < NW; ++wq) s += static_cast<double>(sm.xw[wq * D + c]);
+      } else if (c == P) {
+#pragma unroll
+        for (int wq = 0; wq < NW; ++wq) s += xwd[kMaxWarps + wq];
+      } else {
+#pragma unroll
+        for (int wq = 0; wq < NW; ++wq) s += xwd[wq];
+      }
+      cta_acc[c] = s;
+    }
+    __syncthreads();
+  } else {
+    for (int wq = 0; wq < NW; ++wq) {
+      if (warp == wq) {
+#pragma unroll
+        for (int j = 0; j < LPF; ++j) {
+          const int idx = grp * LPF + j;
+          const int col = ((idx / V) * G + lg) * V + (idx % V);
+          if (idx < KV && col < D) cta_acc[col] = (wq ? cta_acc[col] : 0.0) + static_cast<double>(h[j]);
+        }
+        if (lane == 0) {
+          if (a.has_bias) cta_acc[D] = (wq ? cta_acc[D] : 0.0) + static_cast<double>(gb);
+          cta_acc[P] = (wq ? cta_acc[P] : 0.0) + lp;
+        }
+      }
+      __syncthreads();
+    }
   }
 }
 
 // Sums the per-CTA partials [ncta][P+1] (global, float64) in a fixed order into cta_acc[0..P].
-// Every CTA that calls this gets bit-identical totals. `comb` holds kThreads doubles.
+// Every CTA that calls this gets bit-identical totals. `comb` holds blockDim.x doubles. The loads of a
+// thread are issued in independent batches of 12 so that one or two L2 round trips cover them all.
 __device__ __forceinline__ void reduce_partials(const double* part, int ncta, int P, double* cta_acc, double* comb) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int ncol = P + 1;
+  constexpr int B = 12;
   int cpad = 32;
-  while (cpad < ncol) cpad <<= 1;
-  if (cpad <= kThreads) {
-    const int nsl = kThreads / cpad;
+  while (cpad < ncol && cpad < nthr) cpad <<= 1;
+  if (cpad >= ncol && cpad <= nthr) {
+    const int nsl = nthr / cpad;
     const int c = tid % cpad, q = tid / cpad;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    if (c < ncol) {
-      int cta = q;
-      for (; cta + 3 * nsl < ncta; cta += 4 * nsl) {
-        s0 += __ldcg(part + static_cast<size_t>(cta) * ncol + c);
-        s1 += __ldcg(part + static_cast<size_t>(cta + nsl) * ncol + c);
-        s2 += __ldcg(part + static_cast<size_t>(cta + 2 * nsl) * ncol + c);
-        s3 += __ldcg(part + static_cast<size_t>(cta + 3 * nsl) * ncol + c);
+    double s = 0.0;
+    if (c < ncol && q < nsl) {
+      for (int cta = q; cta < ncta; cta += B * nsl) {
+        double v[B];
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+          const int cc = cta + i * nsl;
+          v[i] = cc < ncta ? __ldcg(part + static_cast<size_t>(cc) * ncol + c) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < B; ++i) s += v[i];
       }
-      for (; cta < ncta; cta += nsl) s0 += __ldcg(part + static_cast<size_t>(cta) * ncol + c);
     }
-    comb[q * cpad + c] = (s0 + s1) + (s2 + s3);
+    if (q < nsl) comb[q * cpad + c] = s;
     __syncthreads();
     if (tid < ncol) {
       double t = 0.0;
@@ -355,79 +519,19 @@ __device__ __forceinline__ void reduce_partials(const double* part, int ncta, in
     }
     __syncthreads();
   } else {
-    for (int c = tid; c < ncol; c += kThreads) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int cta = 0;
-      for (; cta + 3 < ncta; cta += 4) {
-        s0 += __ldcg(part + static_cast<size_t>(cta) * ncol + c);
-        s1 += __ldcg(part + static_cast<size_t>(cta + 1) * ncol + c);
-        s2 += __ldcg(part + static_cast<size_t>(cta + 2) * ncol + c);
-        s3 += __ldcg(part + static_cast<size_t>(cta + 3) * ncol + c);
+    for (int c = tid; c < ncol; c += nthr) {
+      double s = 0.0;
+      for (int cta = 0; cta < ncta; cta += B) {
+        double v[B];
+#pragma unroll
+        for (int i = 0; i < B; ++i) v[i] = (cta + i) < ncta ? __ldcg(part + static_cast<size_t>(cta + i) * ncol + c) : 0.0;
+#pragma unroll
+        for (int i = 0; i < B; ++i) s += v[i];
       }
-      for (; cta < ncta; ++cta) s0 += __ldcg(part + static_cast<size_t>(cta) * ncol + c);
-      cta_acc[c] = (s0 + s1) + (s2 + s3);
+      cta_acc[c] = s;
     }
     __syncthreads();
   }
-}
-
-// Shared-memory carve-up.
-struct SmemLayout {
-  float* ring;
-  uint64_t* bars;
-  double* cta_acc;
-  double* red;
-  double* comb;
-  float* theta_s;
-  float* state;  // 5 * ppad floats
-};
-
-__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-__host__ __device__ inline size_t smem_layout_bytes(int S, int stage_floats, int P, int wpad, size_t* offs /*7*/) {
-  size_t off = 0;
-  offs[0] = off;
-  off += static_cast<size_t>(kWarpsPerCta) * S * stage_floats * 4;
-  off = align_up(off, 128);
-  offs[1] = off;
-  off += static_cast<size_t>(kWarpsPerCta) * kMaxStages * 8;
-  offs[2] = off;
-  off += align_up(static_cast<size_t>(P + 1) * 8, 16);
-  offs[3] = off;
-  off += 64 * 8;
-  offs[4] = off;
-  off += static_cast<size_t>(kThreads) * 8;
-  offs[5] = off;
-  off += align_up(static_cast<size_t>(wpad) * 4, 16);
-  offs[6] = off;
-  off += 5 * align_up(static_cast<size_t>(P) * 4, 16);
-  return align_up(off, 128);
-}
-
-__device__ __forceinline__ SmemLayout carve_smem(unsigned char* raw, const KArgs& a) {
-  size_t offs[7];
-  smem_layout_bytes(a.S, a.stage_floats, a.P, a.wpad, offs);
-  SmemLayout L;
-  L.ring = reinterpret_cast<float*>(raw + offs[0]);
-  L.bars = reinterpret_cast<uint64_t*>(raw + offs[1]);
-  L.cta_acc = reinterpret_cast<double*>(raw + offs[2]);
-  L.red = reinterpret_cast<double*>(raw + offs[3]);
-  L.comb = reinterpret_cast<double*>(raw + offs[4]);
-  L.theta_s = reinterpret_cast<float*>(raw + offs[5]);
-  L.state = reinterpret_cast<float*>(raw + offs[6]);
-  return L;
-}
-
-// Zero the ring (so padded / stale columns are finite), init the mbarriers, zero theta_s.
-__device__ __forceinline__ void smem_setup(const SmemLayout& L, const KArgs& a) {
-  const int tid = threadIdx.x;
-  const int nring = kWarpsPerCta * a.S * a.stage_floats;
-  for (int i = tid; i < nring; i += kThreads) L.ring[i] = 0.0f;
-  for (int i = tid; i < a.wpad; i += kThreads) L.theta_s[i] = 0.0f;
-  if (tid < kWarpsPerCta * kMaxStages) mbar_init(L.bars + tid, 33);  // 32 cp.async arrivals + 1 expect_tx arrival
-  fence_mbar_init();
-  fence_proxy_async_smem();
-  __syncthreads();
 }
 
 }  // namespace edhmc
