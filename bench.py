@@ -354,8 +354,16 @@ def main():
   alg_bytes_step = 4.0 * (r_hi - r_lo) * D + 4.0 * (r_hi - r_lo)  # this rank's shard: X once + y once per leapfrog step
   launch_ms = dev_ms / args.steps if info["plan_in_use"] == 1 else None
   achieved = alg_bytes_step * T * L / (dev_ms / args.steps * 1e-3) / 1e9
+  traffic = None
+  try:
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+      tj = json.load(f)
+    if wl_key in tj and info["plan_in_use"] == 1 and not args.rows:
+      traffic = tj[wl_key]["bytes_per_launch"]
+  except Exception:
+    pass
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-              "traffic": None, "peak_source": peak_src,
+              "traffic": traffic, "peak_source": peak_src,
               "kernel": "edhmc::k_hmc (one persistent launch = T*L passes)" if info["plan_in_use"] == 1
               else "edhmc::k_hmc mode 1 (one pass per launch) + NCCL all-reduce + chain kernels",
               "algorithmic_bytes_per_launch": alg_bytes_step * T * L if info["plan_in_use"] == 1 else alg_bytes_step,

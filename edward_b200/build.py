@@ -1,7 +1,7 @@
 """Builds edward_b200/lib/libedhmc.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
 The kernel template is instantiated in one translation unit per (lanes-per-row, vector-width) pair
-(csrc/inst_g*_v*.cu) so the units compile in parallel; objects land in csrc/_obj/.
+(csrc/inst_g*_v*.cu) so the units compile in parallel; objects land in a scratch directory under /tmp.
 """
 from __future__ import annotations
 
@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_obj")
+OBJ = os.environ.get("EDHMC_OBJ_DIR", os.path.join("/tmp", "edhmc_obj_%d" % (abs(hash(CSRC)) % 10**8)))
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libedhmc.so")
 

@@ -1,0 +1,72 @@
+// chains.cuh — C vectorised HMC chains over one shared design matrix (extension: the reference runs one
+// chain per ed.HMC object, hmc.py:14-130). Shared declarations between chains.cu (kernels) and edhmc.cu.
+//
+// Per leapfrog step the C chains need  S = X·W  (N×D · D×C),  R = y − σ(S)  and  G = Xᵀ·R  (D×C): a dense
+// contraction, executed on the tcgen05 tensor cores in 3xTF32 (k_mc_pass_tc) with TMEM accumulators, or
+// on the CUDA cores (k_mc_pass_simple, the bring-up / cross-check path). The O(C·P) integrator, prior,
+// kinetic energy and Metropolis–Hastings step of every chain run in small per-chain kernels between passes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace edhmc {
+
+constexpr int kMcChainsPerCta = 128;  // chains per CTA: one TMEM lane / one thread per chain
+constexpr int kMcTileRows = 128;      // rows of X per tensor-core tile
+constexpr int kMcMaxD = 64;           // features supported by the many-chain pass kernels
+
+struct McArgs {
+  // problem
+  const float* X;
+  const void* y;
+  long long n_rows;
+  long long ldx;
+  int D;
+  int Dp;  // D rounded up to a multiple of 8 (MMA K granularity for tf32)
+  int family;
+  int y_dtype;
+  float lik_scale;
+  const float* prior_loc;    // [D]
+  const float* prior_scale;  // [D]
+  double prior_const;
+  int C;           // chains (multiple of 128)
+  int n_rowgroups;  // CTAs along the rows
+  int want_logp;    // 1: the pass also accumulates the log-likelihood (only needed at the end of a trajectory)
+  // state, all [C][D] float32 unless noted
+  float* z;
+  float* r;
+  float* g;
+  float* zcur;
+  float* gcur;
+  double* logp_cur;  // [C]
+  double* k_old;     // [C]
+  double* log_u;     // [C]
+  long long* n_accept;  // [C]
+  int* valid;           // [1]
+  int* need_init;       // [1]
+  // pass output: per row group partial sums, [n_rowgroups][C][Dp+1] float32 gradient + [n_rowgroups][C] float64 logp
+  float* part_g;
+  double* part_lp;
+  // run
+  float* params;  // [T][C][D]
+  long long t0;
+  long long n_iter;
+  float eps, half_eps;
+  int L;
+  const float* r0;  // [n_iter][C][D] or null
+  const float* u;   // [n_iter][C] or null
+  unsigned long long seed;
+  double* trace;  // [n_iter][C][8] or null
+};
+
+// host launchers (chains.cu)
+int mc_smem_bytes_tc(int Dp);
+cudaError_t mc_prepare_tc();
+cudaError_t mc_launch_pass(const McArgs& a, const float* theta, int use_tc, int gate, cudaStream_t s);
+cudaError_t mc_launch_check(const McArgs& a, cudaStream_t s);
+cudaError_t mc_launch_init_finish(const McArgs& a, cudaStream_t s);
+cudaError_t mc_launch_begin(const McArgs& a, long long it, cudaStream_t s);
+cudaError_t mc_launch_leap(const McArgs& a, long long it, int step, cudaStream_t s);
+cudaError_t mc_launch_logp_grad_finish(const McArgs& a, const float* theta, double* logp, float* grad, cudaStream_t s);
+
+}  // namespace edhmc
