@@ -10,11 +10,12 @@ import os
 import shutil
 import subprocess
 import sys
+import zlib
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.environ.get("EDHMC_OBJ_DIR", os.path.join("/tmp", "edhmc_obj_%d" % (abs(hash(CSRC)) % 10**8)))
+OBJ = os.environ.get("EDHMC_OBJ_DIR", os.path.join("/tmp", "edhmc_obj_%08x" % zlib.crc32(CSRC.encode())))
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libedhmc.so")
 

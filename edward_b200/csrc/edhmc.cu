@@ -12,6 +12,7 @@
 
 #include "../../include/edhmc.h"
 #include "chain_small.cuh"
+#include "chains.cuh"
 
 using namespace edhmc;
 
@@ -139,6 +140,13 @@ struct edhmc_handle {
   // nccl
   void* comm = nullptr;
   int nranks = 1, rank = 0;
+  // many chains
+  int C = 0, mc_nrg = 0, mc_use_tc = 0, mc_Dp = 0;
+  float *mc_z = nullptr, *mc_r = nullptr, *mc_g = nullptr, *mc_zcur = nullptr, *mc_gcur = nullptr, *mc_part_g = nullptr;
+  double *mc_logp = nullptr, *mc_kold = nullptr, *mc_logu = nullptr, *mc_part_lp = nullptr;
+  long long* mc_nacc = nullptr;
+  int* mc_flags = nullptr;  // [0] valid, [1] need_init
+  double* mc_trace = nullptr;
   // stats
   long long passes_last = 0, launches_last = 0;
   int plan_in_use = 0;
@@ -326,8 +334,14 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   if (cfg->family == EDHMC_NORMAL_IDENTITY && !(cfg->lik_scale > 0.0f))
     return fail(EDHMC_ERR_INVALID, "lik_scale must be > 0 for the Normal family");
   if (!cfg->prior_loc_host || !cfg->prior_scale_host) return fail(EDHMC_ERR_INVALID, "prior arrays are required");
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < 4; ++i)
     if (cfg->reserved[i] != 0) return fail(EDHMC_ERR_INVALID, "reserved fields must be zero");
+  if (cfg->n_chains > 1) {
+    if (cfg->n_chains % kMcChainsPerCta != 0)
+      return fail(EDHMC_ERR_INVALID, "n_chains must be a multiple of %d, got %d", kMcChainsPerCta, cfg->n_chains);
+    if (cfg->n_features > kMcMaxD) return fail(EDHMC_ERR_INVALID, "vectorised chains support n_features <= %d", kMcMaxD);
+    if (cfg->has_bias) return fail(EDHMC_ERR_INVALID, "vectorised chains do not support a bias latent yet");
+  }
   const int P = cfg->n_features + (cfg->has_bias ? 1 : 0);
   double pc = 0.0;
   for (int i = 0; i < P; ++i) {
@@ -383,6 +397,42 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   ALLOC(h->d_ticket, sizeof(unsigned int));
   ALLOC(h->d_sums, static_cast<size_t>(P + 1) * sizeof(double));
   ALLOC(h->d_bad, sizeof(unsigned long long));
+  if (cfg->n_chains > 1) {
+    h->C = cfg->n_chains;
+    h->mc_Dp = (cfg->n_features + 7) / 8 * 8;
+    const long long ntiles = (cfg->n_rows + kMcTileRows - 1) / kMcTileRows;
+    long long nrg = h->num_sms / (h->C / kMcChainsPerCta);
+    if (nrg < 1) nrg = 1;
+    if (nrg > ntiles) nrg = ntiles > 0 ? ntiles : 1;
+    h->mc_nrg = static_cast<int>(nrg);
+    h->mc_use_tc = cfg->ldx <= kMcMaxD ? 1 : 0;
+    if (const char* e = getenv("EDHMC_MC_IMPL")) h->mc_use_tc = (strcmp(e, "tc") == 0 && cfg->ldx <= kMcMaxD) ? 1 : 0;
+    const size_t cd = static_cast<size_t>(h->C) * cfg->n_features * sizeof(float);
+    ALLOC(h->mc_z, cd);
+    ALLOC(h->mc_r, cd);
+    ALLOC(h->mc_g, cd);
+    ALLOC(h->mc_zcur, cd);
+    ALLOC(h->mc_gcur, cd);
+    ALLOC(h->mc_logp, h->C * sizeof(double));
+    ALLOC(h->mc_kold, h->C * sizeof(double));
+    ALLOC(h->mc_logu, h->C * sizeof(double));
+    ALLOC(h->mc_nacc, h->C * sizeof(long long));
+    ALLOC(h->mc_flags, 2 * sizeof(int));
+    ALLOC(h->mc_part_g, static_cast<size_t>(h->mc_nrg) * h->C * h->mc_Dp * sizeof(float));
+    ALLOC(h->mc_part_lp, static_cast<size_t>(h->mc_nrg) * h->C * sizeof(double));
+    cudaMemset(h->mc_zcur, 0, cd);
+    cudaMemset(h->mc_gcur, 0, cd);
+    cudaMemset(h->mc_logp, 0, h->C * sizeof(double));
+    cudaMemset(h->mc_nacc, 0, h->C * sizeof(long long));
+    cudaMemset(h->mc_flags, 0, 2 * sizeof(int));
+    if (h->mc_use_tc) {
+      cudaError_t e = mc_prepare_tc();
+      if (e != cudaSuccess) {
+        edhmc_destroy(h);
+        return fail(EDHMC_ERR_CUDA, "tensor-core pass setup failed: %s", cudaGetErrorString(e));
+      }
+    }
+  }
 #undef ALLOC
   cudaMemcpy(h->d_prior_loc, cfg->prior_loc_host, pb, cudaMemcpyHostToDevice);
   cudaMemcpy(h->d_prior_scale, cfg->prior_scale_host, pb, cudaMemcpyHostToDevice);
@@ -418,6 +468,18 @@ int edhmc_destroy(edhmc_t* h) {
   cudaFree(h->d_sums);
   cudaFree(h->d_bad);
   cudaFree(h->y_owned);
+  cudaFree(h->mc_z);
+  cudaFree(h->mc_r);
+  cudaFree(h->mc_g);
+  cudaFree(h->mc_zcur);
+  cudaFree(h->mc_gcur);
+  cudaFree(h->mc_logp);
+  cudaFree(h->mc_kold);
+  cudaFree(h->mc_logu);
+  cudaFree(h->mc_nacc);
+  cudaFree(h->mc_flags);
+  cudaFree(h->mc_part_g);
+  cudaFree(h->mc_part_lp);
   delete h;
   return 0;
 }
@@ -443,6 +505,7 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
   h->bound = true;
   // data changed: the cached log joint / gradient no longer apply
   CUDA_TRY(cudaMemsetAsync(&h->d_sc->valid, 0, sizeof(int), stream));
+  if (h->mc_flags) CUDA_TRY(cudaMemsetAsync(h->mc_flags, 0, 2 * sizeof(int), stream));
   if (check_finite && h->cfg.n_rows > 0) {
     CUDA_TRY(cudaMemsetAsync(h->d_bad, 0, sizeof(unsigned long long), stream));
     k_check_finite<<<h->num_sms * 8, 256, 0, stream>>>(X, h->cfg.n_rows, h->cfg.ldx, h->cfg.n_features, h->y,
@@ -590,6 +653,10 @@ int edhmc_reset(edhmc_t* h, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   CUDA_TRY(cudaMemsetAsync(h->d_sc, 0, sizeof(ChainScalars), stream));
+  if (h->C > 1) {
+    CUDA_TRY(cudaMemsetAsync(h->mc_nacc, 0, h->C * sizeof(long long), stream));
+    CUDA_TRY(cudaMemsetAsync(h->mc_flags, 0, 2 * sizeof(int), stream));
+  }
   return 0;
 }
 
@@ -618,6 +685,115 @@ int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t 
   NCCL_TRY(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
   h->nranks = nranks;
   h->rank = rank;
+  return 0;
+}
+
+// ---- vectorised chains -----------------------------------------------------------------------------
+static void fill_mc_args(edhmc_handle* h, McArgs& a) {
+  memset(&a, 0, sizeof(a));
+  const edhmc_cfg& c = h->cfg;
+  a.X = h->X;
+  a.y = h->y;
+  a.n_rows = c.n_rows;
+  a.ldx = c.ldx;
+  a.D = c.n_features;
+  a.Dp = h->mc_Dp;
+  a.family = c.family;
+  a.y_dtype = h->y_dtype;
+  a.lik_scale = c.lik_scale;
+  a.prior_loc = h->d_prior_loc;
+  a.prior_scale = h->d_prior_scale;
+  a.prior_const = h->prior_const;
+  a.C = h->C;
+  a.n_rowgroups = h->mc_nrg;
+  a.want_logp = 1;
+  a.z = h->mc_z;
+  a.r = h->mc_r;
+  a.g = h->mc_g;
+  a.zcur = h->mc_zcur;
+  a.gcur = h->mc_gcur;
+  a.logp_cur = h->mc_logp;
+  a.k_old = h->mc_kold;
+  a.log_u = h->mc_logu;
+  a.n_accept = h->mc_nacc;
+  a.valid = h->mc_flags;
+  a.need_init = h->mc_flags + 1;
+  a.part_g = h->mc_part_g;
+  a.part_lp = h->mc_part_lp;
+  a.seed = h->seed;
+  a.trace = h->mc_trace;
+}
+
+int edhmc_run_chains(edhmc_t* h, float* params, int64_t T, int64_t t0, int64_t n_iter, float step_size, int32_t n_steps,
+                     const float* r0, const float* u, void* stream_) {
+  if (!h || !params) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (h->C <= 1) return fail(EDHMC_ERR_STATE, "handle was not created with n_chains > 1");
+  if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data has not been called");
+  if (n_steps < 0 || n_iter < 0 || t0 < 0) return fail(EDHMC_ERR_INVALID, "negative n_steps / n_iter / t0");
+  if (t0 + n_iter > T)
+    return fail(EDHMC_ERR_RANGE, "indices[0] = %lld is not in [0, %lld)", (long long)(t0 + n_iter - 1), (long long)T);
+  if (n_iter == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  McArgs a;
+  fill_mc_args(h, a);
+  a.params = params;
+  a.t0 = t0;
+  a.n_iter = n_iter;
+  a.eps = step_size;
+  a.half_eps = 0.5f * step_size;
+  a.L = n_steps;
+  a.r0 = r0;
+  a.u = u;
+  h->launches_last = 0;
+  h->passes_last = n_iter * n_steps;
+  CUDA_TRY(mc_launch_check(a, stream));
+  CUDA_TRY(mc_launch_pass(a, h->mc_zcur, h->mc_use_tc, 1, stream));
+  CUDA_TRY(mc_launch_init_finish(a, stream));
+  h->launches_last += 3;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    CUDA_TRY(mc_launch_begin(a, it, stream));
+    ++h->launches_last;
+    for (int s = 0; s < n_steps; ++s) {
+      McArgs as = a;
+      as.want_logp = (s == n_steps - 1) ? 1 : 0;  // the log joint is only needed at the end of the trajectory
+      CUDA_TRY(mc_launch_pass(as, h->mc_z, h->mc_use_tc, 0, stream));
+      CUDA_TRY(mc_launch_leap(a, it, s, stream));
+      h->launches_last += 2;
+    }
+  }
+  return 0;
+}
+
+int edhmc_logp_grad_chains(edhmc_t* h, const float* theta, double* logp, float* grad, void* stream_) {
+  if (!h || !theta || !logp || !grad) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (h->C <= 1) return fail(EDHMC_ERR_STATE, "handle was not created with n_chains > 1");
+  if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data has not been called");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  McArgs a;
+  fill_mc_args(h, a);
+  CUDA_TRY(mc_launch_pass(a, theta, h->mc_use_tc, 0, stream));
+  CUDA_TRY(mc_launch_logp_grad_finish(a, theta, logp, grad, stream));
+  h->launches_last = 2;
+  h->passes_last = 1;
+  return 0;
+}
+
+int edhmc_read_chain_state(edhmc_t* h, int64_t* n_accept_host, double* logp_host, void* stream_) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  if (h->C <= 1) return fail(EDHMC_ERR_STATE, "handle was not created with n_chains > 1");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (n_accept_host) CUDA_TRY(cudaMemcpyAsync(n_accept_host, h->mc_nacc, h->C * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  if (logp_host) CUDA_TRY(cudaMemcpyAsync(logp_host, h->mc_logp, h->C * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int edhmc_set_chain_trace(edhmc_t* h, double* trace) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  h->mc_trace = trace;
   return 0;
 }
 

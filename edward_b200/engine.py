@@ -53,7 +53,7 @@ class GLMSampler:
   """One chain of HMC over a GLM. Row-sharded when `comm` (a torch.distributed group spec) is given."""
 
   def __init__(self, spec: GLMSpec, X, y, device=None, plan: int = _C.PLAN_AUTO, debug: bool = False,
-               check_finite: bool = True, n_rows_global: Optional[int] = None):
+               check_finite: bool = True, n_rows_global: Optional[int] = None, n_chains: int = 1):
     self.lib = _C.lib()
     self.dev = _require_cuda(device)
     self.spec = spec
@@ -89,6 +89,8 @@ class GLMSampler:
     cfg.device = self.dev.index
     cfg.plan = int(plan)
     cfg.debug = 1 if debug else 0
+    cfg.n_chains = int(n_chains) if n_chains and n_chains > 1 else 0
+    self.n_chains = max(1, int(n_chains or 1))
     self._h = C.c_void_p()
     _C.check(self.lib.edhmc_create(C.byref(self._h), C.byref(cfg)))
     with torch.cuda.device(self.dev):
@@ -147,6 +149,51 @@ class GLMSampler:
     with torch.cuda.device(self.dev):
       _C.check(self.lib.edhmc_run(self._h, params.data_ptr(), int(params.stride(0)), int(params.shape[0]), int(t0),
                                   int(n_iter), float(step_size), int(n_steps), r0p, up, _stream_ptr(self.dev)))
+
+  # ---- C vectorised chains (extension) ---------------------------------------------------------
+  def logp_grad_chains(self, theta):
+    """theta [C, P] → (logp [C] float64, grad [C, P] float32), one dense contraction on the tensor cores."""
+    th = self._to_device(theta, torch.float32).contiguous().reshape(self.n_chains, self.P)
+    logp = torch.empty(self.n_chains, dtype=torch.float64, device=self.dev)
+    grad = torch.empty(self.n_chains, self.P, dtype=torch.float32, device=self.dev)
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_logp_grad_chains(self._h, th.data_ptr(), logp.data_ptr(), grad.data_ptr(), _stream_ptr(self.dev)))
+    return logp, grad
+
+  def run_chains(self, params: torch.Tensor, t0: int, n_iter: int, step_size: float, n_steps: int,
+                 r0: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None):
+    """n_iter transitions of all C chains in place on `params` [T, C, P] (device, float32, contiguous)."""
+    if params.device != self.dev or params.dtype != torch.float32 or not params.is_contiguous():
+      raise TypeError("params must be a contiguous float32 tensor on %s" % self.dev)
+    if params.dim() != 3 or params.shape[1] != self.n_chains or params.shape[2] != self.P:
+      raise TypeError("params must have shape [T, %d, %d]" % (self.n_chains, self.P))
+    r0p = up = None
+    if r0 is not None:
+      r0 = self._to_device(r0, torch.float32).contiguous()
+      if r0.numel() < n_iter * self.n_chains * self.P:
+        raise ValueError("r0 must hold n_iter*C*P momentum draws")
+      r0p = r0.data_ptr()
+    if u is not None:
+      u = self._to_device(u, torch.float32).contiguous()
+      if u.numel() < n_iter * self.n_chains:
+        raise ValueError("u must hold n_iter*C uniforms")
+      up = u.data_ptr()
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_run_chains(self._h, params.data_ptr(), int(params.shape[0]), int(t0), int(n_iter),
+                                         float(step_size), int(n_steps), r0p, up, _stream_ptr(self.dev)))
+
+  def read_chain_state(self):
+    n = (C.c_int64 * self.n_chains)()
+    lp = (C.c_double * self.n_chains)()
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_read_chain_state(self._h, n, lp, _stream_ptr(self.dev)))
+    return np.array(n[:], np.int64), np.array(lp[:], np.float64)
+
+  def set_chain_trace(self, n_iter: int):
+    tr = torch.zeros(n_iter, self.n_chains, 8, dtype=torch.float64, device=self.dev)
+    self._chain_trace = tr
+    _C.check(self.lib.edhmc_set_chain_trace(self._h, tr.data_ptr()))
+    return tr
 
   def set_trace(self, n_iter: int):
     sc = torch.zeros(n_iter, 8, dtype=torch.float64, device=self.dev)

@@ -82,7 +82,9 @@ typedef struct edhmc_cfg {
   int32_t device;          /* CUDA device ordinal */
   int32_t plan;            /* edhmc_plan */
   int32_t debug;           /* 1: check log-joint/gradient for NaN/Inf after every run (inference.py:279-281) */
-  int32_t reserved[5];     /* must be zero */
+  int32_t n_chains;        /* 0 or 1: one chain (the reference). C > 1: C vectorised chains (extension; C % 128 == 0,
+                              n_features <= 64, no bias) served by edhmc_run_chains / edhmc_logp_grad_chains */
+  int32_t reserved[4];     /* must be zero */
 } edhmc_cfg;
 
 typedef struct edhmc_handle edhmc_t;
@@ -145,6 +147,18 @@ int edhmc_seed(edhmc_t* h, uint64_t seed);
  * all-reduce (sum, float64) the per-shard [grad, logp] once per data pass over NVLink. */
 int edhmc_comm_unique_id(void* id128_host);
 int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t rank);
+
+/* ---- C vectorised chains (extension; the reference runs one chain per ed.HMC object) -------------------------
+ * Every chain is an independent HMC chain on the same data: per leapfrog step the C gradients are one dense
+ * contraction S = X·W, G = Xᵀ·(y − σ(S)) executed on the tcgen05 tensor cores in 3xTF32 (TMEM accumulators).
+ *   params [T, C, P] float32 in place; r0 [n_iter, C, P] / u [n_iter, C] optional injected draws;
+ *   theta [C, P]; logp [C] float64; grad [C, P] float32; trace [n_iter, C, 8] float64 (same columns as above).
+ * Each chain follows exactly the single-chain semantics of edhmc_run (checked against independent runs). */
+int edhmc_run_chains(edhmc_t* h, float* params, int64_t T, int64_t t0, int64_t n_iter, float step_size,
+                     int32_t n_steps, const float* r0, const float* u, void* stream);
+int edhmc_logp_grad_chains(edhmc_t* h, const float* theta, double* logp, float* grad, void* stream);
+int edhmc_read_chain_state(edhmc_t* h, int64_t* n_accept_host /*[C]*/, double* logp_host /*[C]*/, void* stream);
+int edhmc_set_chain_trace(edhmc_t* h, double* trace);
 
 /* Introspection for benches/tests: fills up to `cap` int64 values:
  * {grid_ctas, warps_per_cta, ring_stages, tile_rows, lanes_per_row, vec_width, smem_bytes,
