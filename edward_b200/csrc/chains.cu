@@ -334,20 +334,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mc_pass_tc(const McArgs a, co
         uint32_t v[16], vh[16], vl[16];
         tmem_ld16(tm_s + lane_base + col, v);
         tmem_wait_ld();
+        if (a.want_logp || a.family != 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int m = col + j;
-          float lpv, rv;
-          row_terms(a.family, __uint_as_float(v[j]), ys[m], a.lik_scale, lpv, rv);
-          if (m >= rows) {
-            lpv = 0.0f;
-            rv = 0.0f;
+          for (int j = 0; j < 16; ++j) {
+            const int m = col + j;
+            float lpv, rv;
+            row_terms(a.family, __uint_as_float(v[j]), ys[m], a.lik_scale, lpv, rv);
+            if (m >= rows) {
+              lpv = 0.0f;
+              rv = 0.0f;
+            }
+            lp += static_cast<double>(lpv);
+            float h, l;
+            split_tf32(rv, h, l);
+            vh[j] = __float_as_uint(h);
+            vl[j] = __float_as_uint(l);
           }
-          if (a.want_logp) lp += static_cast<double>(lpv);
-          float h, l;
-          split_tf32(rv, h, l);
-          vh[j] = __float_as_uint(h);
-          vl[j] = __float_as_uint(l);
+        } else {
+          // inside a trajectory only the residual y - sigmoid(eta) is needed (the log joint enters the
+          // Metropolis–Hastings ratio at the trajectory's end only): one exp and one reciprocal per element
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = col + j;
+            const float eta = __uint_as_float(v[j]);
+            const float e = expf(-fabsf(eta));
+            const float qv = __fdividef(e, 1.0f + e);
+            const float yv = ys[m];
+            float rv = eta >= 0.0f ? (yv - 1.0f) + qv : yv - qv;
+            if (m >= rows) rv = 0.0f;
+            float h, l;
+            split_tf32(rv, h, l);
+            vh[j] = __float_as_uint(h);
+            vl[j] = __float_as_uint(l);
+          }
         }
         tmem_st16(tm_s + lane_base + col, vh);
         tmem_st16(tm_lo + lane_base + col, vl);
