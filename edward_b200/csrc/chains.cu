@@ -149,6 +149,15 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// One lane of a converged warp (elect.sync): the pattern under which tcgen05.mma issues at the hardware rate.
+// Issued from a divergent `if (tid == 0)` region the compiler wraps every UTCHMMA in an ELECT/R2UR/BRA.U.ANY
+// loop and the issue cost rises from ~35 to ~190 cycles per instruction (measured, tools/micro/mma_chain*.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);  // the 19 bits the tensor core reads
   lo = x - hi;                                               // exact in fp32
@@ -426,6 +435,693 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mc_pass_tc(const McArgs a, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pipelined tensor-core pass (default). Same mathematics as k_mc_pass_tc, restructured so that the tensor
+// pipe, the operand builders and the epilogue work on different tiles at the same time:
+//   warp 0      control: TMA bulk loads of the raw X tiles + MMA1 issue (one thread); warp 13: MMA2 issue
+//   warps 1-4   builders: raw tile → B1 (rows x K=Dp) and B2 (feats x K=rows) operand tiles, hi/lo split
+//   warps 5-12  epilogue: Sᵀ (TMEM) → residual R (TMEM, hi in place + lo), log-likelihood
+// 64-row tiles, every per-tile resource double-buffered (b = tile & 1):
+//   TMEM  S[b] 64 cols at 64*b, R_lo[b] 64 cols at 128+64*b, G' 64 cols at 256   (512 allocated)
+//   mbarriers  raw_full[b] (TMA) → b_ready[b] (128 builder arrivals) → s_ready[b] (tcgen05.commit after MMA1)
+//              → r_ready[b] (256 epilogue arrivals) → mma2_done[b] (tcgen05.commit after MMA2, frees B[b])
+// MMA1(i+2) may overwrite S[b] only after MMA2(i) has read R[b]: b_ready[b](i+2) implies it, because the
+// builders wait for mma2_done[b](i) before they rebuild B[b].
+// ------------------------------------------------------------------------------------------------
+#define MC_DBG(slot) do { if (dbgp && i < 64) dbgp[i * 16 + (slot)] = clock64(); } while (0)
+constexpr int kT2Rows = 64;
+constexpr int kT2Threads = 14 * 32;  // control/MMA1, 4 builders, 8 epilogue, MMA2 issuer
+constexpr int kT2Builders = 128;
+constexpr int kT2Epilogue = 256;
+
+__host__ __device__ inline int tc2_smem_layout(int Dp, int ldx, int* off /*8*/) {
+  int o = 0;
+  off[0] = o;  // raw[2] (also reused for the final logp combine)
+  const int raw_bytes = (kT2Rows * ldx * 4 + 32 + 127) / 128 * 128;  // + slack: masked over-read of the last row
+  o += 2 * raw_bytes;
+  off[1] = o;  // ys[2][64]
+  o += 2 * kT2Rows * 4;
+  off[2] = o;  // A1 hi, lo
+  o += 2 * (Dp / 4) * 2048;
+  off[3] = o;  // B1[2] {hi, lo}
+  o += 2 * 2 * (Dp / 4) * 1024;
+  off[4] = o;  // B2[2] {hi, lo}
+  o += 2 * 2 * (kT2Rows / 4) * 1024;
+  off[5] = o;  // 10 mbarriers + tmem slot
+  o += 128;
+  off[6] = raw_bytes;
+  return o;
+}
+
+__global__ void __launch_bounds__(kT2Threads, 1) k_mc_pass_tc2(const McArgs a, const float* theta, int gate) {
+  if (gate && !*a.need_init) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  int off[8];
+  const int ldx = static_cast<int>(a.ldx);
+  const int Dp = a.Dp, D = a.D;
+  tc2_smem_layout(Dp, ldx, off);
+  const int raw_bytes = off[6];
+  unsigned char* raw0 = smem + off[0];
+  float* ysm = reinterpret_cast<float*>(smem + off[1]);
+  unsigned char* A1 = smem + off[2];
+  unsigned char* B1 = smem + off[3];
+  unsigned char* B2 = smem + off[4];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off[5]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off[5] + 96);
+  const int kc1 = Dp / 4;
+  const int a1_half = kc1 * 2048;
+  const int b1_half = kc1 * 1024, b1_buf = 2 * b1_half;
+  const int b2_half = (kT2Rows / 4) * 1024, b2_buf = 2 * b2_half;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cb = blockIdx.y * kMcChainsPerCta;
+  // barrier indices: 0,1 raw_full  2,3 b_ready  4,5 s_ready  6,7 r_ready  8,9 mma2_done
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int kind, int b) { return bar0 + static_cast<uint32_t>((kind * 2 + b) * 8); };
+
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars[0 + b], 1);
+      mbar_init(&bars[2 + b], kT2Builders);
+      mbar_init(&bars[4 + b], 1);
+      mbar_init(&bars[6 + b], kT2Epilogue);
+      mbar_init(&bars[8 + b], 1);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  for (int i = tid; i < kMcChainsPerCta * kc1; i += kT2Threads) {
+    const int c = i % kMcChainsPerCta, kc = i / kMcChainsPerCta;
+    float4 h, l;
+    float* hp = &h.x;
+    float* lq = &l.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = kc * 4 + e;
+      const float v = d < D ? theta[static_cast<size_t>(cb + c) * D + d] : 0.0f;
+      split_tf32(v, hp[e], lq[e]);
+    }
+    *reinterpret_cast<float4*>(A1 + kc * 2048 + c * 16) = h;
+    *reinterpret_cast<float4*>(A1 + a1_half + kc * 2048 + c * 16) = l;
+  }
+  for (int i = tid; i < 2 * b2_buf / 16; i += kT2Threads) reinterpret_cast<float4*>(B2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t tm_g = tm + 256;
+
+  // this row group's tiles of 64 rows (two per 128-row unit of the shared partition)
+  long long u0, u1;
+  tile_range(a.n_rows, a.n_rowgroups, blockIdx.x, u0, u1);
+  const long long row_begin = u0 * kMcTileRows;
+  long long row_end = u1 * kMcTileRows;
+  if (row_end > a.n_rows) row_end = a.n_rows;
+  const int nt = row_end > row_begin ? static_cast<int>((row_end - row_begin + kT2Rows - 1) / kT2Rows) : 0;
+  const uint32_t id12 = idesc_tf32(128, kT2Rows);  // MMA1: N = 64 rows;  MMA2: N = 64 features
+  double lp = 0.0;
+  long long* dbgp = (a.dbg && !a.want_logp && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? a.dbg : nullptr;
+
+  if (warp == 0) {
+    // ================= control warp: TMA loads of raw tiles + MMA1 issue =================
+    // The whole warp runs the loop (converged); one elected lane issues. Descriptors are built once; per
+    // k-step only the 14-bit start-address field moves (+bytes/16).
+    auto issue_raw = [&](int i) {
+      const long long r0 = row_begin + static_cast<long long>(i) * kT2Rows;
+      if (row_end - r0 >= kT2Rows) {
+        if (elect_one()) {
+          const int b = i & 1;
+          const uint32_t bytes = kT2Rows * ldx * 4;
+          fence_proxy_async_smem();
+          mbar_arrive_expect_tx_s(BAR(0, b), bytes);
+          bulk_g2s_s(smem_u32(raw0 + b * raw_bytes), a.X + r0 * a.ldx, bytes, BAR(0, b));
+        }
+        __syncwarp();
+      }
+    };
+    for (int i = 0; i < nt && i < 2; ++i) issue_raw(i);
+    const uint64_t da_h = smem_desc(smem_u32(A1), 2048, 128), da_l = smem_desc(smem_u32(A1) + a1_half, 2048, 128);
+    const uint64_t db_h0 = smem_desc(smem_u32(B1), 1024, 128), db_l0 = smem_desc(smem_u32(B1) + b1_half, 1024, 128);
+    const int nks = Dp / 8;
+    for (int i = 0; i < nt; ++i) {
+      const int b = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      mbar_wait_s(BAR(1, b), par);  // b_ready: operand tiles built, raw[b] consumed
+      MC_DBG(0);
+      if (i + 2 < nt) issue_raw(i + 2);
+      tc_fence_after();
+      const uint64_t db_h = db_h0 + static_cast<uint64_t>((b * b1_buf) >> 4), db_l = db_l0 + static_cast<uint64_t>((b * b1_buf) >> 4);
+      const uint32_t ts = tm + 64 * b;
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // Sᵀ[b] = Wᵀ·X(i)ᵀ, K = Dp = 8*nks
+          if (ks < nks) {
+            const uint64_t oa = static_cast<uint64_t>(ks * (4096 >> 4)), ob = static_cast<uint64_t>(ks * (2048 >> 4));
+            tc_mma_ss(ts, da_h + oa, db_h + ob, id12, ks > 0);
+            tc_mma_ss(ts, da_h + oa, db_l + ob, id12, 1);
+            tc_mma_ss(ts, da_l + oa, db_h + ob, id12, 1);
+          }
+        }
+        tc_commit(BAR(2, b));  // s_ready[b]
+      }
+      __syncwarp();
+      MC_DBG(1);
+    }
+  } else if (warp == 13) {
+    // ================= MMA2 issuer warp: G' += R(i)·X(i), A = R from TMEM =================
+    const uint64_t d2_h0 = smem_desc(smem_u32(B2), 1024, 128), d2_l0 = smem_desc(smem_u32(B2) + b2_half, 1024, 128);
+    for (int i = 0; i < nt; ++i) {
+      const int b = i & 1;
+      mbar_wait_s(BAR(3, b), (i >> 1) & 1);  // r_ready[b]
+      MC_DBG(2);
+      tc_fence_after();
+      const uint64_t d2_h = d2_h0 + static_cast<uint64_t>((b * b2_buf) >> 4), d2_l = d2_l0 + static_cast<uint64_t>((b * b2_buf) >> 4);
+      const uint32_t r_h = tm + 64 * b, r_l = tm + 128 + 64 * b;
+      const uint32_t first = (i > 0) ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < kT2Rows / 8; ++ks) {
+          const uint64_t o = static_cast<uint64_t>(ks * (2048 >> 4));
+          tc_mma_ts(tm_g, r_h + ks * 8, d2_h + o, id12, ks > 0 ? 1u : first);
+          tc_mma_ts(tm_g, r_h + ks * 8, d2_l + o, id12, 1);
+          tc_mma_ts(tm_g, r_l + ks * 8, d2_h + o, id12, 1);
+        }
+        tc_commit(BAR(4, b));  // mma2_done[b]: B[b], ys[b], S[b] are free again
+      }
+      __syncwarp();
+      MC_DBG(3);
+    }
+    if (nt > 0) mbar_wait_s(BAR(4, (nt - 1) & 1), ((nt - 1) >> 1) & 1);  // the last commit covers every MMA2
+  } else if (warp <= 4) {
+    // ================= builders =================
+    // Each work item is a 4x4 block (rows 4*mb.., features 4*kc..): loaded once from the raw tile, split once
+    // into hi/lo, and written both as 4 row-chunks of B1 and as 4 feature-chunks of B2.
+    const int bt = tid - 32;
+    for (int i = 0; i < nt; ++i) {
+      const int b = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      const long long r0 = row_begin + static_cast<long long>(i) * kT2Rows;
+      const int rows = row_end - r0 >= kT2Rows ? kT2Rows : static_cast<int>(row_end - r0);
+      if (i >= 2) mbar_wait_s(BAR(4, b), par ^ 1u);  // MMA2(i-2) has finished reading B[b] / ys[b]
+      if (warp == 1) MC_DBG(4);
+      float* rawb = reinterpret_cast<float*>(raw0 + b * raw_bytes);
+      if (rows == kT2Rows) {
+        mbar_wait_s(BAR(0, b), par);
+      } else {  // ragged last tile: stage it through the (idle) raw buffer with plain loads
+        for (int e = bt; e < rows * ldx; e += kT2Builders) {
+          const int m = e / ldx, d = e - m * ldx;
+          rawb[e] = d < D ? a.X[(r0 + m) * a.ldx + d] : 0.0f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kT2Builders) : "memory");
+      }
+      if (warp == 1) MC_DBG(5);
+      if (bt < kT2Rows) ysm[b * kT2Rows + bt] = bt < rows ? ld_y(a.y, a.y_dtype, r0 + bt) : 0.0f;
+      unsigned char* b1 = B1 + b * b1_buf;
+      unsigned char* b2 = B2 + b * b2_buf;
+      // thread → (row block mb = bt & 15, feature chunks kc = (bt >> 4) + 8j): no divisions, 64-bit shared loads
+      const int mb = bt & 15;
+      for (int kc = bt >> 4; kc < kc1; kc += 8) {
+        float v[4][4];
+        const bool even = (ldx & 1) == 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int m = mb * 4 + r;
+          const float* rp = rawb + m * ldx + kc * 4;
+          if (even) {
+            const float2 p0 = *reinterpret_cast<const float2*>(rp);
+            const float2 p1 = *reinterpret_cast<const float2*>(rp + 2);
+            v[r][0] = p0.x;
+            v[r][1] = p0.y;
+            v[r][2] = p1.x;
+            v[r][3] = p1.y;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[r][e] = rp[e];
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (m >= rows || kc * 4 + e >= D) v[r][e] = 0.0f;
+        }
+        float hi[4][4], lo[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_tf32(v[r][e], hi[r][e], lo[r][e]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {  // B1: row 4mb+r, features 4kc..4kc+3
+          const int o = kc * 1024 + (mb * 4 + r) * 16;
+          *reinterpret_cast<float4*>(b1 + o) = make_float4(hi[r][0], hi[r][1], hi[r][2], hi[r][3]);
+          *reinterpret_cast<float4*>(b1 + b1_half + o) = make_float4(lo[r][0], lo[r][1], lo[r][2], lo[r][3]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {  // B2: feature 4kc+e, rows 4mb..4mb+3
+          const int o = mb * 1024 + (kc * 4 + e) * 16;
+          *reinterpret_cast<float4*>(b2 + o) = make_float4(hi[0][e], hi[1][e], hi[2][e], hi[3][e]);
+          *reinterpret_cast<float4*>(b2 + b2_half + o) = make_float4(lo[0][e], lo[1][e], lo[2][e], lo[3][e]);
+        }
+      }
+      // features Dp..63 of B2 are never written by the loop above: they stay zero from the one-time fill
+      if (warp == 1) MC_DBG(6);
+      fence_proxy_async_smem();
+      mbar_arrive(&bars[2 + b]);
+      if (warp == 1) MC_DBG(7);
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3, hf = (warp - 5) >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
+    for (int i = 0; i < nt; ++i) {
+      const int b = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      const long long r0 = row_begin + static_cast<long long>(i) * kT2Rows;
+      const int rows = row_end - r0 >= kT2Rows ? kT2Rows : static_cast<int>(row_end - r0);
+      mbar_wait_s(BAR(2, b), par);
+      if (warp == 5) MC_DBG(8);
+      tc_fence_after();
+      const float* ys = ysm + b * kT2Rows;
+      uint32_t vv[2][16];
+      tmem_ld16(tm + 64 * b + lane_base + hf * 32, vv[0]);
+      tmem_ld16(tm + 64 * b + lane_base + hf * 32 + 16, vv[1]);
+      tmem_wait_ld();
+      if (warp == 5) MC_DBG(9);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col = hf * 32 + cc * 16;
+        uint32_t vh[16], vl[16];
+        const uint32_t* v = vv[cc];
+        if (a.want_logp || a.family != 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = col + j;
+            float lpv, rv;
+            row_terms(a.family, __uint_as_float(v[j]), ys[m], a.lik_scale, lpv, rv);
+            if (m >= rows) {
+              lpv = 0.0f;
+              rv = 0.0f;
+            }
+            lp += static_cast<double>(lpv);
+            float h, l;
+            split_tf32(rv, h, l);
+            vh[j] = __float_as_uint(h);
+            vl[j] = __float_as_uint(l);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = col + j;
+            const float eta = __uint_as_float(v[j]);
+            const float e = expf(-fabsf(eta));
+            const float qv = __fdividef(e, 1.0f + e);
+            const float yv = ys[m];
+            float rv = eta >= 0.0f ? (yv - 1.0f) + qv : yv - qv;
+            if (m >= rows) rv = 0.0f;
+            float h, l;
+            split_tf32(rv, h, l);
+            vh[j] = __float_as_uint(h);
+            vl[j] = __float_as_uint(l);
+          }
+        }
+        tmem_st16(tm + 64 * b + lane_base + col, vh);
+        tmem_st16(tm + 128 + 64 * b + lane_base + col, vl);
+      }
+      if (warp == 5) MC_DBG(10);
+      tmem_wait_st();
+      if (warp == 5) MC_DBG(11);
+      tc_fence_before();
+      mbar_arrive(&bars[6 + b]);
+      if (warp == 5) MC_DBG(12);
+    }
+  }
+
+  // ---- write this row group's partial sums ----
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  double* lpc = reinterpret_cast<double*>(raw0);  // [2][128], the raw buffers are idle now
+  if (warp >= 5 && warp <= 12) {
+    const int q = warp & 3, hf = (warp - 5) >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
+    const int chain = cb + 32 * q + lane;
+    float* pg = a.part_g + (static_cast<size_t>(blockIdx.x) * a.C + chain) * Dp;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col = hf * 32 + cc * 16;
+      uint32_t v[16];
+      if (nt > 0) {
+        tmem_ld16(tm_g + lane_base + col, v);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col + j < Dp) pg[col + j] = __uint_as_float(v[j]);
+    }
+    lpc[hf * 128 + 32 * q + lane] = lp;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < kMcChainsPerCta) a.part_lp[static_cast<size_t>(blockIdx.x) * a.C + cb + tid] = lpc[tid] + lpc[128 + tid];
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tm, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core pass, version 3 (default): no per-pass hi/lo splitting, no builder warps.
+//
+// X is re-laid once (k_mc_pretile, at the first many-chain call after bind) into the UMMA operand layout:
+// per 64-row tile a hi plane and a lo plane (3xTF32 split), each [Dp/4][64 rows][4 floats] with a plane-row
+// pitch of 1040 B (K-major, no-swizzle core matrices; the 16 B of padding per 1024 make the transposing
+// reads below bank-conflict free). A tile is ONE contiguous TMA bulk copy and is used as it lands by
+//   MMA1  Sᵀ = Wᵀ·Xᵀ   B = tile, N=64 rows x K=Dp, K-major (LBO = 1040: next 4 features, SBO = 128: next 8 rows)
+// The second contraction needs the tile with rows as the K dimension. (An MN-major descriptor over the same
+// bytes returned zeros on this part, see DESIGN.md.) The epilogue warps therefore transpose the landed tile
+// once, 4x4 blocks through registers, into B2T[b] ([64/4][64 feats][4 rows], SBO = 144, LBO = 1152: padded so
+// the transposing stores are conflict free), while MMA1 of the same tile runs:
+//   MMA2  G' += R·X     A = R from TMEM, B = B2T[b], N=64 feats x K=64 rows, K-major
+// Warp roles (20 warps): 0 TMA producer, 1 MMA1 issuer, 2 MMA2 issuer, 3 idle, 4-19 epilogue (TMEM lane quadrant =
+// warp % 4, 16 of the tile's 64 columns each). NS-stage operand ring (3, or 2 when Dp = 64), S/R and B2T
+// double-buffered (b = tile & 1).
+//   x_full[s] (TMA) → {MMA1 → s_ready[b]} ‖ {transpose → B2T[b]} → epilogue → r_ready[b] (512 arrivals)
+//   → MMA2 → x_empty[s] (commit).  Tile i may overwrite S[b] / B2T[b] only after x_empty of tile i-2.
+// ------------------------------------------------------------------------------------------------
+constexpr int kT3MaxStages = 3;
+constexpr int kT3Threads = 20 * 32;
+constexpr int kT3Epilogue = 16 * 32;
+constexpr int kT3Pitch = 1040;      // bytes between feature chunks (kc) of a pre-tiled plane
+constexpr int kT3B2Sbo = 144;       // bytes between 8-feature groups of B2T
+constexpr int kT3B2Lbo = 8 * 144;   // bytes between 4-row groups of B2T
+constexpr int kT3B2Plane = 16 * kT3B2Lbo;
+
+__host__ __device__ inline int tc3_tile_bytes(int Dp) { return 2 * (Dp / 4) * kT3Pitch; }
+__host__ __device__ inline int tc3_stages(int Dp) { return Dp > 56 ? 2 : 3; }
+
+__host__ __device__ inline int tc3_smem_layout(int Dp, int* off /*8*/) {
+  int o = 0;
+  off[0] = o;  // operand ring
+  const int stage_bytes = (tc3_tile_bytes(Dp) + 127) / 128 * 128;
+  o += tc3_stages(Dp) * stage_bytes;
+  off[1] = o;  // ys[stages][64]
+  o += kT3MaxStages * kT2Rows * 4;
+  off[2] = o;  // A1 hi, lo
+  o += 2 * (Dp / 4) * 2048;
+  off[3] = o;  // B2T[2] {hi, lo}
+  o += 2 * 2 * kT3B2Plane;
+  off[4] = o;  // mbarriers: x_full[3], x_empty[3], s_ready[2], r_ready[2] + tmem slot
+  o += 128;
+  off[5] = o;  // logp combine [4][128] doubles
+  o += 4 * 128 * 8;
+  off[6] = stage_bytes;
+  return o;
+}
+
+// X → pre-tiled {hi, lo} operand planes + padded y. grid-stride; one thread per (tile, kc, m).
+__global__ void k_mc_pretile(const McArgs a, float* xt, float* yt) {
+  const int kc1 = a.Dp / 4;
+  const long long ntiles = (a.n_rows + kT2Rows - 1) / kT2Rows;
+  const long long total = ntiles * kc1 * kT2Rows;
+  const size_t plane = static_cast<size_t>(kc1) * (kT3Pitch / 4);  // floats per plane
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i % kT2Rows);
+    const long long r = i / kT2Rows;
+    const int kc = static_cast<int>(r % kc1);
+    const long long t = r / kc1;
+    const long long row = t * kT2Rows + m;
+    float4 h, l;
+    float* hp = &h.x;
+    float* lq = &l.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = kc * 4 + e;
+      const float v = (row < a.n_rows && d < a.D) ? a.X[row * a.ldx + d] : 0.0f;
+      split_tf32(v, hp[e], lq[e]);
+    }
+    float* base = xt + static_cast<size_t>(t) * 2 * plane + static_cast<size_t>(kc) * (kT3Pitch / 4) + m * 4;
+    *reinterpret_cast<float4*>(base) = h;
+    *reinterpret_cast<float4*>(base + plane) = l;
+    if (m < 4) {  // the 16 bytes of padding behind each 1024-byte chunk
+      float* pad = xt + static_cast<size_t>(t) * 2 * plane + static_cast<size_t>(kc) * (kT3Pitch / 4) + 256 + m;
+      pad[0] = 0.0f;
+      pad[plane] = 0.0f;
+    }
+    if (kc == 0) yt[t * kT2Rows + m] = row < a.n_rows ? ld_y(a.y, a.y_dtype, row) : 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, const float* theta, int gate) {
+  if (gate && !*a.need_init) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  int off[8];
+  const int Dp = a.Dp, D = a.D;
+  tc3_smem_layout(Dp, off);
+  const int stage_bytes = off[6];
+  const int NS = tc3_stages(Dp);
+  unsigned char* ring = smem + off[0];
+  float* ysm = reinterpret_cast<float*>(smem + off[1]);
+  unsigned char* A1 = smem + off[2];
+  unsigned char* B2T = smem + off[3];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off[4]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off[4] + 112);
+  double* lpc = reinterpret_cast<double*>(smem + off[5]);
+  const int kc1 = Dp / 4;
+  const int a1_half = kc1 * 2048;
+  const int plane_bytes = kc1 * kT3Pitch;
+  const int tile_bytes = 2 * plane_bytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cb = blockIdx.y * kMcChainsPerCta;
+  // barrier indices: 0-2 x_full, 3-5 x_empty, 6-7 s_ready, 8-9 r_ready
+  const uint32_t bar0 = smem_u32(bars);
+  auto XFULL = [&](int s) { return bar0 + static_cast<uint32_t>(s * 8); };
+  auto XEMPTY = [&](int s) { return bar0 + static_cast<uint32_t>((3 + s) * 8); };
+  auto SREADY = [&](int b) { return bar0 + static_cast<uint32_t>((6 + b) * 8); };
+  auto RREADY = [&](int b) { return bar0 + static_cast<uint32_t>((8 + b) * 8); };
+
+  if (tid == 0) {
+    for (int s = 0; s < kT3MaxStages; ++s) {
+      mbar_init(&bars[s], 1);
+      mbar_init(&bars[3 + s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars[6 + b], 1);
+      mbar_init(&bars[8 + b], kT3Epilogue);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  for (int i = tid; i < kMcChainsPerCta * kc1; i += kT3Threads) {
+    const int c = i % kMcChainsPerCta, kc = i / kMcChainsPerCta;
+    float4 h, l;
+    float* hp = &h.x;
+    float* lq = &l.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = kc * 4 + e;
+      const float v = d < D ? theta[static_cast<size_t>(cb + c) * D + d] : 0.0f;
+      split_tf32(v, hp[e], lq[e]);
+    }
+    *reinterpret_cast<float4*>(A1 + kc * 2048 + c * 16) = h;
+    *reinterpret_cast<float4*>(A1 + a1_half + kc * 2048 + c * 16) = l;
+  }
+  // B2T: features Dp..63 and the padding are never written by the transpose: zero once
+  for (int i = tid; i < 4 * kT3B2Plane / 16; i += kT3Threads) reinterpret_cast<float4*>(B2T)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t tm_g = tm + 256;
+
+  long long u0, u1;
+  tile_range(a.n_rows, a.n_rowgroups, blockIdx.x, u0, u1);
+  const long long row_begin = u0 * kMcTileRows;
+  long long row_end = u1 * kMcTileRows;
+  if (row_end > a.n_rows) row_end = a.n_rows;
+  const long long tile0 = row_begin / kT2Rows;  // row_begin is a multiple of 128
+  const int nt = row_end > row_begin ? static_cast<int>((row_end - row_begin + kT2Rows - 1) / kT2Rows) : 0;
+  double lp = 0.0;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % NS;
+      if (i >= NS) mbar_wait_s(XEMPTY(s), ((i / NS) - 1) & 1);
+      if (elect_one()) {
+        fence_proxy_async_smem();
+        mbar_arrive_expect_tx_s(XFULL(s), tile_bytes + kT2Rows * 4);
+        bulk_g2s_s(smem_u32(ring + s * stage_bytes), a.xt + static_cast<size_t>(tile0 + i) * (tile_bytes / 4), tile_bytes, XFULL(s));
+        bulk_g2s_s(smem_u32(ysm + s * kT2Rows), a.yt + (tile0 + i) * kT2Rows, kT2Rows * 4, XFULL(s));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ================= MMA1 issuer: Sᵀ[b] = Wᵀ·X(i)ᵀ =================
+    const uint64_t da_h = smem_desc(smem_u32(A1), 2048, 128), da_l = smem_desc(smem_u32(A1) + a1_half, 2048, 128);
+    const uint32_t id1 = idesc_tf32(128, kT2Rows);
+    const int nks = Dp / 8;
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % NS, b = i & 1;
+      mbar_wait_s(XFULL(s), (i / NS) & 1);
+      if (i >= 2) mbar_wait_s(XEMPTY((i - 2) % NS), ((i - 2) / NS) & 1);  // MMA2(i-2) has read R[b]
+      tc_fence_after();
+      const uint32_t xs = smem_u32(ring + s * stage_bytes);
+      const uint64_t db_h = smem_desc(xs, kT3Pitch, 128), db_l = smem_desc(xs + plane_bytes, kT3Pitch, 128);
+      const uint32_t ts = tm + 64 * b;
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          if (ks < nks) {
+            const uint64_t oa = static_cast<uint64_t>(ks * (4096 >> 4)), ob = static_cast<uint64_t>(ks * ((2 * kT3Pitch) >> 4));
+            tc_mma_ss(ts, da_h + oa, db_h + ob, id1, ks > 0);
+            tc_mma_ss(ts, da_h + oa, db_l + ob, id1, 1);
+            tc_mma_ss(ts, da_l + oa, db_h + ob, id1, 1);
+          }
+        }
+        tc_commit(SREADY(b));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    // ================= MMA2 issuer: G' += R(i)·X(i), A = R from TMEM, B = B2T[b] =================
+    const uint32_t id2 = idesc_tf32(128, kTcN2);
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % NS, b = i & 1;
+      mbar_wait_s(RREADY(b), (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t bs = smem_u32(B2T + b * 2 * kT3B2Plane);
+      const uint64_t d2_h = smem_desc(bs, kT3B2Lbo, kT3B2Sbo), d2_l = smem_desc(bs + kT3B2Plane, kT3B2Lbo, kT3B2Sbo);
+      const uint32_t r_h = tm + 64 * b, r_l = tm + 128 + 64 * b;
+      const uint32_t first = (i > 0) ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < kT2Rows / 8; ++ks) {
+          const uint64_t o = static_cast<uint64_t>(ks * ((2 * kT3B2Lbo) >> 4));  // 8 rows = 2 row groups
+          tc_mma_ts(tm_g, r_h + ks * 8, d2_h + o, id2, ks > 0 ? 1u : first);
+          tc_mma_ts(tm_g, r_h + ks * 8, d2_l + o, id2, 1);
+          tc_mma_ts(tm_g, r_l + ks * 8, d2_h + o, id2, 1);
+        }
+        tc_commit(XEMPTY(s));  // stage s, ys[s], S[b]/R[b] and B2T[b] are free again
+      }
+      __syncwarp();
+    }
+    if (nt > 0) mbar_wait_s(XEMPTY((nt - 1) % NS), ((nt - 1) / NS) & 1);  // the last commit covers every MMA
+  } else if (warp >= 4) {
+    // ================= epilogue (16 warps): transpose the landed tile, then Sᵀ → R =================
+    const int q = warp & 3, cg = (warp - 4) >> 2;  // TMEM lane quadrant, column group (16 columns)
+    const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
+    const int col = cg * 16;
+    // transpose work item of this thread: plane p (hi/lo), feature chunk kc, row block mb; kc fastest across lanes
+    const int et = tid - 128;
+    const int npk = 2 * kc1;              // (plane, kc) pairs
+    const int pk = et % npk, mbt = et / npk;  // valid when mbt < 16
+    const int tp = pk / kc1, tkc = pk - tp * kc1;
+    const bool has_item = mbt < 16;
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % NS, b = i & 1;
+      const long long r0 = row_begin + static_cast<long long>(i) * kT2Rows;
+      const int rows = row_end - r0 >= kT2Rows ? kT2Rows : static_cast<int>(row_end - r0);
+      mbar_wait_s(XFULL(s), (i / NS) & 1);
+      if (i >= 2) mbar_wait_s(XEMPTY((i - 2) % NS), ((i - 2) / NS) & 1);  // MMA2(i-2) has read B2T[b]
+      if (has_item) {
+        const unsigned char* src = ring + s * stage_bytes + tp * plane_bytes + tkc * kT3Pitch + mbt * 64;
+        float4 v0 = *reinterpret_cast<const float4*>(src);
+        float4 v1 = *reinterpret_cast<const float4*>(src + 16);
+        float4 v2 = *reinterpret_cast<const float4*>(src + 32);
+        float4 v3 = *reinterpret_cast<const float4*>(src + 48);
+        const int d0 = tkc * 4;
+        unsigned char* dst = B2T + b * 2 * kT3B2Plane + tp * kT3B2Plane + mbt * kT3B2Lbo + (d0 >> 3) * kT3B2Sbo + (d0 & 7) * 16;
+        *reinterpret_cast<float4*>(dst) = make_float4(v0.x, v1.x, v2.x, v3.x);
+        *reinterpret_cast<float4*>(dst + 16) = make_float4(v0.y, v1.y, v2.y, v3.y);
+        *reinterpret_cast<float4*>(dst + 32) = make_float4(v0.z, v1.z, v2.z, v3.z);
+        *reinterpret_cast<float4*>(dst + 48) = make_float4(v0.w, v1.w, v2.w, v3.w);
+      }
+      fence_proxy_async_smem();
+      mbar_wait_s(SREADY(b), (i >> 1) & 1);
+      tc_fence_after();
+      const float* ys = ysm + s * kT2Rows;
+      uint32_t v[16], vh[16], vl[16];
+      tmem_ld16(tm + 64 * b + lane_base + col, v);
+      tmem_wait_ld();
+      if (a.want_logp || a.family != 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int m = col + j;
+          float lpv, rv;
+          row_terms(a.family, __uint_as_float(v[j]), ys[m], a.lik_scale, lpv, rv);
+          if (m >= rows) {
+            lpv = 0.0f;
+            rv = 0.0f;
+          }
+          lp += static_cast<double>(lpv);
+          float h, l;
+          split_tf32(rv, h, l);
+          vh[j] = __float_as_uint(h);
+          vl[j] = __float_as_uint(l);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int m = col + j;
+          const float eta = __uint_as_float(v[j]);
+          const float e = expf(-fabsf(eta));
+          const float qv = __fdividef(e, 1.0f + e);
+          const float yv = ys[m];
+          float rv = eta >= 0.0f ? (yv - 1.0f) + qv : yv - qv;
+          if (m >= rows) rv = 0.0f;
+          float h, l;
+          split_tf32(rv, h, l);
+          vh[j] = __float_as_uint(h);
+          vl[j] = __float_as_uint(l);
+        }
+      }
+      tmem_st16(tm + 64 * b + lane_base + col, vh);
+      tmem_st16(tm + 128 + 64 * b + lane_base + col, vl);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars[8 + b]);  // R[b] and B2T[b] are ready
+    }
+  }
+
+  // ---- write this row group's partial sums ----
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp >= 4) {
+    const int q = warp & 3, cg = (warp - 4) >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
+    const int chain = cb + 32 * q + lane;
+    float* pg = a.part_g + (static_cast<size_t>(blockIdx.x) * a.C + chain) * Dp;
+    const int col = cg * 16;
+    uint32_t v[16];
+    if (nt > 0) {
+      tmem_ld16(tm_g + lane_base + col, v);
+      tmem_wait_ld();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col + j < Dp) pg[col + j] = __uint_as_float(v[j]);
+    lpc[cg * 128 + 32 * q + lane] = lp;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < kMcChainsPerCta)
+    a.part_lp[static_cast<size_t>(blockIdx.x) * a.C + cb + tid] = (lpc[tid] + lpc[128 + tid]) + (lpc[256 + tid] + lpc[384 + tid]);
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tm, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-chain kernels: grid = C blocks of 64 threads (thread d = feature d)
 // ------------------------------------------------------------------------------------------------
 constexpr int kMcChainThreads = 64;
@@ -602,13 +1298,45 @@ int mc_smem_bytes_tc(int Dp) {
   return tc_smem_layout(Dp, kMcMaxD, off);
 }
 
+size_t mc_pretile_bytes(long long n_rows, int Dp, size_t* yt_bytes) {
+  const long long ntiles = (n_rows + kT2Rows - 1) / kT2Rows;
+  *yt_bytes = static_cast<size_t>(ntiles) * kT2Rows * sizeof(float);
+  return static_cast<size_t>(ntiles) * tc3_tile_bytes(Dp);
+}
+
+cudaError_t mc_launch_pretile(const McArgs& a, float* xt, float* yt, cudaStream_t s) {
+  k_mc_pretile<<<148 * 8, 256, 0, s>>>(a, xt, yt);
+  return cudaGetLastError();
+}
+
 cudaError_t mc_prepare_tc() {
+  int off[8];
+  {
+    int mx = 0;
+    for (int dp = 8; dp <= kMcMaxD; dp += 8) {
+      const int b = tc3_smem_layout(dp, off);
+      if (b > mx) mx = b;
+    }
+    cudaError_t e3 = cudaFuncSetAttribute(k_mc_pass_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (e3 != cudaSuccess) return e3;
+  }
+  cudaError_t e = cudaFuncSetAttribute(k_mc_pass_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       tc2_smem_layout(kMcMaxD, kMcMaxD, off));
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_mc_pass_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, mc_smem_bytes_tc(kMcMaxD));
 }
 
 cudaError_t mc_launch_pass(const McArgs& a, const float* theta, int use_tc, int gate, cudaStream_t s) {
   dim3 grid(a.n_rowgroups, a.C / kMcChainsPerCta);
-  if (use_tc) {
+  if (use_tc == 3) {
+    int off[8];
+    const int smem = tc3_smem_layout(a.Dp, off);
+    k_mc_pass_tc3<<<grid, kT3Threads, smem, s>>>(a, theta, gate);
+  } else if (use_tc == 2) {
+    int off[8];
+    const int smem = tc2_smem_layout(a.Dp, static_cast<int>(a.ldx), off);
+    k_mc_pass_tc2<<<grid, kT2Threads, smem, s>>>(a, theta, gate);
+  } else if (use_tc == 1) {
     int off[8];
     const int smem = tc_smem_layout(a.Dp, static_cast<int>(a.ldx), off);
     k_mc_pass_tc<<<grid, kTcThreads, smem, s>>>(a, theta, gate);

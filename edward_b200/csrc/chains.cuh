@@ -57,12 +57,18 @@ struct McArgs {
   const float* u;   // [n_iter][C] or null
   unsigned long long seed;
   double* trace;  // [n_iter][C][8] or null
+  // pre-tiled operand copy of X for the tensor-core pass (k_mc_pretile): per 64-row tile {hi, lo} x [Dp/4][64][4] f32
+  const float* xt;
+  const float* yt;  // [ntiles64][64] float
+  long long* dbg;  // optional per-role clock64 timeline of CTA (0,0): [tile][16]
 };
 
 // host launchers (chains.cu)
 int mc_smem_bytes_tc(int Dp);
 cudaError_t mc_prepare_tc();
 cudaError_t mc_launch_pass(const McArgs& a, const float* theta, int use_tc, int gate, cudaStream_t s);
+cudaError_t mc_launch_pretile(const McArgs& a, float* xt, float* yt, cudaStream_t s);
+size_t mc_pretile_bytes(long long n_rows, int Dp, size_t* yt_bytes);
 cudaError_t mc_launch_check(const McArgs& a, cudaStream_t s);
 cudaError_t mc_launch_init_finish(const McArgs& a, cudaStream_t s);
 cudaError_t mc_launch_begin(const McArgs& a, long long it, cudaStream_t s);

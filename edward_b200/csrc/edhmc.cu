@@ -147,6 +147,10 @@ struct edhmc_handle {
   long long* mc_nacc = nullptr;
   int* mc_flags = nullptr;  // [0] valid, [1] need_init
   double* mc_trace = nullptr;
+  long long* mc_dbg = nullptr;
+  float* mc_xt = nullptr;  // pre-tiled operand copy of X (tensor-core pass v3)
+  float* mc_yt = nullptr;
+  bool mc_pretiled = false;
   // stats
   long long passes_last = 0, launches_last = 0;
   int plan_in_use = 0;
@@ -405,8 +409,22 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
     if (nrg < 1) nrg = 1;
     if (nrg > ntiles) nrg = ntiles > 0 ? ntiles : 1;
     h->mc_nrg = static_cast<int>(nrg);
-    h->mc_use_tc = cfg->ldx <= kMcMaxD ? 1 : 0;
-    if (const char* e = getenv("EDHMC_MC_IMPL")) h->mc_use_tc = (strcmp(e, "tc") == 0 && cfg->ldx <= kMcMaxD) ? 1 : 0;
+    // pass implementation: 3 = pre-tiled pipelined tcgen05 (default), 2 = pipelined with per-pass operand
+    // builders, 1 = sequential tcgen05, 0 = CUDA cores
+    h->mc_use_tc = 3;
+    if (const char* e = getenv("EDHMC_MC_IMPL")) {
+      if (strcmp(e, "simple") == 0) h->mc_use_tc = 0;
+      else if (strcmp(e, "tc1") == 0) h->mc_use_tc = 1;
+      else if (strcmp(e, "tc2") == 0) h->mc_use_tc = 2;
+      else if (strcmp(e, "tc") == 0) h->mc_use_tc = 3;
+    }
+    if ((h->mc_use_tc == 1 || h->mc_use_tc == 2) && cfg->ldx > kMcMaxD) h->mc_use_tc = 3;
+    if (h->mc_use_tc == 3) {
+      size_t ytb = 0;
+      const size_t xtb = mc_pretile_bytes(cfg->n_rows, h->mc_Dp, &ytb);
+      ALLOC(h->mc_xt, xtb + 4096);
+      ALLOC(h->mc_yt, ytb + 256);
+    }
     const size_t cd = static_cast<size_t>(h->C) * cfg->n_features * sizeof(float);
     ALLOC(h->mc_z, cd);
     ALLOC(h->mc_r, cd);
@@ -480,6 +498,8 @@ int edhmc_destroy(edhmc_t* h) {
   cudaFree(h->mc_flags);
   cudaFree(h->mc_part_g);
   cudaFree(h->mc_part_lp);
+  cudaFree(h->mc_xt);
+  cudaFree(h->mc_yt);
   delete h;
   return 0;
 }
@@ -506,6 +526,7 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
   // data changed: the cached log joint / gradient no longer apply
   CUDA_TRY(cudaMemsetAsync(&h->d_sc->valid, 0, sizeof(int), stream));
   if (h->mc_flags) CUDA_TRY(cudaMemsetAsync(h->mc_flags, 0, 2 * sizeof(int), stream));
+  h->mc_pretiled = false;
   if (check_finite && h->cfg.n_rows > 0) {
     CUDA_TRY(cudaMemsetAsync(h->d_bad, 0, sizeof(unsigned long long), stream));
     k_check_finite<<<h->num_sms * 8, 256, 0, stream>>>(X, h->cfg.n_rows, h->cfg.ldx, h->cfg.n_features, h->y,
@@ -722,6 +743,18 @@ static void fill_mc_args(edhmc_handle* h, McArgs& a) {
   a.part_lp = h->mc_part_lp;
   a.seed = h->seed;
   a.trace = h->mc_trace;
+  a.dbg = h->mc_dbg;
+  a.xt = h->mc_xt;
+  a.yt = h->mc_yt;
+}
+
+// Re-lays X into the tensor-core operand layout once per bound data set.
+static int mc_ensure_pretiled(edhmc_handle* h, const McArgs& a, cudaStream_t stream) {
+  if (h->mc_use_tc == 3 && !h->mc_pretiled) {
+    CUDA_TRY(mc_launch_pretile(a, h->mc_xt, h->mc_yt, stream));
+    h->mc_pretiled = true;
+  }
+  return 0;
 }
 
 int edhmc_run_chains(edhmc_t* h, float* params, int64_t T, int64_t t0, int64_t n_iter, float step_size, int32_t n_steps,
@@ -747,6 +780,7 @@ int edhmc_run_chains(edhmc_t* h, float* params, int64_t T, int64_t t0, int64_t n
   a.u = u;
   h->launches_last = 0;
   h->passes_last = n_iter * n_steps;
+  if (int rc = mc_ensure_pretiled(h, a, stream)) return rc;
   CUDA_TRY(mc_launch_check(a, stream));
   CUDA_TRY(mc_launch_pass(a, h->mc_zcur, h->mc_use_tc, 1, stream));
   CUDA_TRY(mc_launch_init_finish(a, stream));
@@ -773,6 +807,7 @@ int edhmc_logp_grad_chains(edhmc_t* h, const float* theta, double* logp, float* 
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   McArgs a;
   fill_mc_args(h, a);
+  if (int rc = mc_ensure_pretiled(h, a, stream)) return rc;
   CUDA_TRY(mc_launch_pass(a, theta, h->mc_use_tc, 0, stream));
   CUDA_TRY(mc_launch_logp_grad_finish(a, theta, logp, grad, stream));
   h->launches_last = 2;
@@ -788,6 +823,12 @@ int edhmc_read_chain_state(edhmc_t* h, int64_t* n_accept_host, double* logp_host
   if (n_accept_host) CUDA_TRY(cudaMemcpyAsync(n_accept_host, h->mc_nacc, h->C * sizeof(long long), cudaMemcpyDeviceToHost, stream));
   if (logp_host) CUDA_TRY(cudaMemcpyAsync(logp_host, h->mc_logp, h->C * sizeof(double), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int edhmc_set_chain_debug(edhmc_t* h, long long* buf) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  h->mc_dbg = buf;
   return 0;
 }
 

@@ -159,6 +159,8 @@ int edhmc_run_chains(edhmc_t* h, float* params, int64_t T, int64_t t0, int64_t n
 int edhmc_logp_grad_chains(edhmc_t* h, const float* theta, double* logp, float* grad, void* stream);
 int edhmc_read_chain_state(edhmc_t* h, int64_t* n_accept_host /*[C]*/, double* logp_host /*[C]*/, void* stream);
 int edhmc_set_chain_trace(edhmc_t* h, double* trace);
+/* Development aid: [64][16] int64 per-role clock64 timeline of one CTA of the pipelined tensor-core pass. */
+int edhmc_set_chain_debug(edhmc_t* h, long long* buf);
 
 /* Introspection for benches/tests: fills up to `cap` int64 values:
  * {grid_ctas, warps_per_cta, ring_stages, tile_rows, lanes_per_row, vec_width, smem_bytes,
