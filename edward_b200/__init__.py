@@ -7,7 +7,7 @@ own Python surface.
     from edward_b200.models import Bernoulli, Empirical, Normal
 """
 from . import inferences, models, util  # noqa: F401
-from .inferences import HMC, Inference, MonteCarlo  # noqa: F401
+from .inferences import HMC, SGHMC, SGLD, Inference, MonteCarlo  # noqa: F401
 from .models import RandomVariable  # noqa: F401
 from .util import Progbar, check_data, check_latent_vars, dot, get_session, random_variables, set_seed  # noqa: F401
 

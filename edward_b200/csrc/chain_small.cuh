@@ -118,6 +118,49 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_chain_leap(const KArgs a, 
   }
 }
 
+// One SGLD / SGHMC update after the pass at params[max(t-1,0)] (sgld.py:52-87, sghmc.py:58-96); float32 in the
+// op order of the reference graph.
+struct SgArgs {
+  int kind;
+  float step_size, friction, lik_factor;
+  const float* prior_factor;
+  float* velocity;
+  const float* noise;
+};
+__global__ void __launch_bounds__(kChainThreads, 1) k_sg_update(const KArgs a, const SgArgs g, long long it) {
+  const long long t = a.t0 + it;
+  const long long t_prev = t > 0 ? t - 1 : 0;
+  float lr, sd;
+  if (g.kind == 0) {
+    lr = __fdiv_rn(g.step_size, powf(static_cast<float>(t + 1), 0.55f));
+    sd = sqrtf(lr);
+  } else {
+    lr = __fmul_rn(g.step_size, 0.01f);
+    sd = sqrtf(__fmul_rn(lr, g.friction));
+  }
+  for (int c = threadIdx.x; c < a.P; c += kChainThreads) {
+    const float old = a.params[t_prev * a.ldp + c];
+    const double pf = g.prior_factor ? static_cast<double>(g.prior_factor[c]) : 1.0;
+    const float grad = static_cast<float>(static_cast<double>(g.lik_factor) * a.sums[c] +
+                                          pf * prior_grad(old, a.prior_loc[c], a.prior_scale[c]));
+    const float nz = g.noise ? g.noise[it * a.P + c] : philox_normal(a.seed, t, c);
+    float out;
+    if (g.kind == 0) {
+      out = __fadd_rn(__fadd_rn(old, __fmul_rn(__fmul_rn(0.5f, lr), grad)), __fmul_rn(sd, nz));
+    } else {
+      const float v = g.velocity[c];
+      out = __fadd_rn(old, v);
+      g.velocity[c] = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(1.0f, __fmul_rn(0.5f, g.friction)), v), __fmul_rn(lr, grad)),
+                                __fmul_rn(sd, nz));
+    }
+    a.params[t * a.ldp + c] = out;
+  }
+  if (threadIdx.x == 0) {
+    a.sc->n_accept += 1;
+    a.sc->valid = 0;  // the HMC cache does not describe this row
+  }
+}
+
 // edhmc_logp_grad epilogue: prior + all-reduced sums → caller's buffers.
 __global__ void __launch_bounds__(kChainThreads, 1) k_logp_grad_finish(const KArgs a, const float* theta, double* logp_out,
                                                                  float* grad_out) {

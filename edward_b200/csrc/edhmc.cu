@@ -709,6 +709,60 @@ int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t 
   return 0;
 }
 
+int edhmc_sgmcmc_run(edhmc_t* h, int32_t kind, float* params, int64_t ldp, int64_t T, int64_t t0, int64_t n_iter,
+                     float step_size, float friction, float lik_factor, const float* prior_factor, float* velocity,
+                     const float* noise, int64_t batch_rows, void* stream_) {
+  if (!h || !params) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data has not been called");
+  if (kind != 0 && kind != 1) return fail(EDHMC_ERR_INVALID, "kind must be 0 (SGLD) or 1 (SGHMC)");
+  if (kind == 1 && !velocity) return fail(EDHMC_ERR_INVALID, "SGHMC needs a velocity buffer");
+  if (ldp < h->P) return fail(EDHMC_ERR_INVALID, "ldp (%lld) < number of latent dimensions (%d)", (long long)ldp, h->P);
+  if (n_iter < 0 || t0 < 0) return fail(EDHMC_ERR_INVALID, "negative n_iter / t0");
+  if (t0 + n_iter > T)
+    return fail(EDHMC_ERR_RANGE, "indices[0] = %lld is not in [0, %lld)", (long long)(t0 + n_iter - 1), (long long)T);
+  if (batch_rows < 0 || batch_rows % 4 != 0 || batch_rows > h->cfg.n_rows)
+    return fail(EDHMC_ERR_INVALID, "batch_rows must be a multiple of 4 in [0, n_rows]");
+  if (n_iter == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  KArgs a;
+  fill_args(h, a);
+  a.params = params;
+  a.ldp = ldp;
+  a.t0 = t0;
+  a.n_iter = n_iter;
+  SgArgs g;
+  g.kind = kind;
+  g.step_size = step_size;
+  g.friction = friction;
+  g.lik_factor = lik_factor;
+  g.prior_factor = prior_factor;
+  g.velocity = velocity;
+  g.noise = noise;
+  h->launches_last = 0;
+  h->passes_last = n_iter;
+  h->plan_in_use = EDHMC_PLAN_STEPWISE;
+  const int64_t nb = batch_rows > 0 ? h->cfg.n_rows / batch_rows : 1;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t t = t0 + it;
+    const int64_t t_prev = t > 0 ? t - 1 : 0;
+    KArgs ab = a;
+    if (batch_rows > 0) {  // mini-batch: a contiguous slice of the bound rows
+      const int64_t lo = (t % nb) * batch_rows;
+      ab.X = a.X + lo * a.ldx;
+      ab.y = reinterpret_cast<const char*>(a.y) + lo * 4;
+      ab.n_rows = batch_rows;
+    }
+    int rc;
+    if ((rc = launch_pass(h, ab, params + t_prev * ldp, 0, t, stream))) return rc;
+    if ((rc = allreduce_sums(h, stream))) return rc;
+    k_sg_update<<<1, kChainThreads, 0, stream>>>(a, g, it);
+    CUDA_TRY(cudaGetLastError());
+    ++h->launches_last;
+  }
+  return 0;
+}
+
 // ---- vectorised chains -----------------------------------------------------------------------------
 static void fill_mc_args(edhmc_handle* h, McArgs& a) {
   memset(&a, 0, sizeof(a));

@@ -150,6 +150,33 @@ class GLMSampler:
       _C.check(self.lib.edhmc_run(self._h, params.data_ptr(), int(params.stride(0)), int(params.shape[0]), int(t0),
                                   int(n_iter), float(step_size), int(n_steps), r0p, up, _stream_ptr(self.dev)))
 
+  # ---- SGLD / SGHMC on the same gradient kernel (sgld.py:52-87, sghmc.py:58-96) -----------------
+  def sgmcmc_run(self, kind: str, params: torch.Tensor, t0: int, n_iter: int, step_size: float, friction: float = 0.1,
+                 lik_factor: float = 1.0, prior_factor=None, velocity: Optional[torch.Tensor] = None,
+                 noise: Optional[torch.Tensor] = None, batch_rows: int = 0):
+    if params.device != self.dev or params.dtype != torch.float32:
+      raise TypeError("params must be a float32 tensor on %s" % self.dev)
+    if params.dim() == 1:
+      params = params.view(-1, 1)
+    k = {"sgld": 0, "sghmc": 1}[kind]
+    pf = None
+    if prior_factor is not None:
+      self._pf = self._to_device(prior_factor, torch.float32).contiguous().reshape(self.P)
+      pf = self._pf.data_ptr()
+    if k == 1 and velocity is None:
+      raise ValueError("SGHMC needs a velocity tensor")
+    nz = None
+    if noise is not None:
+      noise = self._to_device(noise, torch.float32).contiguous()
+      if noise.numel() < n_iter * self.P:
+        raise ValueError("noise must hold n_iter*P draws")
+      nz = noise.data_ptr()
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_sgmcmc_run(self._h, k, params.data_ptr(), int(params.stride(0)), int(params.shape[0]), int(t0),
+                                         int(n_iter), float(step_size), float(friction), float(lik_factor), pf,
+                                         velocity.data_ptr() if velocity is not None else None, nz, int(batch_rows),
+                                         _stream_ptr(self.dev)))
+
   # ---- C vectorised chains (extension) ---------------------------------------------------------
   def logp_grad_chains(self, theta):
     """theta [C, P] → (logp [C] float64, grad [C, P] float32), one dense contraction on the tensor cores."""

@@ -148,6 +148,19 @@ int edhmc_seed(edhmc_t* h, uint64_t seed);
 int edhmc_comm_unique_id(void* id128_host);
 int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t rank);
 
+/* ---- Stochastic-gradient MCMC on the same log-joint gradient --------------------------------
+ * n_iter iterations t = t0.. of SGLD (kind 0, edward/inferences/sgld.py:52-87) or SGHMC (kind 1, sghmc.py:58-96):
+ * one gradient evaluation at row max(t-1,0) of `params`, then
+ *   SGLD   lr = step_size/(t+1)^0.55;  row t = old + 0.5*lr*grad + sqrt(lr)*noise
+ *   SGHMC  lr = 0.01*step_size;  row t = old + v;  v = (1-0.5*friction)*v + lr*grad + sqrt(lr*friction)*noise
+ * grad = lik_factor * grad_lik + prior_factor[c] * grad_prior  (the `scale` argument of Inference.initialize,
+ * sgld.py:106-119; prior_factor NULL = 1). batch_rows > 0: iteration t uses the rows of mini-batch (t mod
+ * floor(n_rows/batch_rows)) of the bound data (multiple of 4). velocity [P] device (SGHMC, in/out). noise
+ * [n_iter, P] or NULL → device Philox. n_accept += 1 per iteration (sgld.py:86). */
+int edhmc_sgmcmc_run(edhmc_t* h, int32_t kind, float* params, int64_t ldp, int64_t T, int64_t t0, int64_t n_iter,
+                     float step_size, float friction, float lik_factor, const float* prior_factor, float* velocity,
+                     const float* noise, int64_t batch_rows, void* stream);
+
 /* ---- C vectorised chains (extension; the reference runs one chain per ed.HMC object) -------------------------
  * Every chain is an independent HMC chain on the same data: per leapfrog step the C gradients are one dense
  * contraction S = X·W, G = Xᵀ·(y − σ(S)) executed on the tcgen05 tensor cores in 3xTF32 (TMEM accumulators).

@@ -364,3 +364,66 @@ def toy_dataset_cfg1(N=40, noise_std=0.1):
   X = (X - 4.0) / 4.0
   X = X.reshape((N, 1))
   return X, y
+
+
+# --------------------------------------------------------------------------------------------
+# SGLD / SGHMC — edward/inferences/sgld.py:52-121, sghmc.py:58-130
+# --------------------------------------------------------------------------------------------
+def scaled_grad_log_joint(X, y, theta, spec: GLMSpec, lik_factor=1.0, prior_factor=None, dtype=np.float64):
+  """Gradient of SGLD._log_joint (sgld.py:89-121): every log_prob term is multiplied by `scale.get(rv, 1.0)`
+  before it is summed, so the likelihood gradient carries lik_factor and each prior gradient its own factor."""
+  theta = np.asarray(theta, dtype)
+  D = spec.n_features
+  eta = linear_predictor(X, theta, spec, dtype)
+  r = log_lik_grad_eta(eta, y, spec, dtype)
+  g = np.empty(spec.n_params, dtype)
+  g[:D] = np.matmul(np.asarray(X, dtype).T, r[:, None]).reshape(-1)
+  if spec.has_bias:
+    g[D] = np.sum(r, dtype=dtype)
+  pf = np.ones(spec.n_params, dtype) if prior_factor is None else np.asarray(prior_factor, dtype)
+  return (dtype(lik_factor) * g + pf * normal_log_prob_grad(theta, spec.prior_loc, spec.prior_scale, dtype)).astype(dtype)
+
+
+def sgld_run(X, y, params, noise, step_size, spec: GLMSpec, dtype=np.float64, t0=0, n_iter=None, lik_factor=1.0,
+             prior_factor=None, batch_rows=0):
+  """SGLD.build_update (sgld.py:52-87): lr = step_size / (t+1)^0.55; sample = old + 0.5*lr*grad + sqrt(lr)*normal,
+  old = params[max(t-1,0)], written to params[t]. batch_rows > 0: mini-batch (t mod floor(N/B)) of the rows."""
+  T = params.shape[0]
+  n_iter = T - t0 if n_iter is None else n_iter
+  N = X.shape[0]
+  for i in range(n_iter):
+    t = t0 + i
+    old = np.array(params[max(t - 1, 0)], dtype)
+    if batch_rows:
+      lo = (t % (N // batch_rows)) * batch_rows
+      Xb, yb = X[lo:lo + batch_rows], y[lo:lo + batch_rows]
+    else:
+      Xb, yb = X, y
+    lr = dtype(step_size) / np.power(dtype(t + 1), dtype(0.55))
+    g = scaled_grad_log_joint(Xb, yb, old, spec, lik_factor, prior_factor, dtype)
+    params[t] = old + dtype(0.5) * lr * g + np.sqrt(lr) * np.asarray(noise[i], dtype)
+  return params
+
+
+def sghmc_run(X, y, params, noise, step_size, friction, spec: GLMSpec, dtype=np.float64, t0=0, n_iter=None,
+              lik_factor=1.0, prior_factor=None, v0=None, batch_rows=0):
+  """SGHMC.build_update (sghmc.py:58-96): lr = 0.01*step_size; sample = old + v; v = (1-0.5*friction)*v + lr*grad(old)
+  + sqrt(lr*friction)*normal. Returns the final velocity."""
+  T = params.shape[0]
+  n_iter = T - t0 if n_iter is None else n_iter
+  v = np.zeros(spec.n_params, dtype) if v0 is None else np.array(v0, dtype)
+  N = X.shape[0]
+  lr = dtype(step_size) * dtype(0.01)
+  sd = np.sqrt(lr * dtype(friction))
+  for i in range(n_iter):
+    t = t0 + i
+    old = np.array(params[max(t - 1, 0)], dtype)
+    if batch_rows:
+      lo = (t % (N // batch_rows)) * batch_rows
+      Xb, yb = X[lo:lo + batch_rows], y[lo:lo + batch_rows]
+    else:
+      Xb, yb = X, y
+    g = scaled_grad_log_joint(Xb, yb, old, spec, lik_factor, prior_factor, dtype)
+    params[t] = old + v
+    v = (dtype(1.0) - dtype(0.5) * dtype(friction)) * v + lr * g + sd * np.asarray(noise[i], dtype)
+  return v
