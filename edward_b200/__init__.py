@@ -6,7 +6,9 @@ own Python surface.
     from edward_b200 import tfshim as tf
     from edward_b200.models import Bernoulli, Empirical, Normal
 """
-from . import inferences, models, util  # noqa: F401
+from . import criticisms, inferences, models, util  # noqa: F401
+from .criticisms import evaluate, ppc  # noqa: F401
+from .util.copying import copy  # noqa: F401
 from .inferences import HMC, SGHMC, SGLD, Inference, MonteCarlo  # noqa: F401
 from .models import RandomVariable  # noqa: F401
 from .util import Progbar, check_data, check_latent_vars, dot, get_session, random_variables, set_seed  # noqa: F401

@@ -375,10 +375,16 @@ class Lazy(Tensor):
   """A node whose value is produced by a Python callable at evaluation time (random draws, Empirical
   statistics read back from the device store)."""
 
-  def __init__(self, fn, shape, dtype, op_type="Lazy"):
+  def __init__(self, fn, shape, dtype, op_type="Lazy", wants_feed=False):
     self.fn = fn
     self.op_type = op_type
+    self.wants_feed = wants_feed  # fn(feed) receives the internal {id(node): value} feed of this evaluation
     super(Lazy, self).__init__(shape, dtype)
 
   def _eval(self, feed):
-    return np.asarray(self.fn(), self.dtype.np)
+    return np.asarray(self.fn(feed) if self.wants_feed else self.fn(), self.dtype.np)
+
+
+def eval_in(node, feed):
+  """Evaluates `node` inside an ongoing evaluation (feed = internal {id(node): value} dict)."""
+  return convert_to_tensor(node)._eval(feed or {})

@@ -165,5 +165,26 @@ class HMC(MonteCarlo):
     if self.n_print == 0:
       self._sampler.read_state()  # synchronise: run() returns with the samples written
 
+  # checkpoint / resume (the reference relies on tf.train.Saver over params/t/n_accept,
+  # tests/inferences/saver_test.py) -----------------------------------------------------------------
+  def state_dict(self):
+    """The resumable chain state: the Empirical store, the iteration counter, n_accept and the Philox seed.
+    Device draws are a pure function of (seed, t, element), so a resumed chain continues bit-identically."""
+    return {"params": self._packed.detach().cpu().numpy().copy(), "t": int(self._t),
+            "n_accept": int(self._get_n_accept()), "seed": get_seed(),
+            "step_size": float(self.step_size), "n_steps": int(self.n_steps)}
+
+  def load_state_dict(self, state):
+    import torch
+    params = np.asarray(state["params"], np.float32)
+    if tuple(params.shape) != tuple(self._packed.shape):
+      raise ValueError("checkpoint params have shape %s, expected %s" % (params.shape, tuple(self._packed.shape)))
+    self._packed.copy_(torch.as_tensor(params).to(self._packed.device))
+    self._sampler.reset()
+    self._n_accept_base = int(state["n_accept"])
+    self._t = int(state["t"])
+    if state.get("seed") is not None:
+      self._sampler.seed(int(state["seed"]))
+
   def finalize(self):
     super(HMC, self).finalize()

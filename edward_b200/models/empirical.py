@@ -60,7 +60,7 @@ class Empirical(RandomVariable):
     sd = self.stddev()
     return _g.Lazy(lambda: np.square(_g.evaluate(sd)), tuple(self.event_shape), self.dtype, "Variance")
 
-  def _sample_np(self, sample_shape):
+  def _sample_np(self, sample_shape, feed=None):
     """empirical.py:98-110 — rows gathered at uniformly drawn indices."""
     n = int(np.prod(sample_shape)) if len(sample_shape) else 1
     t = self._device_params()

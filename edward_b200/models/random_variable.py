@@ -28,7 +28,8 @@ class RandomVariable(_g.Tensor):
                          % (shape, tuple(t_value.shape)))
       self._value = t_value
     else:
-      self._value = _g.Lazy(lambda: self._sample_np(tuple(self._sample_shape)), shape, self.dtype, "Sample")
+      self._value = _g.Lazy(lambda feed: self._sample_np(tuple(self._sample_shape), feed), shape, self.dtype, "Sample",
+                            wants_feed=True)
     _g.get_default_graph().random_variables.append(self)
 
   # shapes (random_variable.py:140-170)
@@ -57,7 +58,7 @@ class RandomVariable(_g.Tensor):
     raise NotImplementedError("graph traversal utilities are outside the HMC hot path")
 
   # to be provided by the distribution
-  def _sample_np(self, sample_shape):
+  def _sample_np(self, sample_shape, feed=None):
     raise NotImplementedError("sample is not implemented for {0}".format(type(self).__name__))
 
   def log_prob(self, value):
@@ -68,7 +69,7 @@ class RandomVariable(_g.Tensor):
       sample_shape = (int(sample_shape),)
     sample_shape = tuple(sample_shape)
     shape = sample_shape + tuple(self._batch_shape) + tuple(self._event_shape)
-    return _g.Lazy(lambda: self._sample_np(sample_shape), shape, self.dtype, "Sample")
+    return _g.Lazy(lambda feed: self._sample_np(sample_shape, feed), shape, self.dtype, "Sample", wants_feed=True)
 
   def __hash__(self):
     return id(self)

@@ -30,8 +30,8 @@ class Normal(RandomVariable):
     self._args, self._kwargs = (loc, scale), dict(kwargs)
     super(Normal, self).__init__(_bshape(self.loc, self.scale), (), self.loc.dtype, name=name, **kwargs)
 
-  def _sample_np(self, sample_shape):
-    loc, scale = _g.evaluate(self.loc), _g.evaluate(self.scale)
+  def _sample_np(self, sample_shape, feed=None):
+    loc, scale = _g.eval_in(self.loc, feed), _g.eval_in(self.scale, feed)
     shape = tuple(sample_shape) + tuple(self.batch_shape)
     return (loc + scale * np.random.standard_normal(shape)).astype(self.dtype.np)
 
@@ -65,17 +65,17 @@ class Bernoulli(RandomVariable):
 
   def _probs_np(self, feed=None):
     if self._probs is not None:
-      return _g.evaluate(self._probs, feed)
-    return 1.0 / (1.0 + np.exp(-_g.evaluate(self.logits, feed)))
+      return _g.eval_in(self._probs, feed)
+    return 1.0 / (1.0 + np.exp(-_g.eval_in(self.logits, feed)))
 
   @property
   def probs(self):
     if self._probs is not None:
       return self._probs
-    return _g.Lazy(self._probs_np, tuple(self.logits.shape), self.logits.dtype, "Sigmoid")
+    return _g.Lazy(self._probs_np, tuple(self.logits.shape), self.logits.dtype, "Sigmoid", wants_feed=True)
 
-  def _sample_np(self, sample_shape):
-    p = self._probs_np()
+  def _sample_np(self, sample_shape, feed=None):
+    p = self._probs_np(feed)
     return (np.random.uniform(size=tuple(sample_shape) + p.shape) < p).astype(self.dtype.np)
 
   def log_prob(self, value):
@@ -107,11 +107,11 @@ class Poisson(RandomVariable):
     param = self.log_rate if self.log_rate is not None else self._rate
     super(Poisson, self).__init__(tuple(param.shape), (), param.dtype, name=name, **kwargs)
 
-  def _rate_np(self):
-    return _g.evaluate(self._rate) if self._rate is not None else np.exp(_g.evaluate(self.log_rate))
+  def _rate_np(self, feed=None):
+    return _g.eval_in(self._rate, feed) if self._rate is not None else np.exp(_g.eval_in(self.log_rate, feed))
 
-  def _sample_np(self, sample_shape):
-    lam = self._rate_np()
+  def _sample_np(self, sample_shape, feed=None):
+    lam = self._rate_np(feed)
     return np.random.poisson(lam, size=tuple(sample_shape) + lam.shape).astype(self.dtype.np)
 
   def log_prob(self, value):
