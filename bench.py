@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "cfg2": dict(N=581012, D=54, T=100, L=10, name="cfg2: covertype-shaped N=581012 D=54, 1 chain, T=100, n_steps=10, step_size=0.5/N"),
     "cfg4": dict(N=10_000_000, D=1000, T=4, L=10, name="cfg4: N=10000000 D=1000, 1 chain, T=4, n_steps=10, step_size=0.5/N, rows sharded"),
+    "cfg3": dict(N=581012, D=54, T=4, L=10, C=256, name="cfg3: covertype-shaped N=581012 D=54, 256 vectorised chains (tcgen05 3xTF32), T=4, n_steps=10"),
 }
 GEN_BLOCK = 65536
 BASE_SEED = 42
@@ -45,7 +46,8 @@ def parse():
   ap.add_argument("--steps", type=int, default=10)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  ap.add_argument("--workload", default=None, choices=[None, "cfg2", "cfg4"])
+  ap.add_argument("--workload", default=None, choices=[None, "cfg2", "cfg3", "cfg4"])
+  ap.add_argument("--no-scale-ref", action="store_true", help="skip the 1-GPU cfg4 point added to the N=1 line")
   ap.add_argument("--rows", type=int, default=None, help="override the row count (debugging)")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -209,6 +211,61 @@ def run_reference(args, wl, wl_key):
   print(json.dumps(line))
 
 
+def tf32_peak():
+  p = os.path.join(ROOT, "profiles", "r01_tf32_peak.json")
+  if os.path.exists(p):
+    with open(p) as f:
+      return float(json.load(f)["tf32_tflops"]), "measured on this pool (profiles/r01_tf32_peak.json, tools/tf32_peak.py)"
+  return 1100.0, "nominal dense TF32 (no measurement available)"
+
+
+def run_chains(args, wl):
+  """cfg 3: C vectorised chains on one GPU, tensor-core bound. value = chain leapfrog steps/s."""
+  import torch
+  from edward_b200 import engine
+  dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+  torch.cuda.set_device(dev)
+  N, D, T, L, C = wl["N"], wl["D"], wl["T"], wl["L"], wl["C"]
+  X, y = gen_device_rows(torch, dev, 0, N, D)
+  s = engine.GLMSampler(engine.GLMSpec(D), X, y, device=dev, n_chains=C)
+  s.seed(1234)
+  params = torch.zeros(T, C, D, device=dev)
+  flush = torch.empty(512 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+  for _ in range(max(args.warmup, 3)):
+    s.run_chains(params, 0, T, 0.5 / N, L)
+  torch.cuda.synchronize(dev)
+  sampler = ClockSampler(dev.index)
+  sampler.start()
+  evs = []
+  for _ in range(args.steps):
+    flush.fill_(1.0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s.run_chains(params, 0, T, 0.5 / N, L)
+    e1.record()
+    evs.append((e0, e1))
+  torch.cuda.synchronize(dev)
+  clocks = sampler.stop()
+  ms = sum(a.elapsed_time(b) for a, b in evs)
+  steps = args.steps * T * L
+  alg = 4.0 * N * D * C * steps / (ms * 1e-3) / 1e12
+  peak, src = tf32_peak()
+  info = s.plan_info()
+  line = {
+      "metric": "hmc_leapfrog_steps_per_s", "value": C * steps / (ms * 1e-3), "unit": "chain leapfrog steps/s", "n_gpus": 1,
+      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 accumulate)", "data": "synthetic",
+      "config": {"workload": wl["name"], "rows": N, "features": D, "chains": C, "transitions_per_step": T,
+                 "leapfrog_per_transition": L, "l2": "L2 flushed between steps", "rng": "device Philox"},
+      "leapfrog_steps_of_all_chains_per_s": steps / (ms * 1e-3),
+      "roofline": {"bound": "tensor", "achieved": 3.0 * alg, "peak": peak, "unit": "TFLOP/s", "frac": 3.0 * alg / peak,
+                   "traffic": None, "peak_source": src, "algorithmic_tflops": alg,
+                   "kernel": "edhmc::k_mc_pass_tc3 (3xTF32: 3 executed MMA flops per algorithmic flop)"},
+      "cpu_baseline": None, "e2e": None, "gpu_launches": info["launches_last_run"] * args.steps, "clocks": clocks,
+  }
+  print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
   args = parse()
@@ -218,6 +275,9 @@ def main():
     wl["N"] = args.rows
   if args.impl == "reference":
     run_reference(args, wl, wl_key)
+    return
+  if wl_key == "cfg3":
+    run_chains(args, wl)
     return
 
   import numpy as np
@@ -320,7 +380,7 @@ def main():
     from edward_b200.models import Bernoulli, Empirical, Normal
     Xh = X.cpu().pin_memory()
     yh = y.cpu().pin_memory()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(3, min(args.steps, 20))
     times = []
     h2d = Xh.numel() * 4 + yh.numel() * 4
     d2h = T * D * 4 + 16
@@ -344,6 +404,36 @@ def main():
     e2e = {"value": e2e_steps * T * L / sum(times), "unit": "leapfrog steps/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps,
            "call": "ed.HMC({beta: qbeta}, data={X: pinned host array, y: ...}).run(step_size, n_steps) + qbeta.params.eval()"}
+
+  # ---- the N=1 point of the row-sharded scaling series (cfg 4 on this GPU alone), so that the scale-out lines
+  #      (--gpus 2/4/8 run cfg 4) have their single-GPU reference from the same protocol ----
+  scale_n1 = None
+  if world == 1 and wl_key == "cfg2" and not args.no_scale_ref and not args.rows:
+    try:
+      w4 = WORKLOADS["cfg4"]
+      del flush
+      torch.cuda.empty_cache()
+      X4, y4 = gen_device_rows(torch, dev, 0, w4["N"], w4["D"])
+      s4 = engine.GLMSampler(engine.GLMSpec(w4["D"]), X4, y4, device=dev)
+      s4.seed(1234)
+      p4 = torch.zeros(w4["T"], w4["D"], device=dev)
+      s4.run(p4, 0, w4["T"], 0.5 / w4["N"], w4["L"])
+      torch.cuda.synchronize(dev)
+      ms4 = 0.0
+      for _ in range(2):
+        a4, b4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a4.record()
+        s4.run(p4, 0, w4["T"], 0.5 / w4["N"], w4["L"])
+        b4.record()
+        torch.cuda.synchronize(dev)
+        ms4 += a4.elapsed_time(b4)
+      v4 = 2 * w4["T"] * w4["L"] / (ms4 * 1e-3)
+      scale_n1 = {"workload": w4["name"], "value": v4, "unit": "leapfrog steps/s",
+                  "hbm_frac": (4.0 * w4["N"] * w4["D"] + 4.0 * w4["N"]) * v4 / 1e9 / measured_peaks()[0]}
+      s4.close()
+      del X4, y4
+    except Exception as e:  # noqa: BLE001
+      scale_n1 = {"error": str(e)[:200]}
 
   if rank != 0:
     if world > 1:
@@ -396,6 +486,8 @@ def main():
   }
   if n1_same is not None:
     line["n1_same_workload"] = n1_same
+  if scale_n1 is not None:
+    line["scale_series_n1"] = scale_n1
   print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
