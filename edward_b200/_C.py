@@ -21,7 +21,7 @@ PLAN_AUTO, PLAN_PERSISTENT, PLAN_STEPWISE = 0, 1, 2
 EXPORTS = [
     "edhmc_version", "edhmc_last_error", "edhmc_create", "edhmc_destroy", "edhmc_bind_data",
     "edhmc_logp_grad", "edhmc_run", "edhmc_set_trace", "edhmc_read_state", "edhmc_reset", "edhmc_seed",
-    "edhmc_comm_unique_id", "edhmc_comm_init", "edhmc_plan_info",
+    "edhmc_comm_unique_id", "edhmc_comm_init", "edhmc_peer_export", "edhmc_peer_attach", "edhmc_peer_detach", "edhmc_plan_info",
     "edhmc_sgmcmc_run", "edhmc_run_chains", "edhmc_logp_grad_chains", "edhmc_read_chain_state", "edhmc_set_chain_trace", "edhmc_set_chain_debug",
 ]
 
@@ -87,6 +87,9 @@ def lib():
   L.edhmc_seed.argtypes = [vp, C.c_uint64]
   L.edhmc_comm_unique_id.argtypes = [vp]
   L.edhmc_comm_init.argtypes = [vp, vp, i32, i32]
+  L.edhmc_peer_export.argtypes = [vp, vp]
+  L.edhmc_peer_attach.argtypes = [vp, vp, i32, i32]
+  L.edhmc_peer_detach.argtypes = [vp]
   L.edhmc_plan_info.argtypes = [vp, C.POINTER(i64), i32]
   L.edhmc_sgmcmc_run.argtypes = [vp, i32, vp, i64, i64, i64, i64, f32, f32, f32, vp, vp, vp, i64, vp]
   L.edhmc_run_chains.argtypes = [vp, vp, i64, i64, i64, f32, i32, vp, vp, vp]

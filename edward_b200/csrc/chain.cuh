@@ -52,6 +52,64 @@ __device__ __forceinline__ void write_trace(const KArgs& a, long long it, double
   }
 }
 
+// One-shot all-reduce of the shard totals cta_acc[0..P] over the ranks of an NVLink domain, inside the
+// persistent kernel. CTA 0 stores this rank's totals into entry `rank` of EVERY rank's inbox (peer-mapped
+// memory, plain stores over NVLink) and then releases one flag per destination; every CTA of every rank waits
+// for the nranks flags of its own inbox and adds the entries in rank order — so all CTAs on all GPUs hold
+// bit-identical sums, and the chain needs no further broadcast. Two slots (parity of the sequence number)
+// suffice: a rank can run at most one pass ahead of the slowest one, because its next totals depend on
+// everyone's current ones. Returns false if a wait timed out (a peer died): the kernel then unwinds.
+struct PeerArgs {  // passed by value: taking the address of the kernel's KArgs would force a local copy of it
+  unsigned char* const* inbox;
+  int* abort_flag;
+  long long spin_limit;
+  int nranks, rank, ncol;
+};
+static __device__ __noinline__ bool peer_allreduce(const PeerArgs a, unsigned long long seq, double* cta_acc, int* s_flag) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int ncol = a.ncol, R = a.nranks;
+  const int slot = static_cast<int>(seq & 1ull);
+  if (blockIdx.x == 0) {
+    for (int idx = tid; idx < R * ncol; idx += nthr) {
+      const int dst = idx / ncol, c = idx - dst * ncol;
+      double* data = reinterpret_cast<double*>(a.inbox[dst] + kInboxDataOff);
+      data[(static_cast<size_t>(slot) * kMaxRanks + a.rank) * kInboxStride + c] = cta_acc[c];
+    }
+    __syncthreads();
+    if (tid < R) {
+      __threadfence_system();  // cumulative over the CTA's stores (bar.sync above)
+      st_release_sys_u64(reinterpret_cast<unsigned long long*>(a.inbox[tid]) + slot * kMaxRanks + a.rank, seq);
+    }
+  }
+  const unsigned char* own = a.inbox[a.rank];
+  if (tid == 0) *s_flag = 0;
+  __syncthreads();
+  if (tid < R) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(own) + slot * kMaxRanks + tid;
+    const long long t_start = clock64();
+    unsigned int n = 0;
+    while (ld_acquire_sys_u64(f) < seq) {
+      if ((++n & 255u) == 0u) {
+        if (clock64() - t_start > a.spin_limit) atomicExch(a.abort_flag, 1);
+        if (ld_volatile_s32(a.abort_flag)) {
+          *s_flag = 1;
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (*s_flag) return false;
+  const double* data = reinterpret_cast<const double*>(own + kInboxDataOff) + static_cast<size_t>(slot) * kMaxRanks * kInboxStride;
+  for (int c = tid; c < ncol; c += nthr) {
+    double sum = 0.0;
+    for (int rr = 0; rr < R; ++rr) sum += __ldcg(data + static_cast<size_t>(rr) * kInboxStride + c);
+    cta_acc[c] = sum;
+  }
+  __syncthreads();
+  return true;
+}
+
 template <int G, int V, int K, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   constexpr int kThreads = NW * 32;
@@ -179,6 +237,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
 
   int bufsel = 0;
   unsigned long long epoch = 0;
+  const unsigned long long seq0 = (!single && a.nranks > 1) ? *a.comm_seq : 0ull;
+  bool aborted = false;
   for (long long pass = 0; pass < n_passes; ++pass) {
     const float* pos = single ? a.theta_in : (in_init ? zc : z);
     const float bias = a.has_bias ? pos[D] : 0.0f;
@@ -212,13 +272,42 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
         // release (cumulative over the CTA's writes ordered by the bar.sync above) / acquire on one counter
         red_release_add_u64(a.bar, 1ull);
         const unsigned long long target = (epoch + 1) * static_cast<unsigned long long>(ncta);
-        while (ld_acquire_u64(a.bar) < target) {
+        s_last = 0;
+        if (a.nranks > 1) {
+          // a CTA that gave up on a peer never arrives here again: poll the abort flag while waiting
+          unsigned int n = 0;
+          while (ld_acquire_u64(a.bar) < target) {
+            if ((++n & 1023u) == 0u && ld_volatile_s32(a.abort_flag)) {
+              s_last = 1;
+              break;
+            }
+          }
+        } else {
+          while (ld_acquire_u64(a.bar) < target) {
+          }
         }
       }
       __syncthreads();
+      if (s_last) {
+        aborted = true;
+        break;
+      }
       reduce_partials(a.partials + static_cast<size_t>(bufsel) * ncta * (P + 1), ncta, P, sm.cta_acc, sm.comb);
       bufsel ^= 1;
       ++epoch;
+    }
+    if (a.nranks > 1) {
+      PeerArgs pa;
+      pa.inbox = a.peer_inbox;
+      pa.abort_flag = a.abort_flag;
+      pa.spin_limit = a.spin_limit;
+      pa.nranks = a.nranks;
+      pa.rank = a.rank;
+      pa.ncol = P + 1;
+      if (!peer_allreduce(pa, seq0 + static_cast<unsigned long long>(pass) + 1ull, sm.cta_acc, &s_last)) {
+        aborted = true;
+        break;
+      }
     }
 
     // gradient and log joint at `pos`: likelihood totals + Normal prior (hmc.py:183-190)
@@ -257,7 +346,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
     __syncthreads();
   }
 
+  if (aborted) return;
   if (!single && blockIdx.x == 0) {
+    if (a.nranks > 1 && tid == 0) *a.comm_seq = seq0 + static_cast<unsigned long long>(n_passes);
     for (int c = tid; c < P && tid < CT; c += CT) {
       a.zcur[c] = zc[c];
       a.gcur[c] = gc[c];

@@ -14,6 +14,14 @@ constexpr int kXwFloats = 2048;  // per-CTA scratch for the one-shot cross-warp 
 constexpr int kMaxFeatures = 2048;
 constexpr unsigned kFull = 0xffffffffu;
 
+// Peer inbox of the in-kernel all-reduce (row shards over the GPUs of one NVLink domain). One cudaMalloc per
+// rank, exported with cudaIpc: flags[2][kMaxRanks] (u64) at byte 0, data[2][kMaxRanks][kInboxStride] (f64) at
+// byte kInboxDataOff. Slot = parity of the pass sequence number; entry r is written by rank r.
+constexpr int kMaxRanks = 8;
+constexpr int kInboxStride = kMaxFeatures + 8;
+constexpr int kInboxDataOff = 256;
+constexpr size_t kInboxBytes = kInboxDataOff + sizeof(double) * 2 * kMaxRanks * kInboxStride;
+
 // Default warps per CTA as a function of the floats each lane keeps of a row (x, theta and gradient slices
 // live in registers, ~3*KV + 40): 16 warps under 128 registers/thread, 12 under 168, else 8.
 __host__ __device__ constexpr int warps_for(int kv) { return 3 * kv + 40 <= 128 ? 16 : (3 * kv + 40 <= 168 ? 12 : 8); }
@@ -64,6 +72,13 @@ struct KArgs {
   int gate;               // mode 1: return immediately unless sc->need_init
   int par0;               // mode 1: parity of this pass's global leapfrog-step index (zig-zag direction)
   const float* theta_in;  // mode 1: [P]
+  // ---- row shards over several GPUs (persistent plan): one-shot all-reduce through peer memory ----
+  int nranks;                        // 1: no exchange
+  int rank;
+  unsigned char* const* peer_inbox;  // device array [nranks]: inbox base of every rank (own included), peer-mapped
+  unsigned long long* comm_seq;      // passes exchanged so far (identical on every rank, never reset)
+  int* abort_flag;                   // set when a wait on a peer timed out; every spin loop of the kernel polls it
+  long long spin_limit;              // clock64 ticks before a wait on a peer gives up
   // ---- scratch ----
   double* partials;            // [2][grid][P+1]
   unsigned long long* bar;     // grid barrier counter (persistent plan)

@@ -140,6 +140,14 @@ struct edhmc_handle {
   // nccl
   void* comm = nullptr;
   int nranks = 1, rank = 0;
+  // peer inboxes of the in-kernel all-reduce (persistent plan over row shards)
+  unsigned char* d_inbox = nullptr;
+  unsigned char** d_peer_ptrs = nullptr;
+  void* peer_mapped[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned long long* d_comm_seq = nullptr;
+  int* d_abort = nullptr;
+  bool peers_ready = false;
+  long long spin_limit = 0;
   // many chains
   int C = 0, mc_nrg = 0, mc_use_tc = 0, mc_Dp = 0;
   float *mc_z = nullptr, *mc_r = nullptr, *mc_g = nullptr, *mc_zcur = nullptr, *mc_gcur = nullptr, *mc_part_g = nullptr;
@@ -314,6 +322,12 @@ static void fill_args(edhmc_handle* h, KArgs& a) {
   a.seed = h->seed;
   a.trace_scalars = h->trace_scalars;
   a.trace_pos = h->trace_pos;
+  a.nranks = 1;  // the in-kernel exchange is switched on by edhmc_run for the persistent plan only
+  a.rank = h->rank;
+  a.peer_inbox = h->d_peer_ptrs;
+  a.comm_seq = h->d_comm_seq;
+  a.abort_flag = h->d_abort;
+  a.spin_limit = h->spin_limit;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -472,6 +486,12 @@ int edhmc_destroy(edhmc_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (h->peer_mapped[r]) cudaIpcCloseMemHandle(h->peer_mapped[r]);
+  cudaFree(h->d_inbox);
+  cudaFree(h->d_peer_ptrs);
+  cudaFree(h->d_comm_seq);
+  cudaFree(h->d_abort);
   cudaFree(h->d_prior_loc);
   cudaFree(h->d_prior_scale);
   cudaFree(h->d_sc);
@@ -607,10 +627,11 @@ int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int
   h->launches_last = 0;
   h->passes_last = n_iter * n_steps;
 
-  bool persistent = h->nranks == 1;
+  bool persistent = h->nranks == 1 || h->peers_ready;
   if (h->cfg.plan == EDHMC_PLAN_STEPWISE) persistent = false;
   if (h->cfg.plan == EDHMC_PLAN_PERSISTENT && !persistent)
-    return fail(EDHMC_ERR_INVALID, "persistent plan unavailable with row shards");
+    return fail(EDHMC_ERR_INVALID, "persistent plan over row shards needs edhmc_peer_attach");
+  if (persistent && h->nranks > 1) a.nranks = h->nranks;
   h->plan_in_use = persistent ? EDHMC_PLAN_PERSISTENT : EDHMC_PLAN_STEPWISE;
 
   if (persistent) {
@@ -662,8 +683,11 @@ int edhmc_read_state(edhmc_t* h, int64_t* n_accept_host, double* logp_host, void
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   ChainScalars sc;
+  int aborted = 0;
   CUDA_TRY(cudaMemcpyAsync(&sc, h->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, stream));
+  if (h->d_abort) CUDA_TRY(cudaMemcpyAsync(&aborted, h->d_abort, sizeof(int), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
+  if (aborted) return fail(EDHMC_ERR_COMM, "timed out waiting for the shard totals of a peer rank");
   if (n_accept_host) *n_accept_host = sc.n_accept;
   if (logp_host) *logp_host = sc.logp_cur;
   return 0;
@@ -706,6 +730,68 @@ int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t 
   NCCL_TRY(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
   h->nranks = nranks;
   h->rank = rank;
+  return 0;
+}
+
+int edhmc_peer_export(edhmc_t* h, void* handle64_host) {
+  if (!h || !handle64_host) return fail(EDHMC_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (!h->d_inbox) {
+    CUDA_TRY(cudaMalloc(&h->d_inbox, kInboxBytes));
+    CUDA_TRY(cudaMemset(h->d_inbox, 0, kInboxBytes));
+    CUDA_TRY(cudaMalloc(&h->d_peer_ptrs, kMaxRanks * sizeof(unsigned char*)));
+    CUDA_TRY(cudaMalloc(&h->d_comm_seq, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(h->d_comm_seq, 0, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&h->d_abort, sizeof(int)));
+    CUDA_TRY(cudaMemset(h->d_abort, 0, sizeof(int)));
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t ipc;
+  CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->d_inbox));
+  memcpy(handle64_host, &ipc, sizeof(ipc));
+  return 0;
+}
+
+int edhmc_peer_attach(edhmc_t* h, const void* handles_host, int32_t nranks, int32_t rank) {
+  if (!h || !handles_host) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks)
+    return fail(EDHMC_ERR_INVALID, "peer exchange supports 1..%d ranks, got nranks=%d rank=%d", kMaxRanks, nranks, rank);
+  if (!h->d_inbox) return fail(EDHMC_ERR_STATE, "edhmc_peer_export has not been called");
+  if (h->comm && (nranks != h->nranks || rank != h->rank)) return fail(EDHMC_ERR_INVALID, "nranks/rank differ from edhmc_comm_init");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  unsigned char* ptrs[kMaxRanks] = {nullptr};
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {
+      ptrs[r] = h->d_inbox;
+      continue;
+    }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, static_cast<const unsigned char*>(handles_host) + 64 * r, sizeof(ipc));
+    void* mapped = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&mapped, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(EDHMC_ERR_COMM, "cannot map the inbox of rank %d (cudaIpcOpenMemHandle: %s)", r, cudaGetErrorString(e));
+    }
+    h->peer_mapped[r] = mapped;
+    ptrs[r] = static_cast<unsigned char*>(mapped);
+  }
+  CUDA_TRY(cudaMemcpy(h->d_peer_ptrs, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
+  int khz = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->cfg.device));
+  long long ms = 20000;
+  if (const char* e = getenv("EDHMC_PEER_TIMEOUT_MS")) ms = atoll(e);
+  h->spin_limit = ms * static_cast<long long>(khz);
+  h->nranks = nranks;
+  h->rank = rank;
+  h->peers_ready = true;
+  return 0;
+}
+
+int edhmc_peer_detach(edhmc_t* h) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  h->peers_ready = false;
   return 0;
 }
 

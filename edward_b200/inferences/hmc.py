@@ -76,7 +76,7 @@ class HMC(MonteCarlo):
       n_global = int(cnt.item())
 
     self._sampler = GLMSampler(model.spec, self._x_value, y_val, device=dev,
-                               plan=_C.PLAN_STEPWISE if sharded else self._plan, debug=self.debug,
+                               plan=self._plan, debug=self.debug,
                                n_rows_global=n_global)
     if sharded:
       self._sampler.init_comm(dist.get_world_size(), dist.get_rank())

@@ -21,3 +21,14 @@ def broadcast_bytes(payload, src: int = 0, group=None) -> bytes:
   box = [payload if dist.get_rank(group) == src else None]
   dist.broadcast_object_list(box, src=src, group=group)
   return box[0]
+
+
+def allgather_bytes(payload: bytes, group=None) -> bytes:
+  """Every rank returns the concatenation, in rank order, of the equally long `payload`s of all ranks (used
+  for the 64-byte cudaIpc handles of the peer inboxes)."""
+  import torch.distributed as dist
+  box = [None] * dist.get_world_size(group)
+  dist.all_gather_object(box, payload, group=group)
+  if len(set(len(b) for b in box)) != 1:
+    raise ValueError("allgather_bytes: payload lengths differ across ranks")
+  return b"".join(box)

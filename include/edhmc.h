@@ -148,6 +148,20 @@ int edhmc_seed(edhmc_t* h, uint64_t seed);
 int edhmc_comm_unique_id(void* id128_host);
 int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t rank);
 
+/* In-kernel all-reduce over peer memory (NVLink / NVSwitch), used by edhmc_run's persistent plan when rows are
+ * sharded: edhmc_peer_export allocates this rank's inbox and returns its 64-byte cudaIpcMemHandle; the caller
+ * all-gathers the handles (rank order) and every rank calls edhmc_peer_attach with the nranks*64-byte table.
+ * Afterwards edhmc_run executes ALL transitions of a call in one cooperative launch per rank: after each data
+ * pass CTA 0 stores the shard's [grad, logp] totals straight into every rank's inbox and every CTA sums the
+ * nranks entries in rank order (bit-identical on all ranks) — no NCCL call and no kernel boundary per leapfrog
+ * step. nranks <= 8 (one NVLink domain), one process per GPU. edhmc_cfg.plan = EDHMC_PLAN_STEPWISE keeps the
+ * per-pass launch + ncclAllReduce path. A rank that waits longer than EDHMC_PEER_TIMEOUT_MS (default 20000) for a
+ * peer gives up; edhmc_read_state then returns EDHMC_ERR_COMM.
+ * Replaces: nothing in the reference (single device); SURVEY §8(e). */
+int edhmc_peer_export(edhmc_t* h, void* handle64_host);
+int edhmc_peer_attach(edhmc_t* h, const void* handles_host, int32_t nranks, int32_t rank);
+int edhmc_peer_detach(edhmc_t* h); /* back to the ncclAllReduce plan (all ranks must agree) */
+
 /* ---- Stochastic-gradient MCMC on the same log-joint gradient --------------------------------
  * n_iter iterations t = t0.. of SGLD (kind 0, edward/inferences/sgld.py:52-87) or SGHMC (kind 1, sghmc.py:58-96):
  * one gradient evaluation at row max(t-1,0) of `params`, then

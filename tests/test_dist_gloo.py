@@ -30,7 +30,7 @@ def _worker(rank, world, port, out):
   dist.init_process_group("gloo", rank=rank, world_size=world)
   try:
     import hmc_oracle as o
-    from edward_b200.sharding import broadcast_bytes, shard_bounds
+    from edward_b200.sharding import allgather_bytes, broadcast_bytes, shard_bounds
     N, D, block = 5000, 7, 512
     lo, hi = shard_bounds(N, world, rank, block)
     X, y, _ = o.synth_data(N, D)
@@ -50,11 +50,20 @@ def _worker(rank, world, port, out):
     t = torch.tensor(sums, dtype=torch.float64)
     dist.all_reduce(t)
     tot = t.numpy()
+    # the peer-inbox exchange of the persistent plan: every rank's entry gathered (here over gloo), summed in rank
+    # order on every rank → identical bits everywhere; handles travel with allgather_bytes in rank order
+    table = allgather_bytes(bytes([rank]) * 64)
+    inbox = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(inbox, torch.tensor(sums, dtype=torch.float64))
+    acc = np.zeros_like(sums)
+    for entry in inbox:
+      acc = acc + entry.numpy()
+    peer_ok = table == b"".join(bytes([q]) * 64 for q in range(world)) and np.allclose(acc, tot, rtol=1e-14)
     grad = tot[:D] + o.normal_log_prob_grad(theta, spec.prior_loc, spec.prior_scale, np.float64)
     logp = tot[D] + np.sum(o.normal_log_prob(theta, spec.prior_loc, spec.prior_scale, np.float64))
     want_g = o.grad_log_joint(X, y, theta, spec)
     want_lp = o.log_joint(X, y, theta, spec)
-    ok = (uid == bytes(range(128)) and int(cnt.item()) == N and np.allclose(grad, want_g, rtol=1e-10)
+    ok = (peer_ok and uid == bytes(range(128)) and int(cnt.item()) == N and np.allclose(grad, want_g, rtol=1e-10)
           and abs(logp - want_lp) < 1e-8 * abs(want_lp))
     out[rank] = (ok, lo, hi)
   finally:

@@ -1,5 +1,6 @@
-"""Row-sharded HMC over 2 GPUs (NCCL all-reduce of [grad, logp] per leapfrog step) against the single-GPU
-result and the oracle. Skipped on boxes with fewer than 2 GPUs."""
+"""Row-sharded HMC over 2 GPUs against the single-GPU result and the oracle, on both multi-GPU plans: the
+persistent kernel with its in-kernel all-reduce over peer memory, and the per-pass launch + ncclAllReduce plan.
+Skipped on boxes with fewer than 2 GPUs."""
 import os
 import socket
 import sys
@@ -19,7 +20,7 @@ def _free_port():
   return p
 
 
-def _worker(rank, world, port, N, D, T, L, eps, out):
+def _worker(rank, world, port, N, D, T, L, eps, out, plan_name="stepwise"):
   import torch
   import torch.distributed as dist
   sys.path.insert(0, ROOT)
@@ -34,8 +35,8 @@ def _worker(rank, world, port, N, D, T, L, eps, out):
     from edward_b200.sharding import shard_bounds
     X, y, _ = o.synth_data(N, D)
     lo, hi = shard_bounds(N, world, rank, block=1024)
-    s = engine.GLMSampler(engine.GLMSpec(D), X[lo:hi], y[lo:hi], device="cuda:%d" % rank, plan=_C.PLAN_STEPWISE,
-                          n_rows_global=N)
+    plan = {"stepwise": _C.PLAN_STEPWISE, "auto": _C.PLAN_AUTO}[plan_name]
+    s = engine.GLMSampler(engine.GLMSpec(D), X[lo:hi], y[lo:hi], device="cuda:%d" % rank, plan=plan, n_rows_global=N)
     s.init_comm(world, rank)
     r0, u = o.synth_draws(T, D)
     params = torch.zeros(T, D, device="cuda:%d" % rank)
@@ -44,7 +45,16 @@ def _worker(rank, world, port, N, D, T, L, eps, out):
     n_acc, logp = s.read_state()
     th = (0.1 * np.arange(D) / D).astype(np.float32)
     lp, g = s.logp_grad(th)
+    # a second, chunked call continues the chain: sequence numbers of the peer exchange carry across launches
+    params2 = torch.zeros(T, D, device="cuda:%d" % rank)
+    s.reset()
+    s.run(params2, 0, 3, eps, L, r0=torch.tensor(r0[:3]), u=torch.tensor(u[:3]))
+    s.run(params2, 3, T - 3, eps, L, r0=torch.tensor(r0[3:]), u=torch.tensor(u[3:]))
+    s.read_state()
+    info = s.plan_info()
     out[rank] = (params.cpu().numpy(), n_acc, logp, float(lp.cpu()[0]), g.cpu().numpy(), sc.cpu().numpy())
+    out["extra%d" % rank] = (params2.cpu().numpy(), bool(getattr(s, "peer_exchange", False)), info["plan_in_use"],
+                             info["launches_last_run"])
     s.close()
   finally:
     dist.destroy_process_group()
@@ -76,3 +86,29 @@ def test_two_gpu_row_shards_match_single_gpu_and_oracle():
   assert abs(l0 - o.log_joint(X, y, th, spec)) <= 1e-5 * abs(l0)
   g64 = o.grad_log_joint(X, y, th, spec)
   assert np.max(np.abs(g0 - g64)) <= 1e-5 * np.max(np.abs(g64))
+
+
+def test_two_gpu_peer_exchange_matches_nccl_plan_bitwise():
+  """The persistent kernel's in-kernel all-reduce (stores into peer inboxes over NVLink) against the ncclAllReduce
+  plan: with two ranks both sum a+b, so the chains must agree bit for bit; one launch per run() call."""
+  import torch
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs 2 GPUs")
+  import torch.multiprocessing as mp
+  from edward_b200 import _C
+  N, D, T, L, eps = 30000, 200, 8, 5, 0.002
+  res = {}
+  for plan_name in ("stepwise", "auto"):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), N, D, T, L, eps, out, plan_name), nprocs=2, join=True)
+    res[plan_name] = (out[0], out[1], out["extra0"], out["extra1"])
+  a0, a1, ax0, ax1 = res["auto"]
+  s0, s1, sx0, sx1 = res["stepwise"]
+  assert ax0[1] and ax1[1], "peer inboxes were not mapped"
+  assert ax0[2] == _C.PLAN_PERSISTENT and ax0[3] == 1
+  assert sx0[2] == _C.PLAN_STEPWISE
+  assert np.array_equal(a0[0], a1[0]) and a0[1] == a1[1] and a0[2] == a1[2]
+  assert np.array_equal(a0[0], s0[0]) and a0[1] == s0[1] and a0[2] == s0[2]
+  assert np.array_equal(a0[5], s0[5])  # per-transition trace: logp, K, ratio, accept
+  assert np.array_equal(ax0[0], a0[0]) and np.array_equal(ax1[0], a0[0])  # chunked launches == one launch
