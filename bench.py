@@ -47,6 +47,8 @@ def parse():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--workload", default=None, choices=[None, "cfg2", "cfg3", "cfg4"])
+  ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                  help="N>1: in-kernel all-reduce over peer memory (default) or per-pass launch + ncclAllReduce")
   ap.add_argument("--no-scale-ref", action="store_true", help="skip the 1-GPU cfg4 point added to the N=1 line")
   ap.add_argument("--rows", type=int, default=None, help="override the row count (debugging)")
   ap.add_argument("--no-e2e", action="store_true")
@@ -301,9 +303,9 @@ def main():
   r_lo, r_hi = shard_bounds(N, world, rank)
   X, y = gen_device_rows(torch, dev, r_lo, r_hi - r_lo, D)
   s = engine.GLMSampler(engine.GLMSpec(D), X, y, device=dev, n_rows_global=N,
-                        plan=engine._C.PLAN_STEPWISE if world > 1 else engine._C.PLAN_AUTO)
+                        plan=engine._C.PLAN_STEPWISE if (world > 1 and args.collective == "nccl") else engine._C.PLAN_AUTO)
   if world > 1:
-    s.init_comm(world, rank)
+    s.init_comm(world, rank, peers=args.collective == "peer")
   s.seed(1234)
   params = torch.zeros(T, D, device=dev)
   flush = torch.empty(512 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
@@ -477,7 +479,8 @@ def main():
       "data": "synthetic",
       "config": {"workload": wl["name"], "rows": N, "features": D, "transitions_per_step": T, "leapfrog_per_transition": L,
                  "chains": 1, "plan": {1: "persistent", 2: "stepwise"}[info["plan_in_use"]],
-                 "parallelism": "rows sharded over %d GPUs, NCCL all-reduce per leapfrog step" % world if world > 1 else "1 GPU",
+                 "parallelism": ("rows sharded over %d GPUs, %s" % (world, "one persistent launch per GPU, in-kernel all-reduce of [grad, logp] through peer inboxes over NVLink each leapfrog step"
+                                  if info["plan_in_use"] == 1 else "NCCL all-reduce per leapfrog step")) if world > 1 else "1 GPU",
                  "l2": "L2 flushed between steps (512 MiB write); within a step X (%.1f MB) is re-streamed every leapfrog step" % (4e-6 * (r_hi - r_lo) * D),
                  "rng": "device Philox", "grid_ctas": info["grid_ctas"], "ring_stages": info["ring_stages"], "tile_rows": info["tile_rows"]},
       "rows_steps_per_s": value * N,

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libedhmc.so")
+LIB_PATH = os.environ.get("EDHMC_LIB_PATH") or os.path.join(HERE, "lib", "libedhmc.so")  # override: A/B of two builds
 
 EDHMC_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NONFINITE, ERR_RANGE, ERR_STATE, ERR_COMM, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7

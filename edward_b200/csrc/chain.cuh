@@ -110,6 +110,102 @@ static __device__ __noinline__ bool peer_allreduce(const PeerArgs a, unsigned lo
   return true;
 }
 
+// Canonical summation order of a wide column (P+1 > kWideCols) over the per-CTA partials: lane l adds the CTAs
+// l, l+32, ... in ascending order, then an xor butterfly (the same tree in every lane). Both plans use it, so
+// they stay bit-identical.
+__device__ __forceinline__ double wide_column_sum(const double* part, int ncta, int ncol, int c, int lane) {
+  double s = 0.0;
+  for (int cta = lane; cta < ncta; cta += 32) s += __ldcg(part + static_cast<size_t>(cta) * ncol + c);
+#pragma unroll
+  for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+  return s;
+}
+// Stepwise plan: the last CTA folds all columns in that order, four columns per warp at a time for load parallelism.
+__device__ __forceinline__ void reduce_partials_wide(const double* part, int ncta, int ncol, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int c = warp * 4; c < ncol; c += nwarp * 4) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int cta = lane; cta < ncta; cta += 32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c + i < ncol) s[i] += __ldcg(part + static_cast<size_t>(cta) * ncol + c + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int off = 16; off; off >>= 1) s[i] += __shfl_xor_sync(kFull, s[i], off);
+      if (lane == 0 && c + i < ncol) out[c + i] = s[i];
+    }
+  }
+  __syncthreads();
+}
+
+// Two-level variant for wide models (P+1 > kWideCols), used with one rank as well: letting every CTA read every
+// CTA's partials costs ncta^2 * (P+1) float64 loads from L2 per leapfrog step (175 MB at D=1000 on 148 SMs).
+// Instead the columns are cut into kWideSlices slices; after the grid barrier the CTA that owns a slice sums
+// that slice over all CTAs' partials (one warp per column, fixed order), stores the slice totals into entry
+// `rank` of every rank's inbox and bumps that inbox's slice counter (release, system scope; remote atomics over
+// NVLink for peers). A CTA continues once its own inbox has all slices of all ranks, and adds the entries in
+// rank order. Traffic per step: ncta * (P+1) loads for the slices + nranks * (P+1) per CTA for the totals.
+struct WideArgs {
+  const double* part;  // [ncta][ncol] partials of this pass
+  unsigned char* const* inbox;
+  int* abort_flag;
+  long long spin_limit;
+  int nranks, rank, ncol, ncta;
+};
+static __device__ __noinline__ bool wide_allreduce(const WideArgs a, unsigned long long seq, double* cta_acc, int* s_flag) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int R = a.nranks;
+  const int slot = static_cast<int>(seq & 1ull);
+  const int w = (a.ncol + kWideSlices - 1) / kWideSlices;
+  const int n_slices = (a.ncol + w - 1) / w;
+  const size_t entry = (static_cast<size_t>(slot) * kMaxRanks + a.rank) * kInboxStride;
+  int mine = 0;
+  for (int sl = blockIdx.x; sl < n_slices; sl += a.ncta) {
+    const int c0 = sl * w, c1 = min(a.ncol, c0 + w);
+    for (int c = c0 + warp; c < c1; c += nwarp) {
+      const double s = wide_column_sum(a.part, a.ncta, a.ncol, c, lane);
+      if (lane < R) reinterpret_cast<double*>(a.inbox[lane] + kInboxDataOff)[entry + c] = s;
+    }
+    ++mine;
+  }
+  __syncthreads();
+  if (mine && tid < R) {
+    __threadfence_system();  // cumulative over the CTA's stores (bar.sync above)
+    red_release_sys_add_u64(reinterpret_cast<unsigned long long*>(a.inbox[tid] + kInboxCountOff) + slot * kMaxRanks + a.rank,
+                            static_cast<unsigned long long>(mine));
+  }
+  const unsigned char* own = a.inbox[a.rank];
+  if (tid == 0) *s_flag = 0;
+  __syncthreads();
+  if (tid < R) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(own + kInboxCountOff) + slot * kMaxRanks + tid;
+    const unsigned long long target = static_cast<unsigned long long>(n_slices) * ((seq + static_cast<unsigned long long>(slot)) >> 1);
+    const long long t_start = clock64();
+    unsigned int n = 0;
+    while (ld_acquire_sys_u64(f) < target) {
+      if ((++n & 255u) == 0u) {
+        if (clock64() - t_start > a.spin_limit) atomicExch(a.abort_flag, 1);
+        if (ld_volatile_s32(a.abort_flag)) {
+          *s_flag = 1;
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (*s_flag) return false;
+  const double* data = reinterpret_cast<const double*>(own + kInboxDataOff) + static_cast<size_t>(slot) * kMaxRanks * kInboxStride;
+  for (int c = tid; c < a.ncol; c += nthr) {
+    double sum = 0.0;
+    for (int rr = 0; rr < R; ++rr) sum += __ldcg(data + static_cast<size_t>(rr) * kInboxStride + c);
+    cta_acc[c] = sum;
+  }
+  __syncthreads();
+  return true;
+}
+
 template <int G, int V, int K, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   constexpr int kThreads = NW * 32;
@@ -237,12 +333,17 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
 
   int bufsel = 0;
   unsigned long long epoch = 0;
-  const unsigned long long seq0 = (!single && a.nranks > 1) ? *a.comm_seq : 0ull;
+  constexpr bool kMayWide = G * K * V + 2 > kWideCols;  // P + 1 <= G*K*V + 2: narrow kernels carry no wide path
+  const bool wide = kMayWide && !single && ncta > 1 && P + 1 > kWideCols;
+  const bool guarded = a.nranks > 1 || wide;  // waits that can time out: poll the abort flag
+  const unsigned long long seq0 = (!single && guarded) ? *a.comm_seq : 0ull;
   bool aborted = false;
   for (long long pass = 0; pass < n_passes; ++pass) {
     const float* pos = single ? a.theta_in : (in_init ? zc : z);
     const float bias = a.has_bias ? pos[D] : 0.0f;
-    stream_pass<G, V, K, NW>(a, pr, wt, ring, sm, bias, policy);
+    // the log likelihood is only consumed at the ends of a trajectory (initial evaluation, last leapfrog step)
+    const bool want_lp = single || in_init || s + 1 >= a.L;
+    stream_pass<G, V, K, NW>(a, pr, wt, ring, sm, bias, policy, want_lp);
 
     if (single) {
       // last-arriving CTA folds the partials (threadFenceReduction pattern), fixed summation order
@@ -257,7 +358,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
       }
       __syncthreads();
       if (s_last) {
-        reduce_partials(a.partials, ncta, P, sm.cta_acc, sm.comb);
+        if (kMayWide && P + 1 > kWideCols)
+          reduce_partials_wide(a.partials, ncta, P + 1, sm.cta_acc);
+        else
+          reduce_partials(a.partials, ncta, P, sm.cta_acc, sm.comb);
         for (int c = tid; c <= P; c += kThreads) a.sums[c] = sm.cta_acc[c];
         if (tid == 0) *a.ticket = 0u;
       }
@@ -273,7 +377,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
         red_release_add_u64(a.bar, 1ull);
         const unsigned long long target = (epoch + 1) * static_cast<unsigned long long>(ncta);
         s_last = 0;
-        if (a.nranks > 1) {
+        if (guarded) {
           // a CTA that gave up on a peer never arrives here again: poll the abort flag while waiting
           unsigned int n = 0;
           while (ld_acquire_u64(a.bar) < target) {
@@ -292,11 +396,25 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
         aborted = true;
         break;
       }
-      reduce_partials(a.partials + static_cast<size_t>(bufsel) * ncta * (P + 1), ncta, P, sm.cta_acc, sm.comb);
+      if (!wide) reduce_partials(a.partials + static_cast<size_t>(bufsel) * ncta * (P + 1), ncta, P, sm.cta_acc, sm.comb);
       bufsel ^= 1;
       ++epoch;
     }
-    if (a.nranks > 1) {
+    if (wide) {
+      WideArgs wa;
+      wa.part = a.partials + static_cast<size_t>(bufsel ^ 1) * ncta * (P + 1);
+      wa.inbox = a.peer_inbox;
+      wa.abort_flag = a.abort_flag;
+      wa.spin_limit = a.spin_limit;
+      wa.nranks = a.nranks;
+      wa.rank = a.nranks > 1 ? a.rank : 0;
+      wa.ncol = P + 1;
+      wa.ncta = ncta;
+      if (!wide_allreduce(wa, seq0 + static_cast<unsigned long long>(pass) + 1ull, sm.cta_acc, &s_last)) {
+        aborted = true;
+        break;
+      }
+    } else if (a.nranks > 1) {
       PeerArgs pa;
       pa.inbox = a.peer_inbox;
       pa.abort_flag = a.abort_flag;
@@ -316,10 +434,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
     for (int c = tid; c < P && tid < CT; c += CT) {
       const float loc = a.prior_loc[c], sc = a.prior_scale[c];
       gout[c] = static_cast<float>(sm.cta_acc[c] + prior_grad(pos[c], loc, sc));
-      pl += prior_quad(pos[c], loc, sc);
+      if (want_lp) pl += prior_quad(pos[c], loc, sc);
     }
-    const double lik = sm.cta_acc[P];
-    logp_new = (block_sum_f64(pl, sm.red) - a.prior_const) + lik;
+    if (want_lp) {
+      const double lik = sm.cta_acc[P];
+      logp_new = (block_sum_f64(pl, sm.red) - a.prior_const) + lik;
+    }
 
     if (in_init) {
       logp_cur = logp_new;
@@ -348,7 +468,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
 
   if (aborted) return;
   if (!single && blockIdx.x == 0) {
-    if (a.nranks > 1 && tid == 0) *a.comm_seq = seq0 + static_cast<unsigned long long>(n_passes);
+    if (guarded && tid == 0) *a.comm_seq = seq0 + static_cast<unsigned long long>(n_passes);
     for (int c = tid; c < P && tid < CT; c += CT) {
       a.zcur[c] = zc[c];
       a.gcur[c] = gc[c];

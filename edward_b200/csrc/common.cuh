@@ -14,12 +14,16 @@ constexpr int kXwFloats = 2048;  // per-CTA scratch for the one-shot cross-warp 
 constexpr int kMaxFeatures = 2048;
 constexpr unsigned kFull = 0xffffffffu;
 
-// Peer inbox of the in-kernel all-reduce (row shards over the GPUs of one NVLink domain). One cudaMalloc per
-// rank, exported with cudaIpc: flags[2][kMaxRanks] (u64) at byte 0, data[2][kMaxRanks][kInboxStride] (f64) at
+// Inbox of the in-kernel all-reduce (row shards over the GPUs of one NVLink domain; also the second level of
+// the wide single-GPU reduction). One cudaMalloc per rank, exported with cudaIpc: flags[2][kMaxRanks] (u64) at
+// byte 0, slice counters[2][kMaxRanks] (u64) at byte kInboxCountOff, data[2][kMaxRanks][kInboxStride] (f64) at
 // byte kInboxDataOff. Slot = parity of the pass sequence number; entry r is written by rank r.
 constexpr int kMaxRanks = 8;
 constexpr int kInboxStride = kMaxFeatures + 8;
+constexpr int kInboxCountOff = 128;
 constexpr int kInboxDataOff = 256;
+constexpr int kWideCols = 256;    // more totals than this: two-level reduction (column slices) instead of all-read-all
+constexpr int kWideSlices = 128;  // column slices of the two-level reduction (independent of the grid size)
 constexpr size_t kInboxBytes = kInboxDataOff + sizeof(double) * 2 * kMaxRanks * kInboxStride;
 
 // Default warps per CTA as a function of the floats each lane keeps of a row (x, theta and gradient slices
@@ -67,6 +71,7 @@ struct KArgs {
   int ldx_i;         // ldx as int
   int tl;            // floats per full tile = RT*ldx
   int tm;            // tl & 3: per-tile drift of the 16-byte alignment (non-zero only if ldx % 4 != 0)
+  int interleave;    // 1: tile t belongs to warp t % (grid*NW) (moving window); 0: contiguous row range per warp
   // ---- launch mode ----
   int mode;               // 0: run n_iter transitions (cooperative launch); 1: one data pass at theta_in
   int gate;               // mode 1: return immediately unless sc->need_init
@@ -109,6 +114,24 @@ struct KArgs {
 // Likelihood families. Returns log p(y|eta) and d/deta log p(y|eta), float32, in the op order of
 // the TensorFlow path the reference executes (see oracle/hmc_oracle.py for the citations).
 // ---------------------------------------------------------------------------------------------
+// Gradient-only variant for the leapfrog steps inside a trajectory: the log joint enters the transition only at
+// its two ends (hmc.py:104-105), so the log1p / lgamma work is skipped there. r is bit-identical to row_terms'.
+__device__ __forceinline__ float row_resid(int family, float eta, float yv, float lik_scale) {
+  if (family == 0) {
+    const bool pos = eta >= 0.0f;
+    const float e = expf(-fabsf(eta));
+    const float u = __fadd_rn(1.0f, e);
+    const float inv = __fdividef(1.0f, u);
+    const float q = __fmul_rn(e, inv);
+    return pos ? __fadd_rn(__fsub_rn(yv, 1.0f), q) : __fsub_rn(yv, q);
+  } else if (family == 1) {
+    const float zz = __fdiv_rn(__fsub_rn(yv, eta), lik_scale);
+    return __fdiv_rn(zz, lik_scale);
+  } else {
+    return __fsub_rn(yv, expf(eta));
+  }
+}
+
 __device__ __forceinline__ void row_terms(int family, float eta, float yv, float lik_scale, float& lp, float& r) {
   if (family == 0) {
     // -(where(l>=0,l,0) - l*y + log1p(exp(-|l|)));  gradient y - sigmoid(l), piecewise as autodiff does.

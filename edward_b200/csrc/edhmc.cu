@@ -118,6 +118,7 @@ struct edhmc_handle {
   Plan plan;
   int zigzag = 1;
   int l2_hint = 0;
+  int interleave = 0;
   // device buffers
   float* d_prior_loc = nullptr;
   float* d_prior_scale = nullptr;
@@ -310,6 +311,7 @@ static void fill_args(edhmc_handle* h, KArgs& a) {
   a.ldx_i = static_cast<int>(c.ldx);
   a.tl = p.tl;
   a.tm = p.tm;
+  a.interleave = h->interleave;
   a.partials = h->d_partials;
   a.bar = h->d_bar;
   a.ticket = h->d_ticket;
@@ -381,6 +383,7 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   h->prior_const = pc;
   if (const char* e = getenv("EDHMC_ZIGZAG")) h->zigzag = atoi(e);
   if (const char* e = getenv("EDHMC_L2_HINT")) h->l2_hint = atoi(e);
+  if (const char* e = getenv("EDHMC_INTERLEAVE")) h->interleave = atoi(e);
   cudaError_t e1 = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   cudaError_t e2 = cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -468,6 +471,25 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
 #undef ALLOC
   cudaMemcpy(h->d_prior_loc, cfg->prior_loc_host, pb, cudaMemcpyHostToDevice);
   cudaMemcpy(h->d_prior_scale, cfg->prior_scale_host, pb, cudaMemcpyHostToDevice);
+  {
+    // inbox of the in-kernel reductions (second level of the wide single-GPU reduce; peer exchange when sharded)
+    unsigned char* own[kMaxRanks] = {nullptr};
+    if (cudaMalloc(&h->d_inbox, kInboxBytes) != cudaSuccess || cudaMalloc(&h->d_peer_ptrs, sizeof(own)) != cudaSuccess ||
+        cudaMalloc(&h->d_comm_seq, sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&h->d_abort, sizeof(int)) != cudaSuccess) {
+      edhmc_destroy(h);
+      return fail(EDHMC_ERR_NOMEM, "cudaMalloc failed (inbox)");
+    }
+    own[0] = h->d_inbox;
+    cudaMemset(h->d_inbox, 0, kInboxBytes);
+    cudaMemcpy(h->d_peer_ptrs, own, sizeof(own), cudaMemcpyHostToDevice);
+    cudaMemset(h->d_comm_seq, 0, sizeof(unsigned long long));
+    cudaMemset(h->d_abort, 0, sizeof(int));
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->cfg.device);
+    long long ms = 20000;
+    if (const char* e = getenv("EDHMC_PEER_TIMEOUT_MS")) ms = atoll(e);
+    h->spin_limit = ms * static_cast<long long>(khz);
+  }
   cudaMemset(h->d_sc, 0, sizeof(ChainScalars));
   cudaMemset(h->d_zcur, 0, pb);
   cudaMemset(h->d_gcur, 0, pb);
@@ -737,16 +759,6 @@ int edhmc_peer_export(edhmc_t* h, void* handle64_host) {
   if (!h || !handle64_host) return fail(EDHMC_ERR_INVALID, "null argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  if (!h->d_inbox) {
-    CUDA_TRY(cudaMalloc(&h->d_inbox, kInboxBytes));
-    CUDA_TRY(cudaMemset(h->d_inbox, 0, kInboxBytes));
-    CUDA_TRY(cudaMalloc(&h->d_peer_ptrs, kMaxRanks * sizeof(unsigned char*)));
-    CUDA_TRY(cudaMalloc(&h->d_comm_seq, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(h->d_comm_seq, 0, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMalloc(&h->d_abort, sizeof(int)));
-    CUDA_TRY(cudaMemset(h->d_abort, 0, sizeof(int)));
-    CUDA_TRY(cudaDeviceSynchronize());
-  }
   cudaIpcMemHandle_t ipc;
   CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->d_inbox));
   memcpy(handle64_host, &ipc, sizeof(ipc));
@@ -757,7 +769,6 @@ int edhmc_peer_attach(edhmc_t* h, const void* handles_host, int32_t nranks, int3
   if (!h || !handles_host) return fail(EDHMC_ERR_INVALID, "null argument");
   if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks)
     return fail(EDHMC_ERR_INVALID, "peer exchange supports 1..%d ranks, got nranks=%d rank=%d", kMaxRanks, nranks, rank);
-  if (!h->d_inbox) return fail(EDHMC_ERR_STATE, "edhmc_peer_export has not been called");
   if (h->comm && (nranks != h->nranks || rank != h->rank)) return fail(EDHMC_ERR_INVALID, "nranks/rank differ from edhmc_comm_init");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   unsigned char* ptrs[kMaxRanks] = {nullptr};
@@ -778,11 +789,6 @@ int edhmc_peer_attach(edhmc_t* h, const void* handles_host, int32_t nranks, int3
     ptrs[r] = static_cast<unsigned char*>(mapped);
   }
   CUDA_TRY(cudaMemcpy(h->d_peer_ptrs, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
-  int khz = 0;
-  CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->cfg.device));
-  long long ms = 20000;
-  if (const char* e = getenv("EDHMC_PEER_TIMEOUT_MS")) ms = atoll(e);
-  h->spin_limit = ms * static_cast<long long>(khz);
   h->nranks = nranks;
   h->rank = rank;
   h->peers_ready = true;

@@ -37,12 +37,24 @@ struct WarpTiles {
 };
 
 __device__ __forceinline__ WarpTiles warp_tiles(const KArgs& a, int gw, int total_w) {
+  WarpTiles w;
+  if (a.interleave) {
+    // tile t belongs to warp t % total_w: at any moment the grid reads one compact window of X that moves forward
+    // (DRAM page locality of a grid-stride loop) instead of total_w separate streams
+    const long long ntiles = (a.n_rows + a.RT - 1) / a.RT;
+    w.nt = gw < ntiles ? static_cast<int>((ntiles - gw + total_w - 1) / total_w) : 0;
+    w.x0 = a.X + static_cast<long long>(gw) * a.tl;
+    w.y0 = reinterpret_cast<const char*>(a.y) + static_cast<long long>(gw) * a.RT * 4;
+    const bool owns_last = w.nt > 0 && gw + static_cast<long long>(w.nt - 1) * total_w == ntiles - 1;
+    w.rows_last = w.nt ? (owns_last ? static_cast<int>(a.n_rows - (ntiles - 1) * a.RT) : a.RT) : 0;
+    w.tail = owns_last ? 1 : 0;
+    return w;
+  }
   const long long units = (a.n_rows + 3) >> 2;  // 4-row units keep every warp's first row 16-byte aligned
   const long long u0 = units * gw / total_w, u1 = units * (gw + 1) / total_w;
   long long begin = u0 * 4;
   long long end = u1 * 4 < a.n_rows ? u1 * 4 : a.n_rows;
   if (end < begin) end = begin;
-  WarpTiles w;
   w.x0 = a.X + begin * a.ldx;
   w.y0 = reinterpret_cast<const char*>(a.y) + begin * 4;
   const long long n = end - begin;
@@ -80,6 +92,8 @@ __device__ __forceinline__ void ring_init(Ring& ring, float* base, uint64_t* bar
 // Loop-invariant plan constants, hoisted into registers once per kernel.
 struct PlanRegs {
   int stage_bytes, y_off_bytes, RT, tm, tl, S, ldx, D, zigzag, l2_hint;
+  long long xstride;  // floats between consecutive tiles of a warp
+  long long ystride;  // bytes of y between them
 };
 __device__ __forceinline__ PlanRegs plan_regs(const KArgs& a) {
   PlanRegs p;
@@ -93,6 +107,9 @@ __device__ __forceinline__ PlanRegs plan_regs(const KArgs& a) {
   p.D = a.D;
   p.zigzag = a.zigzag;
   p.l2_hint = a.l2_hint;
+  const long long every = a.interleave ? static_cast<long long>(gridDim.x) * (blockDim.x >> 5) : 1;
+  p.xstride = every * a.tl;
+  p.ystride = every * a.RT * 4;
   return p;
 }
 
@@ -106,14 +123,15 @@ __device__ __forceinline__ void ring_issue(const PlanRegs& pr, const WarpTiles& 
   const int rows = last ? wt.rows_last : pr.RT;
   const uint32_t sb = ring.base_s + ring.istage * pr.stage_bytes;
   const uint32_t bar = ring.bars_s + ring.istage * 8;
-  const char* ysrc = wt.y0 + (static_cast<long long>(kk) * pr.RT + lane) * 4;
+  const char* ysrc = wt.y0 + kk * pr.ystride + lane * 4;
   const uint32_t ydst = sb + pr.y_off_bytes + lane * 4;
   if (lane < rows) cp_async4_s(ydst, ysrc);
   for (int e = 32; lane + e < rows; e += 32) cp_async4_s(ydst + e * 4, ysrc + e * 4);
   cp_async_mbar_arrive_noinc_s(bar);
   if (lane == 0) {
-    const int m = (kk * pr.tm) & 3;
-    const float* src = wt.x0 + static_cast<long long>(kk) * pr.tl - m;
+    const float* tile = wt.x0 + kk * pr.xstride;
+    const int m = static_cast<int>(reinterpret_cast<uintptr_t>(tile) >> 2) & 3;  // X itself is 16-byte aligned
+    const float* src = tile - m;
     uint32_t bytes;
     if (last && wt.tail) {
       // never read past the last valid float of X: bulk-copy the 16-byte multiple, finish with scalar copies
@@ -280,7 +298,7 @@ __host__ __device__ constexpr int reg_cap(int nw) { return nw >= 16 ? 128 : (nw 
 
 template <int G, int V, int K, int NW>
 __device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, const WarpTiles& wt, Ring& ring,
-                                            const SmemLayout& sm, float bias, uint64_t policy) {
+                                            const SmemLayout& sm, float bias, uint64_t policy, bool want_lp) {
   constexpr int RPS = 32 / G;  // rows processed concurrently by a warp
   constexpr int KV = K * V;
   constexpr int NA = (V == 1) ? KV : KV / 2;          // packed accumulators per lane
@@ -308,13 +326,19 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, 
   float gb = 0.0f;
   double lp = 0.0;
 
+  // Wide models (NW*D floats exceed the xw scratch): the cross-warp reduction parks each warp's column sums in
+  // the ring stage that warp consumed last, so the re-arm of that one stage waits until the sums are read.
+  constexpr bool kMayPark = NW * G * K * V > kXwFloats;  // D <= G*K*V: narrow kernels never park
+  const bool park = kMayPark && NW * pr.D > kXwFloats;
+  bool deferred = false;
+  uint32_t park_s = ring.base_s;  // a warp without tiles never arms its ring: stage 0 is free
   const bool backward = pr.zigzag && (ring.cpass & 1);
   const int row_bytes = pr.ldx * 4;
   const uint32_t lane_off = grp * row_bytes + lg * V * 4;
   for (int kt = 0; kt < wt.nt; ++kt) {
     const int kk = backward ? (wt.nt - 1 - kt) : kt;
     const int rows = (kk == wt.nt - 1) ? wt.rows_last : pr.RT;
-    const int m = (kk * pr.tm) & 3;
+    const int m = static_cast<int>(reinterpret_cast<uintptr_t>(wt.x0 + kk * pr.xstride) >> 2) & 3;
     const uint32_t sb = ring.base_s + ring.stage * pr.stage_bytes;
     mbar_wait_s(ring.bars_s + ring.stage * 8, ring.parity);
     const uint32_t ys = sb + pr.y_off_bytes;
@@ -381,14 +405,17 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, 
 #pragma unroll
       for (int off = G / 2; off > 0; off >>= 1) dotv += __shfl_xor_sync(kFull, dotv, off);
       const float eta = dotv + bias;
-      float lpv, rv;
-      row_terms(family, eta, yv, lik_scale, lpv, rv);
+      float lpv = 0.0f, rv;
+      if (want_lp)  // CTA-uniform
+        row_terms(family, eta, yv, lik_scale, lpv, rv);
+      else
+        rv = row_resid(family, eta, yv, lik_scale);
       if (!valid) {
         lpv = 0.0f;
         rv = 0.0f;
       }
       if (lg == 0) {
-        lp += static_cast<double>(lpv);
+        if (want_lp) lp += static_cast<double>(lpv);
         gb += rv;
       }
       if constexpr (V == 1) {
@@ -405,7 +432,12 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, 
       ring.stage = 0;
       ring.parity ^= 1u;
     }
-    if (ring.qi < ring.q_total) ring_issue(pr, wt, ring, lane, policy);
+    if (park && kt == wt.nt - 1) {
+      park_s = sb;
+      deferred = ring.qi < ring.q_total;
+    } else if (ring.qi < ring.q_total) {
+      ring_issue(pr, wt, ring, lane, policy);
+    }
   }
   ++ring.cpass;
 
@@ -438,7 +470,7 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, 
   //      indices grp*LPF + j, i.e. chunk k = idx / V, element v = idx % V, column (k*G+lg)*V+v. ----
   const int D = a.D, P = a.P;
   double* xwd = reinterpret_cast<double*>(sm.xw + kXwFloats);  // [2][kMaxWarps]: bias-gradient and logp per warp
-  if (NW * D <= kXwFloats) {
+  if (!park) {
     // one-shot: every warp publishes its column sums, then each column is summed over the warps in order
 #pragma unroll
     for (int j = 0; j < LPF; ++j) {
@@ -467,21 +499,38 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, 
     }
     __syncthreads();
   } else {
-    for (int wq = 0; wq < NW; ++wq) {
-      if (warp == wq) {
+    // parked one-shot: same arithmetic as above (float64 sum over the warps in ascending order), the scratch of
+    // warp w being the D floats at the start of its parked stage
+    uint32_t* park_tab = reinterpret_cast<uint32_t*>(sm.xw);
 #pragma unroll
-        for (int j = 0; j < LPF; ++j) {
-          const int idx = grp * LPF + j;
-          const int col = ((idx / V) * G + lg) * V + (idx % V);
-          if (idx < KV && col < D) cta_acc[col] = (wq ? cta_acc[col] : 0.0) + static_cast<double>(h[j]);
-        }
-        if (lane == 0) {
-          if (a.has_bias) cta_acc[D] = (wq ? cta_acc[D] : 0.0) + static_cast<double>(gb);
-          cta_acc[P] = (wq ? cta_acc[P] : 0.0) + lp;
-        }
-      }
-      __syncthreads();
+    for (int j = 0; j < LPF; ++j) {
+      const int idx = grp * LPF + j;
+      const int col = ((idx / V) * G + lg) * V + (idx % V);
+      if (idx < KV && col < D) sts_f32(park_s + col * 4, h[j]);
     }
+    if (lane == 0) {
+      park_tab[warp] = park_s;
+      xwd[warp] = static_cast<double>(gb);
+      xwd[kMaxWarps + warp] = lp;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c <= P; c += NW * 32) {
+      double s = 0.0;
+      if (c < D) {
+#pragma unroll
+        for (int wq = 0; wq < NW; ++wq) s += static_cast<double>(lds_f32<0>(park_tab[wq] + c * 4));
+      } else if (c == P) {
+#pragma unroll
+        for (int wq = 0; wq < NW; ++wq) s += xwd[kMaxWarps + wq];
+      } else {
+#pragma unroll
+        for (int wq = 0; wq < NW; ++wq) s += xwd[wq];
+      }
+      cta_acc[c] = s;
+    }
+    fence_proxy_async_smem();  // the parked stages go back to the TMA (async proxy) after the barrier
+    __syncthreads();
+    if (deferred) ring_issue(pr, wt, ring, lane, policy);
   }
 }
 
