@@ -13,6 +13,7 @@
 #include "../../include/edhmc.h"
 #include "chain_small.cuh"
 #include "chains.cuh"
+#include "chains_wide.cuh"
 
 using namespace edhmc;
 
@@ -157,6 +158,9 @@ struct edhmc_handle {
   int* mc_flags = nullptr;  // [0] valid, [1] need_init
   double* mc_trace = nullptr;
   long long* mc_dbg = nullptr;
+  // wide models / row shards: two-GEMM path (chains_wide.cu)
+  bool mc_wide = false, mcw_pretiled = false;
+  McwArgs mcw;  // tiling + buffers; the run fields are filled per call
   float* mc_xt = nullptr;  // pre-tiled operand copy of X (tensor-core pass v3)
   float* mc_yt = nullptr;
   bool mc_pretiled = false;
@@ -359,7 +363,6 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   if (cfg->n_chains > 1) {
     if (cfg->n_chains % kMcChainsPerCta != 0)
       return fail(EDHMC_ERR_INVALID, "n_chains must be a multiple of %d, got %d", kMcChainsPerCta, cfg->n_chains);
-    if (cfg->n_features > kMcMaxD) return fail(EDHMC_ERR_INVALID, "vectorised chains support n_features <= %d", kMcMaxD);
     if (cfg->has_bias) return fail(EDHMC_ERR_INVALID, "vectorised chains do not support a bias latent yet");
   }
   const int P = cfg->n_features + (cfg->has_bias ? 1 : 0);
@@ -429,14 +432,39 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
     // pass implementation: 3 = pre-tiled pipelined tcgen05 (default), 2 = pipelined with per-pass operand
     // builders, 1 = sequential tcgen05, 0 = CUDA cores
     h->mc_use_tc = 3;
+    h->mc_wide = cfg->n_features > kMcMaxD;
     if (const char* e = getenv("EDHMC_MC_IMPL")) {
+      if (strcmp(e, "wide") == 0) h->mc_wide = true;
       if (strcmp(e, "simple") == 0) h->mc_use_tc = 0;
       else if (strcmp(e, "tc1") == 0) h->mc_use_tc = 1;
       else if (strcmp(e, "tc2") == 0) h->mc_use_tc = 2;
       else if (strcmp(e, "tc") == 0) h->mc_use_tc = 3;
     }
     if ((h->mc_use_tc == 1 || h->mc_use_tc == 2) && cfg->ldx > kMcMaxD) h->mc_use_tc = 3;
-    if (h->mc_use_tc == 3) {
+    memset(&h->mcw, 0, sizeof(h->mcw));
+    if (h->mc_wide) {
+      McwArgs& w = h->mcw;
+      w.n_rows = cfg->n_rows;
+      w.D = cfg->n_features;
+      w.C = h->C;
+      mcw_plan(w, h->num_sms);
+      const McwSizes z = mcw_sizes(w);
+      ALLOC(w.xk, z.xk);
+      ALLOC(w.xt, z.xt);
+      ALLOC(w.yt, z.yt);
+      ALLOC(w.wt, z.wt);
+      ALLOC(w.rp, z.rp);
+      ALLOC(w.part_g64, z.part_g64);
+      ALLOC(w.part_lp, z.part_lp);
+      ALLOC(w.gsum, z.gsum);
+      h->mc_use_tc = 0;
+      h->mc_nrg = 1;
+      cudaError_t e = mcw_prepare();
+      if (e != cudaSuccess) {
+        edhmc_destroy(h);
+        return fail(EDHMC_ERR_CUDA, "wide many-chain setup failed: %s", cudaGetErrorString(e));
+      }
+    } else if (h->mc_use_tc == 3) {
       size_t ytb = 0;
       const size_t xtb = mc_pretile_bytes(cfg->n_rows, h->mc_Dp, &ytb);
       ALLOC(h->mc_xt, xtb + 4096);
@@ -542,6 +570,14 @@ int edhmc_destroy(edhmc_t* h) {
   cudaFree(h->mc_part_lp);
   cudaFree(h->mc_xt);
   cudaFree(h->mc_yt);
+  cudaFree(h->mcw.xk);
+  cudaFree(h->mcw.xt);
+  cudaFree(h->mcw.yt);
+  cudaFree(h->mcw.wt);
+  cudaFree(h->mcw.rp);
+  cudaFree(h->mcw.part_g64);
+  cudaFree(h->mcw.part_lp);
+  cudaFree(h->mcw.gsum);
   delete h;
   return 0;
 }
@@ -569,6 +605,7 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
   CUDA_TRY(cudaMemsetAsync(&h->d_sc->valid, 0, sizeof(int), stream));
   if (h->mc_flags) CUDA_TRY(cudaMemsetAsync(h->mc_flags, 0, 2 * sizeof(int), stream));
   h->mc_pretiled = false;
+  h->mcw_pretiled = false;
   if (check_finite && h->cfg.n_rows > 0) {
     CUDA_TRY(cudaMemsetAsync(h->d_bad, 0, sizeof(unsigned long long), stream));
     k_check_finite<<<h->num_sms * 8, 256, 0, stream>>>(X, h->cfg.n_rows, h->cfg.ldx, h->cfg.n_features, h->y,
@@ -894,6 +931,82 @@ static void fill_mc_args(edhmc_handle* h, McArgs& a) {
   a.yt = h->mc_yt;
 }
 
+static void fill_mcw_args(edhmc_handle* h, McwArgs& a) {
+  a = h->mcw;  // tiling + buffers
+  const edhmc_cfg& c = h->cfg;
+  a.X = h->X;
+  a.y = h->y;
+  a.ldx = c.ldx;
+  a.family = c.family;
+  a.y_dtype = h->y_dtype;
+  a.lik_scale = c.lik_scale;
+  a.prior_loc = h->d_prior_loc;
+  a.prior_scale = h->d_prior_scale;
+  a.prior_const = h->prior_const;
+  a.want_logp = 1;
+  a.z = h->mc_z;
+  a.r = h->mc_r;
+  a.g = h->mc_g;
+  a.zcur = h->mc_zcur;
+  a.gcur = h->mc_gcur;
+  a.logp_cur = h->mc_logp;
+  a.k_old = h->mc_kold;
+  a.log_u = h->mc_logu;
+  a.n_accept = h->mc_nacc;
+  a.valid = h->mc_flags;
+  a.need_init = h->mc_flags + 1;
+  a.seed = h->seed;
+  a.trace = h->mc_trace;
+}
+
+// One evaluation of the per-chain [grad, logp] likelihood sums at theta, summed over the row shards.
+static int mcw_pass(edhmc_handle* h, const McwArgs& a, const float* theta, int gate, cudaStream_t stream) {
+  if (!h->mcw_pretiled) {
+    CUDA_TRY(mcw_launch_pretile(a, stream));
+    h->mcw_pretiled = true;
+    h->launches_last += 2;
+  }
+  CUDA_TRY(mcw_launch_pass(a, theta, gate, stream));
+  h->launches_last += 4;
+  if (h->nranks > 1) {
+    NCCL_TRY(g_nccl.AllReduce(a.gsum, a.gsum, static_cast<size_t>(a.C) * (a.D + 1), kNcclFloat64, kNcclSum, h->comm, stream));
+    ++h->launches_last;
+  }
+  return 0;
+}
+
+static int run_chains_wide(edhmc_handle* h, float* params, int64_t t0, int64_t n_iter, float step_size, int32_t n_steps,
+                           const float* r0, const float* u, cudaStream_t stream) {
+  McwArgs a;
+  fill_mcw_args(h, a);
+  a.params = params;
+  a.t0 = t0;
+  a.n_iter = n_iter;
+  a.eps = step_size;
+  a.half_eps = 0.5f * step_size;
+  a.L = n_steps;
+  a.r0 = r0;
+  a.u = u;
+  h->launches_last = 0;
+  h->passes_last = n_iter * n_steps;
+  CUDA_TRY(mcw_launch_check(a, stream));
+  if (int rc = mcw_pass(h, a, h->mc_zcur, 1, stream)) return rc;
+  CUDA_TRY(mcw_launch_init_finish(a, stream));
+  h->launches_last += 2;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    CUDA_TRY(mcw_launch_begin(a, it, stream));
+    ++h->launches_last;
+    for (int s = 0; s < n_steps; ++s) {
+      McwArgs as = a;
+      as.want_logp = (s == n_steps - 1) ? 1 : 0;
+      if (int rc = mcw_pass(h, as, h->mc_z, 0, stream)) return rc;
+      CUDA_TRY(mcw_launch_leap(a, it, s, stream));
+      ++h->launches_last;
+    }
+  }
+  return 0;
+}
+
 // Re-lays X into the tensor-core operand layout once per bound data set.
 static int mc_ensure_pretiled(edhmc_handle* h, const McArgs& a, cudaStream_t stream) {
   if (h->mc_use_tc == 3 && !h->mc_pretiled) {
@@ -914,6 +1027,8 @@ int edhmc_run_chains(edhmc_t* h, float* params, int64_t T, int64_t t0, int64_t n
   if (n_iter == 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (h->mc_wide) return run_chains_wide(h, params, t0, n_iter, step_size, n_steps, r0, u, stream);
+  if (h->nranks > 1) return fail(EDHMC_ERR_INVALID, "row-sharded vectorised chains use the wide path: set EDHMC_MC_IMPL=wide");
   McArgs a;
   fill_mc_args(h, a);
   a.params = params;
@@ -951,6 +1066,16 @@ int edhmc_logp_grad_chains(edhmc_t* h, const float* theta, double* logp, float* 
   if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data has not been called");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (h->mc_wide) {
+    McwArgs w;
+    fill_mcw_args(h, w);
+    h->launches_last = 0;
+    h->passes_last = 1;
+    if (int rc = mcw_pass(h, w, theta, 0, stream)) return rc;
+    CUDA_TRY(mcw_launch_logp_grad_finish(w, theta, logp, grad, stream));
+    ++h->launches_last;
+    return 0;
+  }
   McArgs a;
   fill_mc_args(h, a);
   if (int rc = mc_ensure_pretiled(h, a, stream)) return rc;

@@ -115,6 +115,64 @@ def test_chain_argument_checks():
   X, y = _data(100, 8, 0)
   with pytest.raises(_C.EdhmcError):
     engine.GLMSampler(engine.GLMSpec(8), X, y, n_chains=100)   # not a multiple of 128
-  Xw, yw = _data(100, 70, 0)
   with pytest.raises(_C.EdhmcError):
-    engine.GLMSampler(engine.GLMSpec(70), Xw, yw, n_chains=128)  # D > 64
+    engine.GLMSampler(engine.GLMSpec(8, has_bias=True), X, y, n_chains=128)  # no bias latent with vectorised chains
+
+
+# ---- wide models / the two-GEMM path (chains_wide.cu): n_features > 64, or forced with EDHMC_MC_IMPL=wide ----
+@pytest.mark.parametrize("N,D,C,impl", [(1000, 54, 128, "wide"), (5000, 200, 128, "tc"), (2111, 1000, 256, "tc"),
+                                        (20000, 72, 128, "tc"), (300, 1000, 128, "tc")])
+def test_wide_chain_logp_grad_matches_oracle(N, D, C, impl, monkeypatch):
+  X, y = _data(N, D, N + D)
+  s = _sampler(X, y, D, C, impl, monkeypatch)
+  rng = np.random.default_rng(5)
+  theta = (0.3 * rng.standard_normal((C, D)) / np.sqrt(D)).astype(np.float32)
+  theta[0] = 0.0
+  lp, g = s.logp_grad_chains(theta)
+  lp, g = lp.cpu().numpy(), g.cpu().numpy()
+  spec = o.GLMSpec(D)
+  for c in list(range(0, C, 37)) + [C - 1]:
+    lp64 = float(o.log_joint(X, y, theta[c], spec))
+    g64 = o.grad_log_joint(X, y, theta[c], spec)
+    assert abs(lp[c] - lp64) <= REL_LOGP * abs(lp64), (c, lp[c], lp64)
+    rel = np.max(np.abs(g[c] - g64)) / np.max(np.abs(g64))
+    assert rel <= REL_GRAD, (c, rel)
+  s.close()
+
+
+@pytest.mark.parametrize("D,impl", [(54, "wide"), (300, "tc")])
+def test_wide_chain_run_matches_independent_oracle_runs(D, impl, monkeypatch):
+  import torch
+  N, C, T, L, eps = 2000, 128, 5, 4, 0.02
+  X, y = _data(N, D, 11)
+  s = _sampler(X, y, D, C, impl, monkeypatch)
+  rng = np.random.Generator(np.random.Philox(key=99))
+  r0 = rng.standard_normal((T, C, D), dtype=np.float32)
+  u = np.clip(rng.random((T, C), dtype=np.float32), 1e-7, 1 - 1e-7).astype(np.float32)
+  z0 = (0.05 * rng.standard_normal((C, D))).astype(np.float32)
+  params = torch.zeros(T, C, D, device="cuda")
+  params[0] = torch.tensor(z0)
+  tr = s.set_chain_trace(T)
+  s.run_chains(params, 0, T, eps, L, r0=torch.tensor(r0), u=torch.tensor(u))
+  n_acc, logp = s.read_chain_state()
+  got = params.cpu().numpy()
+  tr = tr.cpu().numpy()
+  spec = o.GLMSpec(D)
+  ties = 0
+  for c in [0, 1, 64, 127]:
+    p64 = np.zeros((T, D))
+    p64[0] = z0[c]
+    infos, nacc = o.run(X, y, p64, r0[:, c], u[:, c], eps, L, spec)
+    forked = False
+    for i, info in enumerate(infos):
+      assert abs(tr[i, c, 1] - info.logp_new) <= REL_LOGP * abs(info.logp_new) + 1e-6, (c, i)
+      if bool(tr[i, c, 6] > 0.5) != info.accept:
+        assert info.margin < TIE_EPS, (c, i, info)
+        ties += 1
+        forked = True
+        break
+      assert np.max(np.abs(got[i, c] - p64[i])) <= REL_POS * max(np.max(np.abs(p64[i])), 1e-3), (c, i)
+    if not forked:
+      assert n_acc[c] == nacc
+  assert ties <= 1
+  s.close()
