@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "cfg2": dict(N=581012, D=54, T=100, L=10, name="cfg2: covertype-shaped N=581012 D=54, 1 chain, T=100, n_steps=10, step_size=0.5/N"),
     "cfg4": dict(N=10_000_000, D=1000, T=4, L=10, name="cfg4: N=10000000 D=1000, 1 chain, T=4, n_steps=10, step_size=0.5/N, rows sharded"),
+    "cfg5": dict(N=1_250_000, D=1000, T=1, L=4, C=1024, name="cfg5: N=1250000 rows PER GPU (10M at 8 GPUs) D=1000, 1024 vectorised chains (two tcgen05 3xTF32 GEMMs per step), rows sharded, ncclAllReduce of [grad, logp] per leapfrog step"),
     "cfg3": dict(N=581012, D=54, T=4, L=10, C=256, name="cfg3: covertype-shaped N=581012 D=54, 256 vectorised chains (tcgen05 3xTF32), T=4, n_steps=10"),
 }
 GEN_BLOCK = 65536
@@ -46,7 +47,7 @@ def parse():
   ap.add_argument("--steps", type=int, default=10)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  ap.add_argument("--workload", default=None, choices=[None, "cfg2", "cfg3", "cfg4"])
+  ap.add_argument("--workload", default=None, choices=[None, "cfg2", "cfg3", "cfg4", "cfg5"])
   ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                   help="N>1: in-kernel all-reduce over peer memory (default) or per-pass launch + ncclAllReduce")
   ap.add_argument("--no-scale-ref", action="store_true", help="skip the 1-GPU cfg4 point added to the N=1 line")
@@ -224,18 +225,31 @@ def tf32_peak():
 def run_chains(args, wl):
   """cfg 3: C vectorised chains on one GPU, tensor-core bound. value = chain leapfrog steps/s."""
   import torch
+  import torch.distributed as dist
   from edward_b200 import engine
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
   dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
   torch.cuda.set_device(dev)
-  N, D, T, L, C = wl["N"], wl["D"], wl["T"], wl["L"], wl["C"]
-  X, y = gen_device_rows(torch, dev, 0, N, D)
-  s = engine.GLMSampler(engine.GLMSpec(D), X, y, device=dev, n_chains=C)
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+  n_loc, D, T, L, C = wl["N"], wl["D"], wl["T"], wl["L"], wl["C"]
+  N = n_loc * world if world > 1 else n_loc  # rows are per GPU for the sharded workload (weak scaling)
+  r_lo, r_hi = shard_bounds(N, world, rank)  # block-aligned shards: the data do not depend on the world size
+  X, y = gen_device_rows(torch, dev, r_lo, r_hi - r_lo, D)
+  s = engine.GLMSampler(engine.GLMSpec(D), X, y, device=dev, n_chains=C, n_rows_global=N)
+  if world > 1:
+    s.init_comm(world, rank, peers=False)
   s.seed(1234)
   params = torch.zeros(T, C, D, device=dev)
   flush = torch.empty(512 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
   for _ in range(max(args.warmup, 3)):
     s.run_chains(params, 0, T, 0.5 / N, L)
   torch.cuda.synchronize(dev)
+  if world > 1:
+    dist.barrier()
+    torch.cuda.synchronize(dev)
   sampler = ClockSampler(dev.index)
   sampler.start()
   evs = []
@@ -247,25 +261,40 @@ def run_chains(args, wl):
     e1.record()
     evs.append((e0, e1))
   torch.cuda.synchronize(dev)
+  if world > 1:
+    dist.barrier()
+    torch.cuda.synchronize(dev)
   clocks = sampler.stop()
   ms = sum(a.elapsed_time(b) for a, b in evs)
-  steps = args.steps * T * L
-  alg = 4.0 * N * D * C * steps / (ms * 1e-3) / 1e12
-  peak, src = tf32_peak()
+  if world > 1:
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
   info = s.plan_info()
+  if rank != 0:
+    dist.destroy_process_group()
+    return
+  steps = args.steps * T * L
+  alg = 4.0 * (float(N) / world) * D * C * steps / (ms * 1e-3) / 1e12  # per GPU (mean shard)
+  peak, src = tf32_peak()
+  wide = D > 64
   line = {
-      "metric": "hmc_leapfrog_steps_per_s", "value": C * steps / (ms * 1e-3), "unit": "chain leapfrog steps/s", "n_gpus": 1,
+      "metric": "hmc_leapfrog_steps_per_s", "value": C * steps / (ms * 1e-3), "unit": "chain leapfrog steps/s", "n_gpus": world,
       "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 accumulate)", "data": "synthetic",
-      "config": {"workload": wl["name"], "rows": N, "features": D, "chains": C, "transitions_per_step": T,
-                 "leapfrog_per_transition": L, "l2": "L2 flushed between steps", "rng": "device Philox"},
+      "config": {"workload": wl["name"], "rows": N, "rows_per_gpu": n_loc, "features": D, "chains": C, "transitions_per_step": T,
+                 "leapfrog_per_transition": L, "l2": "L2 flushed between steps", "rng": "device Philox",
+                 "parallelism": "rows sharded over %d GPUs, ncclAllReduce of [grad, logp] (%d float64) per leapfrog step" % (world, C * (D + 1)) if world > 1 else "1 GPU"},
       "leapfrog_steps_of_all_chains_per_s": steps / (ms * 1e-3),
+      "rows_steps_per_s": float(N) * C * steps / (ms * 1e-3),
       "roofline": {"bound": "tensor", "achieved": 3.0 * alg, "peak": peak, "unit": "TFLOP/s", "frac": 3.0 * alg / peak,
                    "traffic": None, "peak_source": src, "algorithmic_tflops": alg,
-                   "kernel": "edhmc::k_mc_pass_tc3 (3xTF32: 3 executed MMA flops per algorithmic flop)"},
+                   "kernel": ("edhmc::k_mcw_gemm<1> + k_mcw_gemm<2>" if wide else "edhmc::k_mc_pass_tc3") + " (3xTF32: 3 executed MMA flops per algorithmic flop); per GPU"},
       "cpu_baseline": None, "e2e": None, "gpu_launches": info["launches_last_run"] * args.steps, "clocks": clocks,
   }
   print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -278,7 +307,7 @@ def main():
   if args.impl == "reference":
     run_reference(args, wl, wl_key)
     return
-  if wl_key == "cfg3":
+  if wl_key in ("cfg3", "cfg5"):
     run_chains(args, wl)
     return
 

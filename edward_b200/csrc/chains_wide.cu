@@ -375,20 +375,24 @@ __device__ __forceinline__ double mcw_finish_gradient(const McwArgs& a, int c, c
   return (mcw_chain_sum(pl, sh) - a.prior_const) + gs[a.D];
 }
 
-__global__ void k_mcw_check(const McwArgs a) {  // one block of 256 threads
-  __shared__ int s_need;
-  if (threadIdx.x == 0) s_need = !*a.valid;
-  __syncthreads();
+// Does the cached state (zcur, gcur, logp_cur) describe row max(t0-1,0) of the Empirical store? Two grid-wide
+// steps over the C*D elements: compare (any mismatch raises a.valid[2]), then re-seed zcur and publish need_init.
+__global__ void k_mcw_check_compare(const McwArgs a) {
   const long long t_prev = a.t0 > 0 ? a.t0 - 1 : 0;
   const size_t n = static_cast<size_t>(a.C) * a.D;
   bool mismatch = false;
-  for (size_t i = threadIdx.x; i < n; i += blockDim.x)
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
     if (__float_as_uint(a.params[t_prev * n + i]) != __float_as_uint(a.zcur[i])) mismatch = true;
-  if (mismatch) s_need = 1;
-  __syncthreads();
-  if (s_need)
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) a.zcur[i] = a.params[t_prev * n + i];
-  if (threadIdx.x == 0) *a.need_init = s_need;
+  if (__syncthreads_or(mismatch ? 1 : 0) && threadIdx.x == 0) atomicExch(a.valid + 2, 1);
+}
+__global__ void k_mcw_check_apply(const McwArgs a) {
+  const int need = (!a.valid[0] || a.valid[2]) ? 1 : 0;
+  const long long t_prev = a.t0 > 0 ? a.t0 - 1 : 0;
+  const size_t n = static_cast<size_t>(a.C) * a.D;
+  if (need)
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+      a.zcur[i] = a.params[t_prev * n + i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.need_init = need;  // nobody in this grid reads need_init
 }
 
 __global__ void __launch_bounds__(kMwChainThreads) k_mcw_init_finish(const McwArgs a) {
@@ -569,7 +573,10 @@ cudaError_t mcw_launch_pass(const McwArgs& a, const float* theta, int gate, cuda
   return cudaGetLastError();
 }
 cudaError_t mcw_launch_check(const McwArgs& a, cudaStream_t s) {
-  k_mcw_check<<<1, 256, 0, s>>>(a);
+  cudaError_t e = cudaMemsetAsync(a.valid + 2, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  k_mcw_check_compare<<<148, 256, 0, s>>>(a);
+  k_mcw_check_apply<<<148, 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t mcw_launch_init_finish(const McwArgs& a, cudaStream_t s) {

@@ -480,14 +480,14 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
     ALLOC(h->mc_kold, h->C * sizeof(double));
     ALLOC(h->mc_logu, h->C * sizeof(double));
     ALLOC(h->mc_nacc, h->C * sizeof(long long));
-    ALLOC(h->mc_flags, 2 * sizeof(int));
+    ALLOC(h->mc_flags, 4 * sizeof(int));
     ALLOC(h->mc_part_g, static_cast<size_t>(h->mc_nrg) * h->C * h->mc_Dp * sizeof(float));
     ALLOC(h->mc_part_lp, static_cast<size_t>(h->mc_nrg) * h->C * sizeof(double));
     cudaMemset(h->mc_zcur, 0, cd);
     cudaMemset(h->mc_gcur, 0, cd);
     cudaMemset(h->mc_logp, 0, h->C * sizeof(double));
     cudaMemset(h->mc_nacc, 0, h->C * sizeof(long long));
-    cudaMemset(h->mc_flags, 0, 2 * sizeof(int));
+    cudaMemset(h->mc_flags, 0, 4 * sizeof(int));
     if (h->mc_use_tc) {
       cudaError_t e = mc_prepare_tc();
       if (e != cudaSuccess) {
@@ -603,7 +603,7 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
   h->bound = true;
   // data changed: the cached log joint / gradient no longer apply
   CUDA_TRY(cudaMemsetAsync(&h->d_sc->valid, 0, sizeof(int), stream));
-  if (h->mc_flags) CUDA_TRY(cudaMemsetAsync(h->mc_flags, 0, 2 * sizeof(int), stream));
+  if (h->mc_flags) CUDA_TRY(cudaMemsetAsync(h->mc_flags, 0, 4 * sizeof(int), stream));
   h->mc_pretiled = false;
   h->mcw_pretiled = false;
   if (check_finite && h->cfg.n_rows > 0) {
@@ -759,7 +759,7 @@ int edhmc_reset(edhmc_t* h, void* stream_) {
   CUDA_TRY(cudaMemsetAsync(h->d_sc, 0, sizeof(ChainScalars), stream));
   if (h->C > 1) {
     CUDA_TRY(cudaMemsetAsync(h->mc_nacc, 0, h->C * sizeof(long long), stream));
-    CUDA_TRY(cudaMemsetAsync(h->mc_flags, 0, 2 * sizeof(int), stream));
+    CUDA_TRY(cudaMemsetAsync(h->mc_flags, 0, 4 * sizeof(int), stream));
   }
   return 0;
 }

@@ -112,3 +112,59 @@ def test_two_gpu_peer_exchange_matches_nccl_plan_bitwise():
   assert np.array_equal(a0[0], s0[0]) and a0[1] == s0[1] and a0[2] == s0[2]
   assert np.array_equal(a0[5], s0[5])  # per-transition trace: logp, K, ratio, accept
   assert np.array_equal(ax0[0], a0[0]) and np.array_equal(ax1[0], a0[0])  # chunked launches == one launch
+
+
+def _chain_worker(rank, world, port, N, D, C, T, L, eps, out):
+  import torch
+  import torch.distributed as dist
+  sys.path.insert(0, ROOT)
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  torch.cuda.set_device(rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  try:
+    import hmc_oracle as o
+    from edward_b200 import engine
+    from edward_b200.sharding import shard_bounds
+    X, y, _ = o.synth_data(N, D)
+    lo, hi = shard_bounds(N, world, rank, block=1024)
+    s = engine.GLMSampler(engine.GLMSpec(D), X[lo:hi], y[lo:hi], device="cuda:%d" % rank, n_rows_global=N, n_chains=C)
+    s.init_comm(world, rank)
+    rng = np.random.Generator(np.random.Philox(key=5))
+    r0 = rng.standard_normal((T, C, D), dtype=np.float32)
+    u = np.clip(rng.random((T, C), dtype=np.float32), 1e-7, 1 - 1e-7).astype(np.float32)
+    params = torch.zeros(T, C, D, device="cuda:%d" % rank)
+    s.run_chains(params, 0, T, eps, L, r0=torch.tensor(r0), u=torch.tensor(u))
+    n_acc, logp = s.read_chain_state()
+    out[rank] = (params.cpu().numpy(), np.asarray(n_acc), np.asarray(logp), r0, u)
+    s.close()
+  finally:
+    dist.destroy_process_group()
+
+
+def test_two_gpu_row_sharded_vectorised_chains_match_oracle():
+  """Config-5 shape in miniature: wide model, many chains, rows sharded over 2 GPUs, [grad, logp] of all chains
+  all-reduced once per leapfrog step; every rank holds the same chains, each equal to an independent oracle run."""
+  import torch
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs 2 GPUs")
+  import torch.multiprocessing as mp
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  import hmc_oracle as o
+  N, D, C, T, L, eps = 6000, 200, 128, 4, 3, 0.01
+  mgr = mp.Manager()
+  out = mgr.dict()
+  mp.spawn(_chain_worker, args=(2, _free_port(), N, D, C, T, L, eps, out), nprocs=2, join=True)
+  p0, n0, lp0, r0, u = out[0]
+  p1, n1, lp1, _, _ = out[1]
+  assert np.array_equal(p0, p1) and np.array_equal(n0, n1) and np.array_equal(lp0, lp1)
+  X, y, _ = o.synth_data(N, D)
+  spec = o.GLMSpec(D)
+  for c in (0, 77, 127):
+    p64 = np.zeros((T, D))
+    infos, nacc = o.run(X, y, p64, r0[:, c], u[:, c], eps, L, spec)
+    if any(info.margin < 1e-3 for info in infos):
+      continue
+    assert np.max(np.abs(p0[:, c] - p64)) <= 1e-4 * max(np.max(np.abs(p64)), 1e-3), c
+    assert n0[c] == nacc
