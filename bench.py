@@ -266,10 +266,25 @@ def run_chains(args, wl):
     torch.cuda.synchronize(dev)
   clocks = sampler.stop()
   ms = sum(a.elapsed_time(b) for a, b in evs)
+  per_rank_ms, allreduce_us = None, None
   if world > 1:
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms = float(tmax.item())
+    mine = torch.tensor([ms], dtype=torch.float64, device=dev)
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    per_rank_ms = [float(g.item()) / args.steps for g in gathered]
+    ms = max(float(g.item()) for g in gathered)
+    # the collective alone, same payload as one leapfrog step ([grad, logp] of all chains, float64)
+    buf = torch.zeros(C * (D + 1), dtype=torch.float64, device=dev)
+    for _ in range(3):
+      dist.all_reduce(buf)
+    torch.cuda.synchronize(dev)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(10):
+      dist.all_reduce(buf)
+    a1.record()
+    torch.cuda.synchronize(dev)
+    allreduce_us = a0.elapsed_time(a1) * 100.0
   info = s.plan_info()
   if rank != 0:
     dist.destroy_process_group()
@@ -287,6 +302,8 @@ def run_chains(args, wl):
                  "parallelism": "rows sharded over %d GPUs, ncclAllReduce of [grad, logp] (%d float64) per leapfrog step" % (world, C * (D + 1)) if world > 1 else "1 GPU"},
       "leapfrog_steps_of_all_chains_per_s": steps / (ms * 1e-3),
       "rows_steps_per_s": float(N) * C * steps / (ms * 1e-3),
+      "per_rank_ms_per_step": per_rank_ms, "allreduce_us_same_payload": allreduce_us,
+      "rows_per_rank": [shard_bounds(N, world, q)[1] - shard_bounds(N, world, q)[0] for q in range(world)],
       "roofline": {"bound": "tensor", "achieved": 3.0 * alg, "peak": peak, "unit": "TFLOP/s", "frac": 3.0 * alg / peak,
                    "traffic": None, "peak_source": src, "algorithmic_tflops": alg,
                    "kernel": ("edhmc::k_mcw_gemm<1> + k_mcw_gemm<2>" if wide else "edhmc::k_mc_pass_tc3") + " (3xTF32: 3 executed MMA flops per algorithmic flop); per GPU"},

@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(kMwThreads, 1) k_mcw_gemm(const McwArgs a, int
           tmem_wait_ld();
           const long long row0 = t * kMwRowTile + col0;
           float rv[16];
+          float lps = 0.0f;  // 16 terms in fp32, then one float64 add: the FP64 pipe is narrow
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float eta = __uint_as_float(v[j]);
@@ -278,9 +279,10 @@ __global__ void __launch_bounds__(kMwThreads, 1) k_mcw_gemm(const McwArgs a, int
               lpv = 0.0f;
               r = 0.0f;
             }
-            lp += static_cast<double>(lpv);
+            lps += lpv;
             rv[j] = r;
           }
+          lp += static_cast<double>(lps);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             float4 h, l;
@@ -526,8 +528,26 @@ void mcw_plan(McwArgs& a, int num_sms) {
   a.nrt = static_cast<int>((a.n_rows + kMwRowTile - 1) / kMwRowTile);
   if (a.nrt < 1) a.nrt = 1;
   a.rowsP = static_cast<long long>(a.nrt) * kMwRowTile;
-  a.nft = (a.D + 255) / 256;
-  a.NB2 = ((a.D + a.nft - 1) / a.nft + 15) / 16 * 16;
+  // GEMM 2 tiling: feature tiles of NB2 <= 256 columns (multiple of 16) x K splits; pick the tile count that keeps
+  // most SMs busy after padding (e.g. C=1024, D=1000: 6 tiles of 176 x 3 splits = 144 CTAs instead of 4 x 256 x 4 = 128)
+  {
+    const int nft0 = (a.D + 255) / 256;
+    double best = -1.0;
+    for (int nft = nft0; nft <= nft0 + 6; ++nft) {
+      const int nb = ((a.D + nft - 1) / nft + 15) / 16 * 16;
+      if (nb < 128 && nft > nft0) break;
+      int sp = num_sms / (a.nct * nft);
+      if (sp < 1) sp = 1;
+      const double ctas = static_cast<double>(a.nct) * nft * sp;
+      const double waves = ctas <= num_sms ? 1.0 : static_cast<double>((static_cast<int>(ctas) + num_sms - 1) / num_sms);
+      const double eff = ctas / (waves * num_sms) * a.D / (static_cast<double>(nft) * nb);
+      if (eff > best + 1e-9) {
+        best = eff;
+        a.nft = nft;
+        a.NB2 = nb;
+      }
+    }
+  }
   a.Dp2 = a.nft * a.NB2;
   int g1 = num_sms / a.nct;
   if (g1 < 1) g1 = 1;

@@ -52,4 +52,14 @@ for impl in ("simple", "tc"):
     assert torch.isfinite(params).all()
     s.close()
   print("chains ok", impl, flush=True)
+os.environ["EDHMC_MC_IMPL"] = "tc"
+for (N, D) in [(700, 200), (300, 1000)]:
+  X, y = data(N, D)
+  s = engine.GLMSampler(engine.GLMSpec(D), X, y, device=dev, n_chains=128)
+  s.seed(7)
+  params = torch.zeros(2, 128, D, device=dev)
+  s.run_chains(params, 0, 2, 0.01 / N, 2)
+  assert torch.isfinite(params).all()
+  s.close()
+print("wide chains ok", flush=True)
 print("ALL OK")
