@@ -238,20 +238,41 @@ static int make_plan(edhmc_handle* h) {
     }
   if (!p.K) return fail(EDHMC_ERR_INVALID, "internal: no tier for %d chunks", p.Kact);
   p.NW = force_nw > 0 ? force_nw : warps_for(p.K * p.V);
-  p.fn = lookup_kernel(p.G, p.V, p.K, p.NW);
-  if (!p.fn) return fail(EDHMC_ERR_INVALID, "no kernel compiled for G=%d V=%d K=%d NW=%d", p.G, p.V, p.K, p.NW);
   p.wpad = p.G * p.K * p.V;
   const int RPS = 32 / p.G;
   const long long row_bytes = ldx * 4;
   const size_t budget = static_cast<size_t>(h->smem_optin) - 1024;
   size_t offs[8];
-  const size_t fixed = smem_layout_bytes(p.NW, 0, 0, h->P, p.wpad, offs);
+  size_t fixed = smem_layout_bytes(p.NW, 0, 0, h->P, p.wpad, offs);
   if (fixed + 4096 > budget) return fail(EDHMC_ERR_INVALID, "chain state does not fit shared memory");
-  long long tile_target = static_cast<long long>((budget - fixed) / (static_cast<size_t>(p.NW) * 3));
-  if (tile_target > 7168) tile_target = 7168;
-  long long J = tile_target / (RPS * row_bytes);
-  if (J < 1) J = 1;
-  if (J > 8) J = 8;
+  // Tile size. Every tile costs ~150 instructions of ring bookkeeping per warp, so small tiles make the pass
+  // issue-bound instead of HBM-bound (D=1000, one 4 KB row per tile, 12 warps: 88 % of HBM peak; two rows per tile,
+  // 8 warps, double-buffered: 104 %). Default: three stages per warp with the default warp count; when that leaves
+  // tiles under 6 KB, trade warps for tile size (8 warps, three stages, or two if that is what doubles the tile).
+  // Not for odd row strides (V = 1): those kernels are bound by 32-bit shared loads and want the warps (measured).
+  auto rows_for = [&](int nw, int stages, long long cap) -> long long {
+    const size_t fx = smem_layout_bytes(nw, 0, 0, h->P, p.wpad, offs);
+    long long target = static_cast<long long>((budget - fx) / (static_cast<size_t>(nw) * stages)) - 192;
+    if (target > cap) target = cap;
+    long long j = target / (RPS * row_bytes);
+    return j < 1 ? 1 : (j > 8 ? 8 : j);
+  };
+  long long J = rows_for(p.NW, 3, 7168);
+  int bigtile = 1;
+  if (const char* e = getenv("EDHMC_BIGTILE")) bigtile = atoi(e);
+  if (bigtile && force_nw == 0 && p.NW != 8 && p.G >= 2 && p.V >= 2 && J * RPS * row_bytes < 6000 && lookup_kernel(p.G, p.V, p.K, 8)) {
+    const long long j3 = rows_for(8, 3, 8192 + 64), j2 = rows_for(8, 2, 12288);
+    long long jb = j3;
+    if (j3 * RPS * row_bytes < 6000 && j2 > j3) jb = j2;
+    if (jb * RPS * row_bytes >= J * RPS * row_bytes * 3 / 2) {
+      p.NW = 8;
+      J = jb;
+      fixed = smem_layout_bytes(p.NW, 0, 0, h->P, p.wpad, offs);
+    }
+  }
+  if (const char* e = getenv("EDHMC_FORCE_J")) J = atoi(e) > 0 ? atoi(e) : J;  // development: rows-per-tile multiplier
+  p.fn = lookup_kernel(p.G, p.V, p.K, p.NW);
+  if (!p.fn) return fail(EDHMC_ERR_INVALID, "no kernel compiled for G=%d V=%d K=%d NW=%d", p.G, p.V, p.K, p.NW);
   p.J = static_cast<int>(J);
   p.RT = RPS * p.J;
   p.tl = static_cast<int>(p.RT * ldx);
