@@ -168,3 +168,57 @@ def test_two_gpu_row_sharded_vectorised_chains_match_oracle():
       continue
     assert np.max(np.abs(p0[:, c] - p64)) <= 1e-4 * max(np.max(np.abs(p64)), 1e-3), c
     assert n0[c] == nacc
+
+
+def _frontend_worker(rank, world, port, N, D, T, out):
+  import torch
+  import torch.distributed as dist
+  sys.path.insert(0, ROOT)
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  if world > 1:
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  try:
+    import hmc_oracle as o
+    import edward_b200 as ed
+    from edward_b200 import tfshim as tf
+    from edward_b200.models import Bernoulli, Empirical, Normal
+    from edward_b200.sharding import shard_bounds
+    Xall, yall, _ = o.synth_data(N, D)
+    lo, hi = shard_bounds(N, world, rank, block=1024)
+    ed.set_seed(7)
+    X = tf.placeholder(tf.float32, [hi - lo, D])
+    w = Normal(loc=tf.zeros(D), scale=tf.ones(D))
+    y = Bernoulli(logits=ed.dot(X, w))
+    qw = Empirical(params=tf.Variable(tf.zeros([T, D])))
+    inference = ed.HMC({w: qw}, data={X: Xall[lo:hi], y: yall[lo:hi]})
+    inference.run(step_size=0.5 / N, n_steps=5, n_print=0, device="cuda:%d" % rank)
+    info = inference._sampler.plan_info()
+    out[(world, rank)] = (qw.params.eval(), int(inference.n_accept.eval()), info["plan_in_use"], info["launches_last_run"])
+  finally:
+    if world > 1:
+      dist.destroy_process_group()
+
+
+def test_two_gpu_ed_hmc_row_sharded_through_the_frontend():
+  """ed.HMC under torch.distributed: each rank passes its row shard as `data`, the sampler runs as one persistent
+  launch per GPU with the in-kernel all-reduce, and every rank ends with the chain a single GPU produces."""
+  import torch
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs 2 GPUs")
+  import torch.multiprocessing as mp
+  from edward_b200 import _C
+  N, D, T = 40000, 54, 30
+  mgr = mp.Manager()
+  out = mgr.dict()
+  mp.spawn(_frontend_worker, args=(2, _free_port(), N, D, T, out), nprocs=2, join=True)
+  mp.spawn(_frontend_worker, args=(1, _free_port(), N, D, T, out), nprocs=1, join=True)
+  p0, n0, plan0, launches0 = out[(2, 0)]
+  p1, n1, _, _ = out[(2, 1)]
+  ps, ns, _, _ = out[(1, 0)]
+  assert plan0 == _C.PLAN_PERSISTENT and launches0 == 1
+  assert np.array_equal(p0, p1) and n0 == n1
+  assert n0 == ns
+  assert np.max(np.abs(p0 - ps)) <= 1e-4 * np.max(np.abs(ps))
