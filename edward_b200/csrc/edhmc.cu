@@ -249,7 +249,8 @@ static int make_plan(edhmc_handle* h) {
   // issue-bound instead of HBM-bound (D=1000, one 4 KB row per tile, 12 warps: 88 % of HBM peak; two rows per tile,
   // 8 warps, double-buffered: 104 %). Default: three stages per warp with the default warp count; when that leaves
   // tiles under 6 KB, trade warps for tile size (8 warps, three stages, or two if that is what doubles the tile).
-  // Not for odd row strides (V = 1): those kernels are bound by 32-bit shared loads and want the warps (measured).
+  // Not for odd row strides (V = 1: bound by 32-bit shared loads) and not for lanes that hold fewer than 20 floats of a
+  // row (D = 8, 16, 32: the per-row link-function work dominates there): both want the warps (measured, profiles/README).
   auto rows_for = [&](int nw, int stages, long long cap) -> long long {
     const size_t fx = smem_layout_bytes(nw, 0, 0, h->P, p.wpad, offs);
     long long target = static_cast<long long>((budget - fx) / (static_cast<size_t>(nw) * stages)) - 192;
@@ -260,7 +261,7 @@ static int make_plan(edhmc_handle* h) {
   long long J = rows_for(p.NW, 3, 7168);
   int bigtile = 1;
   if (const char* e = getenv("EDHMC_BIGTILE")) bigtile = atoi(e);
-  if (bigtile && force_nw == 0 && p.NW != 8 && p.G >= 2 && p.V >= 2 && J * RPS * row_bytes < 6000 && lookup_kernel(p.G, p.V, p.K, 8)) {
+  if (bigtile && force_nw == 0 && p.NW != 8 && p.V >= 2 && p.K * p.V >= 20 && J * RPS * row_bytes < 6000 && lookup_kernel(p.G, p.V, p.K, 8)) {
     const long long j3 = rows_for(8, 3, 8192 + 64), j2 = rows_for(8, 2, 12288);
     long long jb = j3;
     if (j3 * RPS * row_bytes < 6000 && j2 > j3) jb = j2;
