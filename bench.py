@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     "cfg2": dict(N=581012, D=54, T=100, L=10, name="cfg2: covertype-shaped N=581012 D=54, 1 chain, T=100, n_steps=10, step_size=0.5/N"),
-    "cfg4": dict(N=10_000_000, D=1000, T=4, L=10, name="cfg4: N=10000000 D=1000, 1 chain, T=4, n_steps=10, step_size=0.5/N, rows sharded"),
+    "cfg4": dict(N=10_000_000, D=1000, T=100, L=10, name="cfg4: N=10000000 D=1000, 1 chain, T=100, n_steps=10, step_size=0.5/N, rows sharded"),
     "cfg5": dict(N=1_250_000, D=1000, T=1, L=4, C=1024, name="cfg5: N=1250000 rows PER GPU (10M at 8 GPUs) D=1000, 1024 vectorised chains (two tcgen05 3xTF32 GEMMs per step), rows sharded, ncclAllReduce of [grad, logp] per leapfrog step"),
     "cfg3": dict(N=581012, D=54, T=4, L=10, C=256, name="cfg3: covertype-shaped N=581012 D=54, 256 vectorised chains (tcgen05 3xTF32), T=4, n_steps=10"),
 }
@@ -404,7 +404,7 @@ def main():
         s1.run(p1, 0, T, eps, L)
         torch.cuda.synchronize(dev)
         ms1 = 0.0
-        for _ in range(2):
+        for _ in range(1):
           flush.fill_(1.0)
           a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
           a.record()
@@ -412,7 +412,7 @@ def main():
           b.record()
           torch.cuda.synchronize(dev)
           ms1 += a.elapsed_time(b)
-        n1_same = {"value": 2 * T * L / (ms1 * 1e-3), "unit": "leapfrog steps/s", "plan": "persistent, 1 GPU, same job"}
+        n1_same = {"value": 1 * T * L / (ms1 * 1e-3), "unit": "leapfrog steps/s", "plan": "persistent, 1 GPU, same job"}
         s1.close()
         del X1, y1
       except Exception as e:  # noqa: BLE001
@@ -421,14 +421,17 @@ def main():
 
   # ---- end to end through the public API: host arrays -> ed.HMC(...).run() -> samples on the host ----
   e2e = None
-  if not args.no_e2e and world == 1:
+  if not args.no_e2e:
     import edward_b200 as ed
     from edward_b200 import graph as g
     from edward_b200 import tfshim as tf
     from edward_b200.models import Bernoulli, Empirical, Normal
-    Xh = X.cpu().pin_memory()
-    yh = y.cpu().pin_memory()
-    e2e_steps = max(3, min(args.steps, 20))
+    n_loc = r_hi - r_lo
+    Xh = torch.empty(X.shape, dtype=X.dtype, pin_memory=True)
+    Xh.copy_(X)
+    yh = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+    yh.copy_(y)
+    e2e_steps = max(3, min(args.steps, 20)) if world == 1 else 2
     times = []
     h2d = Xh.numel() * 4 + yh.numel() * 4
     d2h = T * D * 4 + 16
@@ -436,8 +439,11 @@ def main():
       g.reset_default_graph()
       flush.fill_(1.0)
       torch.cuda.synchronize(dev)
+      if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize(dev)
       t0 = time.perf_counter()
-      xs = tf.placeholder(tf.float32, [N, D])
+      xs = tf.placeholder(tf.float32, [n_loc, D])  # under torch.distributed each rank passes its row shard
       beta = Normal(loc=tf.zeros(D), scale=tf.ones(D))
       ys = Bernoulli(logits=ed.dot(xs, beta))
       qbeta = Empirical(params=tf.Variable(tf.zeros([T, D])))
@@ -446,12 +452,20 @@ def main():
       samples = qbeta.params.eval()  # D2H read of the result
       n_acc = int(inference.n_accept.eval())
       dt = time.perf_counter() - t0
+      if world > 1:  # whole job: the slowest rank
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
       if i > 0:
         times.append(dt)
       assert samples.shape == (T, D) and 0 <= n_acc <= T
+      inference._sampler.close()
+      del inference, qbeta
     e2e = {"value": e2e_steps * T * L / sum(times), "unit": "leapfrog steps/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-           "call": "ed.HMC({beta: qbeta}, data={X: pinned host array, y: ...}).run(step_size, n_steps) + qbeta.params.eval()"}
+           "call": "ed.HMC({beta: qbeta}, data={X: pinned host array%s, y: ...}).run(step_size, n_steps) + qbeta.params.eval()"
+                   % (" (this rank's row shard; bytes are per rank)" if world > 1 else "")}
+    del Xh, yh
 
   # ---- the N=1 point of the row-sharded scaling series (cfg 4 on this GPU alone), so that the scale-out lines
   #      (--gpus 2/4/8 run cfg 4) have their single-GPU reference from the same protocol ----
@@ -468,14 +482,14 @@ def main():
       s4.run(p4, 0, w4["T"], 0.5 / w4["N"], w4["L"])
       torch.cuda.synchronize(dev)
       ms4 = 0.0
-      for _ in range(2):
+      for _ in range(1):
         a4, b4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a4.record()
         s4.run(p4, 0, w4["T"], 0.5 / w4["N"], w4["L"])
         b4.record()
         torch.cuda.synchronize(dev)
         ms4 += a4.elapsed_time(b4)
-      v4 = 2 * w4["T"] * w4["L"] / (ms4 * 1e-3)
+      v4 = 1 * w4["T"] * w4["L"] / (ms4 * 1e-3)
       scale_n1 = {"workload": w4["name"], "value": v4, "unit": "leapfrog steps/s",
                   "hbm_frac": (4.0 * w4["N"] * w4["D"] + 4.0 * w4["N"]) * v4 / 1e9 / measured_peaks()[0]}
       s4.close()

@@ -164,6 +164,10 @@ struct edhmc_handle {
   float* mc_xt = nullptr;  // pre-tiled operand copy of X (tensor-core pass v3)
   float* mc_yt = nullptr;
   bool mc_pretiled = false;
+  // one slab for the small per-handle buffers: a handle costs 2 cudaMalloc / cudaFree instead of ~20 (each cudaFree is
+  // a device synchronisation; ed.HMC builds and drops a handle per inference object)
+  unsigned char* arena = nullptr;
+  size_t arena_cap = 0, arena_used = 0;
   // stats
   long long passes_last = 0, launches_last = 0;
   int plan_in_use = 0;
@@ -171,6 +175,22 @@ struct edhmc_handle {
 
 // Shared-memory bank-conflict degree of the row loads for G lanes per row, vectors of V floats, row stride
 // ldx floats: lanes of one LDS phase (32/V lanes) hit bank groups of V words; returns the worst multiplicity.
+static cudaError_t h_alloc(edhmc_handle* h, void** p, size_t bytes) {
+  const size_t need = (bytes + 255) / 256 * 256;
+  if (h->arena && h->arena_used + need <= h->arena_cap) {
+    *p = h->arena + h->arena_used;
+    h->arena_used += need;
+    return cudaSuccess;
+  }
+  return cudaMalloc(p, bytes);
+}
+static void h_free(edhmc_handle* h, void* p) {
+  if (!p) return;
+  const unsigned char* q = static_cast<const unsigned char*>(p);
+  if (h->arena && q >= h->arena && q < h->arena + h->arena_cap) return;  // carved from the slab
+  cudaFree(p);
+}
+
 static int conflict_degree(long long ldx, int V, int G) {
   const int phase = 32 / V;  // lanes served together by one shared-memory wavefront
   int cnt[32] = {0};
@@ -422,13 +442,22 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   }
 #define ALLOC(ptr, bytes)                                                                    \
   do {                                                                                       \
-    cudaError_t e__ = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes));                 \
+    cudaError_t e__ = h_alloc(h, reinterpret_cast<void**>(&(ptr)), (bytes));                 \
     if (e__ != cudaSuccess) {                                                                \
       edhmc_destroy(h);                                                                      \
       return fail(EDHMC_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e__)); \
     }                                                                                        \
   } while (0)
   const size_t pb = static_cast<size_t>(P) * sizeof(float);
+  {
+    const size_t cap = static_cast<size_t>(2) * h->num_sms * (P + 1) * sizeof(double) + 24 * (static_cast<size_t>(P) + 64) * sizeof(double) + 65536;
+    if (cudaMalloc(reinterpret_cast<void**>(&h->arena), cap) == cudaSuccess) {
+      h->arena_cap = cap;
+    } else {
+      cudaGetLastError();
+      h->arena = nullptr;  // fall back to one allocation per buffer
+    }
+  }
   ALLOC(h->d_prior_loc, pb);
   ALLOC(h->d_prior_scale, pb);
   ALLOC(h->d_sc, sizeof(ChainScalars));
@@ -524,8 +553,11 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   {
     // inbox of the in-kernel reductions (second level of the wide single-GPU reduce; peer exchange when sharded)
     unsigned char* own[kMaxRanks] = {nullptr};
-    if (cudaMalloc(&h->d_inbox, kInboxBytes) != cudaSuccess || cudaMalloc(&h->d_peer_ptrs, sizeof(own)) != cudaSuccess ||
-        cudaMalloc(&h->d_comm_seq, sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&h->d_abort, sizeof(int)) != cudaSuccess) {
+    // the inbox is its own allocation: cudaIpcGetMemHandle exports whole allocations
+    if (cudaMalloc(&h->d_inbox, kInboxBytes) != cudaSuccess ||
+        h_alloc(h, reinterpret_cast<void**>(&h->d_peer_ptrs), sizeof(own)) != cudaSuccess ||
+        h_alloc(h, reinterpret_cast<void**>(&h->d_comm_seq), sizeof(unsigned long long)) != cudaSuccess ||
+        h_alloc(h, reinterpret_cast<void**>(&h->d_abort), sizeof(int)) != cudaSuccess) {
       edhmc_destroy(h);
       return fail(EDHMC_ERR_NOMEM, "cudaMalloc failed (inbox)");
     }
@@ -560,46 +592,47 @@ int edhmc_destroy(edhmc_t* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (int r = 0; r < kMaxRanks; ++r)
     if (h->peer_mapped[r]) cudaIpcCloseMemHandle(h->peer_mapped[r]);
-  cudaFree(h->d_inbox);
-  cudaFree(h->d_peer_ptrs);
-  cudaFree(h->d_comm_seq);
-  cudaFree(h->d_abort);
-  cudaFree(h->d_prior_loc);
-  cudaFree(h->d_prior_scale);
-  cudaFree(h->d_sc);
-  cudaFree(h->d_zcur);
-  cudaFree(h->d_gcur);
-  cudaFree(h->d_z);
-  cudaFree(h->d_r);
-  cudaFree(h->d_g);
-  cudaFree(h->d_partials);
-  cudaFree(h->d_bar);
-  cudaFree(h->d_ticket);
-  cudaFree(h->d_sums);
-  cudaFree(h->d_bad);
-  cudaFree(h->y_owned);
-  cudaFree(h->mc_z);
-  cudaFree(h->mc_r);
-  cudaFree(h->mc_g);
-  cudaFree(h->mc_zcur);
-  cudaFree(h->mc_gcur);
-  cudaFree(h->mc_logp);
-  cudaFree(h->mc_kold);
-  cudaFree(h->mc_logu);
-  cudaFree(h->mc_nacc);
-  cudaFree(h->mc_flags);
-  cudaFree(h->mc_part_g);
-  cudaFree(h->mc_part_lp);
-  cudaFree(h->mc_xt);
-  cudaFree(h->mc_yt);
-  cudaFree(h->mcw.xk);
-  cudaFree(h->mcw.xt);
-  cudaFree(h->mcw.yt);
-  cudaFree(h->mcw.wt);
-  cudaFree(h->mcw.rp);
-  cudaFree(h->mcw.part_g64);
-  cudaFree(h->mcw.part_lp);
-  cudaFree(h->mcw.gsum);
+  h_free(h, h->d_inbox);
+  h_free(h, h->d_peer_ptrs);
+  h_free(h, h->d_comm_seq);
+  h_free(h, h->d_abort);
+  h_free(h, h->d_prior_loc);
+  h_free(h, h->d_prior_scale);
+  h_free(h, h->d_sc);
+  h_free(h, h->d_zcur);
+  h_free(h, h->d_gcur);
+  h_free(h, h->d_z);
+  h_free(h, h->d_r);
+  h_free(h, h->d_g);
+  h_free(h, h->d_partials);
+  h_free(h, h->d_bar);
+  h_free(h, h->d_ticket);
+  h_free(h, h->d_sums);
+  h_free(h, h->d_bad);
+  h_free(h, h->y_owned);
+  h_free(h, h->mc_z);
+  h_free(h, h->mc_r);
+  h_free(h, h->mc_g);
+  h_free(h, h->mc_zcur);
+  h_free(h, h->mc_gcur);
+  h_free(h, h->mc_logp);
+  h_free(h, h->mc_kold);
+  h_free(h, h->mc_logu);
+  h_free(h, h->mc_nacc);
+  h_free(h, h->mc_flags);
+  h_free(h, h->mc_part_g);
+  h_free(h, h->mc_part_lp);
+  h_free(h, h->mc_xt);
+  h_free(h, h->mc_yt);
+  h_free(h, h->mcw.xk);
+  h_free(h, h->mcw.xt);
+  h_free(h, h->mcw.yt);
+  h_free(h, h->mcw.wt);
+  h_free(h, h->mcw.rp);
+  h_free(h, h->mcw.part_g64);
+  h_free(h, h->mcw.part_lp);
+  h_free(h, h->mcw.gsum);
+  cudaFree(h->arena);
   delete h;
   return 0;
 }
