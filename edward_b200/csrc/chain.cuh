@@ -334,7 +334,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   int bufsel = 0;
   unsigned long long epoch = 0;
   constexpr bool kMayWide = G * K * V + 2 > kWideCols;  // P + 1 <= G*K*V + 2: narrow kernels carry no wide path
-  const bool wide = kMayWide && !single && ncta > 1 && P + 1 > kWideCols;
+  // (with row shards the choice must not depend on this rank's grid size: every rank has to speak the same protocol)
+  const bool wide = kMayWide && !single && P + 1 > kWideCols && (ncta > 1 || a.nranks > 1);
   const bool guarded = a.nranks > 1 || wide;  // waits that can time out: poll the abort flag
   const unsigned long long seq0 = (!single && guarded) ? *a.comm_seq : 0ull;
   bool aborted = false;
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
       return;
     }
 
-    if (ncta > 1) {
+    if (ncta > 1 || wide) {
       double* mine = a.partials + (static_cast<size_t>(bufsel) * ncta + blockIdx.x) * (P + 1);
       for (int c = tid; c <= P; c += kThreads) mine[c] = sm.cta_acc[c];
       __syncthreads();

@@ -34,7 +34,7 @@ def _worker(rank, world, port, N, D, T, L, eps, out, plan_name="stepwise"):
     from edward_b200 import _C, engine
     from edward_b200.sharding import shard_bounds
     X, y, _ = o.synth_data(N, D)
-    lo, hi = shard_bounds(N, world, rank, block=1024)
+    lo, hi = shard_bounds(N, world, rank, block=1024 if N >= 4096 else 64)
     plan = {"stepwise": _C.PLAN_STEPWISE, "auto": _C.PLAN_AUTO}[plan_name]
     s = engine.GLMSampler(engine.GLMSpec(D), X[lo:hi], y[lo:hi], device="cuda:%d" % rank, plan=plan, n_rows_global=N)
     s.init_comm(world, rank)
@@ -88,15 +88,16 @@ def test_two_gpu_row_shards_match_single_gpu_and_oracle():
   assert np.max(np.abs(g0 - g64)) <= 1e-5 * np.max(np.abs(g64))
 
 
-def test_two_gpu_peer_exchange_matches_nccl_plan_bitwise():
+@pytest.mark.parametrize("N,D,T,L,eps", [(30000, 200, 8, 5, 0.002), (30000, 300, 6, 4, 0.002), (150, 300, 6, 4, 0.05)])
+def test_two_gpu_peer_exchange_matches_nccl_plan_bitwise(N, D, T, L, eps):
   """The persistent kernel's in-kernel all-reduce (stores into peer inboxes over NVLink) against the ncclAllReduce
-  plan: with two ranks both sum a+b, so the chains must agree bit for bit; one launch per run() call."""
+  plan: with two ranks both sum a+b, so the chains must agree bit for bit; one launch per run() call. D=200 uses the
+  flag protocol, D=300 the two-level slice protocol of wide models; 150 rows leave each rank with a one-CTA grid."""
   import torch
   if torch.cuda.device_count() < 2:
     pytest.skip("needs 2 GPUs")
   import torch.multiprocessing as mp
   from edward_b200 import _C
-  N, D, T, L, eps = 30000, 200, 8, 5, 0.002
   res = {}
   for plan_name in ("stepwise", "auto"):
     mgr = mp.Manager()
