@@ -86,3 +86,26 @@ def test_no_gpu_means_loud_failure():
   from edward_b200 import _C, engine
   with pytest.raises(_C.EdhmcError):
     engine.GLMSampler(engine.GLMSpec(2), np.zeros((4, 2), np.float32), np.zeros(4, np.int32))
+
+
+def test_generated_kernel_instances_are_in_sync(tmp_path, monkeypatch):
+  """csrc/inst_*.cu and inst_table.inc are what csrc/gen_inst.py generates (nobody edited them by hand, nobody forgot to
+  re-run the generator after changing the tiers)."""
+  import importlib.util
+  import shutil
+  csrc = os.path.join(ROOT, "edward_b200", "csrc")
+  spec = importlib.util.spec_from_file_location("gen_inst", os.path.join(csrc, "gen_inst.py"))
+  gen = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(gen)
+  monkeypatch.setattr(gen, "HERE", str(tmp_path))
+  gen.main()
+  produced = sorted(os.listdir(tmp_path))
+  committed = sorted(f for f in os.listdir(csrc) if f.startswith("inst_"))
+  assert produced == committed
+  for f in produced:
+    assert open(os.path.join(tmp_path, f)).read() == open(os.path.join(csrc, f)).read(), f
+  # every feature count the C ABI accepts has a kernel: the planner's rule restated in gen_inst.select
+  for V in (1, 2, 4):
+    for D in range(1, gen.MAXD + 1):
+      r = gen.select(D, V)
+      assert r is not None and r[1] is not None, (D, V)
