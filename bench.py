@@ -189,6 +189,9 @@ def run_reference(args, wl, wl_key):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
+  # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is one process that may use the whole host
+  if "LOCAL_RANK" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
   rows_cap = wl["N"] if wl_key == "cfg2" else wl["N"] // 64
   n_tr = 2
   for _ in range(args.warmup):
