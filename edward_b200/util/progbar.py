@@ -1,60 +1,78 @@
-"""Text progress bar with the output format of edward/util/progbar.py:12-115."""
+"""Console progress line for `Inference.run` / `print_progress`.
+
+The text a user sees is the reference's (edward/util/progbar.py): counter, percentage, a 30-cell bar, ETA while
+running and the elapsed time at the end, then ` | name: value` per reported statistic. The implementation is split
+into a pure formatter (`format_progress`, unit-testable without a terminal) and a small rate-limited writer.
+"""
 from __future__ import annotations
 
 import sys
 import time
+from typing import Mapping, Optional
+
+
+def _cells(n: int, stream) -> str:
+  """n filled cells: a block glyph where the stream can encode it, '*' elsewhere."""
+  glyph = "█"
+  codec = getattr(stream, "encoding", None) or "utf-8"
+  try:
+    glyph.encode(codec)
+  except (UnicodeEncodeError, LookupError):
+    glyph = "*"
+  return glyph * n
+
+
+def format_progress(done: int, total: int, elapsed: float, stats: Mapping[str, float], width: int = 30, stream=None):
+  """Returns (bar, tail): `  7/100 [  7%] ██            ` and ` ETA: 12s | Acceptance Rate: 0.912`."""
+  digits = len(str(total))
+  filled = int(width * float(done) / total)
+  bar = "".join([
+      str(done).rjust(digits), "/", str(total).rjust(digits),
+      " [", str(int(done / total * 100)).rjust(3), "%] ",
+      _cells(filled, stream if stream is not None else sys.stdout), " " * (width - filled),
+  ])
+  if done < total:
+    per_unit = elapsed / done if done else 0.0
+    tail = " ETA: %ds" % (per_unit * (total - done))
+  else:
+    tail = " Elapsed: %ds" % elapsed
+  tail += "".join(" | %s: %0.3f" % (name, value) for name, value in stats.items())
+  return bar, tail
 
 
 class Progbar(object):
+  """`Progbar(target).update(current, values={'Loss': x})`; `verbose=0` silences it."""
+
   def __init__(self, target, width=30, interval=0.01, verbose=1):
     self.target = target
     self.width = width
     self.interval = interval
     self.verbose = verbose
     self.stored_values = {}
+    self.seen_so_far = 0
+    self.total_width = 0
     self.start = time.time()
     self.last_update = 0
-    self.total_width = 0
-    self.seen_so_far = 0
 
-  def update(self, current, values=None, force=False):
-    """Print `current/target [pct%] bar ETA|Elapsed | name: value` (progbar.py:38-115): at most every
-    `interval` seconds unless `force` or the target is reached."""
-    for k, v in (values or {}).items():
-      self.stored_values[k] = v
+  def _due(self, now: float, current: int, force: bool) -> bool:
+    return force or current >= self.target or (now - self.last_update) >= self.interval
+
+  def update(self, current, values: Optional[Mapping[str, float]] = None, force=False):
+    if values:
+      self.stored_values.update(values)
     self.seen_so_far = current
     now = time.time()
-    if not force and (now - self.last_update) < self.interval and current < self.target:
+    if not self._due(now, current, force):
       return
     self.last_update = now
-    if self.verbose == 0:
+    if not self.verbose:
       return
-    prev_total_width = self.total_width
-    out = sys.stdout
-    out.write("\b" * prev_total_width)
-    out.write("\r")
-    n_digits = len(str(self.target))
-    bar = "%*d/%*d" % (n_digits, current, n_digits, self.target)
-    bar += " [{0}%] ".format(str(int(current / self.target * 100)).rjust(3))
-    prog_width = int(self.width * float(current) / self.target)
-    if prog_width > 0:
-      try:
-        block = "█" * prog_width
-        block.encode(getattr(out, "encoding", None) or "utf-8")
-      except (UnicodeEncodeError, LookupError):
-        block = "*" * prog_width
-      bar += block
-    bar += " " * (self.width - prog_width)
-    out.write(bar)
-    time_per_unit = (now - self.start) / current if current else 0
-    eta = time_per_unit * (self.target - current)
-    info = " ETA: %ds" % eta if current < self.target else " Elapsed: %ds" % (now - self.start)
-    for k, v in self.stored_values.items():
-      info += " | {0:s}: {1:0.3f}".format(k, v)
-    self.total_width = len(bar) + len(info)
-    if prev_total_width > self.total_width:
-      info += (prev_total_width - self.total_width) * " "
-    out.write(info)
-    out.flush()
+    stream = sys.stdout
+    bar, tail = format_progress(current, self.target, now - self.start, self.stored_values, self.width, stream)
+    shown = len(bar) + len(tail)
+    pad = " " * max(0, self.total_width - shown)  # blank out the remains of a longer previous line
+    stream.write("\b" * self.total_width + "\r" + bar + tail + pad)
+    self.total_width = shown
+    stream.flush()
     if current >= self.target:
-      out.write("\n")
+      stream.write("\n")
