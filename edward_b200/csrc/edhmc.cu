@@ -1164,6 +1164,23 @@ int edhmc_set_chain_trace(edhmc_t* h, double* trace) {
   return 0;
 }
 
+int edhmc_chains_plan_probe(int64_t n_rows, int32_t n_features, int32_t n_chains, int32_t num_sms, int64_t* out8) {
+  if (!out8) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (n_rows < 1 || n_features < 1 || n_features > kMaxFeatures || num_sms < 1)
+    return fail(EDHMC_ERR_INVALID, "bad n_rows / n_features / num_sms");
+  if (n_chains < kMcChainsPerCta || n_chains % kMcChainsPerCta != 0)
+    return fail(EDHMC_ERR_INVALID, "n_chains must be a multiple of %d, got %d", kMcChainsPerCta, n_chains);
+  McwArgs w;
+  memset(&w, 0, sizeof(w));
+  w.n_rows = n_rows;
+  w.D = n_features;
+  w.C = n_chains;
+  mcw_plan(w, num_sms);
+  const int64_t v[8] = {w.nct, w.Kp1, w.nrt, w.nft, w.NB2, w.g1, w.splits, w.Dp2};
+  for (int i = 0; i < 8; ++i) out8[i] = v[i];
+  return 0;
+}
+
 int edhmc_plan_info(edhmc_t* h, int64_t* out, int32_t cap) {
   if (!h || !out) return fail(EDHMC_ERR_INVALID, "null argument");
   const int64_t v[10] = {h->plan.grid,

@@ -109,3 +109,26 @@ def test_generated_kernel_instances_are_in_sync(tmp_path, monkeypatch):
     for D in range(1, gen.MAXD + 1):
       r = gen.select(D, V)
       assert r is not None and r[1] is not None, (D, V)
+
+
+def test_wide_chain_tiling_probe():
+  """Host-side planner of the two-GEMM vectorised-chain path (chains_wide.cu::mcw_plan), no GPU needed."""
+  from edward_b200 import _C
+  L = _C.lib()
+  out = (ctypes.c_int64 * 8)()
+
+  def probe(n, d, c, sms=148):
+    assert L.edhmc_chains_plan_probe(n, d, c, sms, out) == 0, L.edhmc_last_error()
+    return dict(zip(["nct", "Kp1", "nrt", "nft", "NB2", "g1", "splits", "Dp2"], list(out)))
+
+  p = probe(1_250_000, 1000, 1024)  # config 5, one GPU's shard
+  assert p["nct"] == 8 and p["Kp1"] == 1008 and p["nrt"] == 4883
+  assert (p["nft"], p["NB2"], p["splits"], p["Dp2"]) == (6, 176, 3, 1056)  # 144 of 148 SMs instead of 128
+  assert p["g1"] == 18
+  for n, d, c in [(300, 1000, 128), (2111, 1000, 256), (5000, 200, 128), (20000, 72, 128), (1000, 54, 128), (7, 2048, 256)]:
+    p = probe(n, d, c)
+    assert p["NB2"] % 16 == 0 and 16 <= p["NB2"] <= 256 and p["nft"] * p["NB2"] == p["Dp2"] >= d
+    assert p["Kp1"] % 16 == 0 and p["Kp1"] >= d and p["nrt"] * 256 >= n
+    assert 1 <= p["g1"] <= max(1, p["nrt"]) and p["nct"] * p["g1"] <= 148
+    assert p["splits"] >= 1 and p["nct"] * p["nft"] * p["splits"] <= max(148, p["nct"] * p["nft"])
+  assert L.edhmc_chains_plan_probe(100, 8, 100, 148, out) == _C.ERR_INVALID
