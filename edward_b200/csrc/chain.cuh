@@ -14,7 +14,7 @@
 // extra forward passes per transition (hmc.py:199,206,104-105); the values it recomputes — gradient
 // and log joint of the transition's start state — are cached here from the previous transition.
 #pragma once
-#include "stream.cuh"
+#include "stream_cta.cuh"
 
 namespace edhmc {
 
@@ -22,6 +22,12 @@ namespace edhmc {
 // (hmc.py:203-204,208: r + 0.5*step_size*grad ; z + step_size*r).
 __device__ __forceinline__ float kick(float r, float half_eps, float g) { return __fadd_rn(r, __fmul_rn(half_eps, g)); }
 __device__ __forceinline__ float drift(float z, float eps, float r) { return __fadd_rn(z, __fmul_rn(eps, r)); }
+
+struct ChainRegs {
+  double logp_cur, logp_new, k_old, log_u;
+  long long it, n_acc;
+  int s, nonfinite, in_init, pad;
+};
 
 struct AcceptResult {
   double ratio, log_u;
@@ -206,7 +212,21 @@ static __device__ __noinline__ bool wide_allreduce(const WideArgs a, unsigned lo
   return true;
 }
 
-template <int G, int V, int K, int NW>
+// Development timeline (edhmc_set_timeline): thread 0 of every CTA stamps clock64 / globaltimer at fixed points of
+// the first tl_cap passes of a persistent launch. Record = kTlRec int64: {pass start, tiles done + CTA reduced, partials
+// published, grid barrier passed, totals ready (incl. peer exchange), integrator done, globaltimer at pass start,
+// globaltimer at barrier passed, cycles warps 0..7 spent waiting for their tiles to land}.
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define EDHMC_TL(slot, val)                                                                                   \
+  do {                                                                                                        \
+    if (tl_on && pass < a.tl_cap) a.timeline[(static_cast<size_t>(pass) * gridDim.x + blockIdx.x) * kTlRec + (slot)] = (val); \
+  } while (0)
+
+template <int G, int V, int K, int NW, int RM = 0>
 __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   constexpr int kThreads = NW * 32;
   constexpr int CT = kChainThreads;  // O(P) chain work is owned by the first 256 threads: same reduction order for every NW
@@ -214,7 +234,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   if (single && a.gate && !a.sc->need_init) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_last;
-  const SmemLayout sm = carve_smem(smem_raw, a, NW);
+  // The chain scalars live in shared memory BETWEEN the serial sections: every thread reloads them after a data pass
+  // and thread 0 stores them back before the next one, so none of them occupies a register across the tile loop (with
+  // them live the allocator rematerialised address arithmetic inside the loop: 262 instructions per 32 rows, ncu r02).
+  // Two copies, selected by the parity of the pass: thread 0 may already store the state for pass p+1 while a slow
+  // warp still reads the state of pass p (a mid-trajectory serial section has no barrier between the two).
+  __shared__ ChainRegs s_cs2[2];
+  const int ngroups = RM == 1 ? NW / a.wpg : NW;  // ring mode 1: warp groups, each with a row range and a ring
+  const SmemLayout sm = carve_smem(smem_raw, a, ngroups);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = a.P, D = a.D;
   const int ncta = gridDim.x;
@@ -225,12 +252,32 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   float* zc = g + ppad;
   float* gc = zc + ppad;
 
-  smem_setup(sm, a, NW);
+  if constexpr (RM == 1)
+    smem_setup_cta(sm, a, ngroups);
+  else
+    smem_setup(sm, a, NW);
   const PlanRegs pr = plan_regs(a);
-  const uint64_t policy = a.l2_hint ? l2_policy_evict_last() : 0ull;
-  const WarpTiles wt = warp_tiles(a, blockIdx.x * NW + warp, ncta * NW);
-  Ring ring;
-  ring_init(ring, sm.ring + warp * a.S * a.stage_floats, sm.bars + warp * kMaxStages);
+  const uint64_t policy = a.l2_hint == 2 ? l2_policy_pin_fraction(a.l2_frac) : (a.l2_hint ? l2_policy_evict_last() : 0ull);
+  // ring mode 0: every warp owns a row range and a private ring; ring mode 1: the CTA owns a row range and one ring
+  const int group = RM == 1 ? warp / a.wpg : warp;
+  const WarpTiles wt = warp_tiles(a, blockIdx.x * ngroups + group, ncta * ngroups);
+  using RingT = typename std::conditional<RM == 1, CtaRing, Ring>::type;
+  RingT ring;
+  if constexpr (RM == 1)
+    cta_ring_init(ring, sm, a, group);
+  else
+    ring_init(ring, sm.ring + warp * a.S * a.stage_floats, sm.bars + warp * kMaxStages);
+  const bool tl_on = a.timeline != nullptr && tid == 0 && !single;
+
+  // prior of this thread's first latent, in registers: keeps two global loads and two float64 divisions off the
+  // serial section between two data passes
+  float pl0 = 0.0f, ps0 = 1.0f;
+  double piv0 = 1.0;
+  if (tid < P && tid < CT) {
+    pl0 = a.prior_loc[tid];
+    ps0 = a.prior_scale[tid];
+    piv0 = prior_inv_var(ps0);
+  }
 
   // ---- chain registers (uniform across threads and CTAs) ----
   double logp_cur = 0.0, logp_new = 0.0, k_old = 0.0, log_u = 0.0;
@@ -319,9 +366,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   {
     const int par0 = single ? (a.par0 & 1) : static_cast<int>((a.t0 * a.L - (in_init ? 1 : 0)) & 1);
     ring.cpass = par0;
-    ring.ipass = par0;
+    if constexpr (RM == 1)
+      ring.par0 = par0;
+    else
+      ring.ipass = par0;
   }
-  ring_prologue(pr, wt, ring, n_passes, lane, policy);
+  if constexpr (RM == 1)
+    cta_ring_prologue(pr, wt, ring, n_passes, policy, tid == group * a.wpg * 32);
+  else
+    ring_prologue(pr, wt, ring, n_passes, lane, policy);
   if (!single) {
     if (in_init) {
       for (int c = tid; c < D && tid < CT; c += CT) sm.theta_s[c] = zc[c];
@@ -329,6 +382,33 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
       start_next();
     }
   }
+  auto store_chain = [&](long long for_pass) {
+    if (tid == 0) {
+      ChainRegs& cs = s_cs2[for_pass & 1];
+      cs.logp_cur = logp_cur;
+      cs.logp_new = logp_new;
+      cs.k_old = k_old;
+      cs.log_u = log_u;
+      cs.it = it;
+      cs.n_acc = n_acc;
+      cs.s = s;
+      cs.nonfinite = nonfinite;
+      cs.in_init = in_init ? 1 : 0;
+    }
+  };
+  auto load_chain = [&](long long of_pass) {
+    const ChainRegs& cs = s_cs2[of_pass & 1];
+    logp_cur = cs.logp_cur;
+    logp_new = cs.logp_new;
+    k_old = cs.k_old;
+    log_u = cs.log_u;
+    it = cs.it;
+    n_acc = cs.n_acc;
+    s = cs.s;
+    nonfinite = cs.nonfinite;
+    in_init = cs.in_init != 0;
+  };
+  store_chain(0);
   __syncthreads();
 
   int bufsel = 0;
@@ -340,11 +420,18 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   const unsigned long long seq0 = (!single && guarded) ? *a.comm_seq : 0ull;
   bool aborted = false;
   for (long long pass = 0; pass < n_passes; ++pass) {
-    const float* pos = single ? a.theta_in : (in_init ? zc : z);
+    const bool in_init_p = s_cs2[pass & 1].in_init != 0;
+    const float* pos = single ? a.theta_in : (in_init_p ? zc : z);
     const float bias = a.has_bias ? pos[D] : 0.0f;
     // the log likelihood is only consumed at the ends of a trajectory (initial evaluation, last leapfrog step)
-    const bool want_lp = single || in_init || s + 1 >= a.L;
-    stream_pass<G, V, K, NW>(a, pr, wt, ring, sm, bias, policy, want_lp);
+    const bool want_lp = single || in_init_p || s_cs2[pass & 1].s + 1 >= a.L;
+    EDHMC_TL(0, clock64());
+    EDHMC_TL(6, global_timer_ns());
+    if constexpr (RM == 1)
+      stream_pass_cta<G, V, K, NW>(a, pr, wt, ring, sm, bias, policy, want_lp);
+    else
+      stream_pass<G, V, K, NW>(a, pr, wt, ring, sm, bias, policy, want_lp);
+    EDHMC_TL(1, clock64());
 
     if (single) {
       // last-arriving CTA folds the partials (threadFenceReduction pattern), fixed summation order
@@ -362,7 +449,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
         if (kMayWide && P + 1 > kWideCols)
           reduce_partials_wide(a.partials, ncta, P + 1, sm.cta_acc);
         else
-          reduce_partials(a.partials, ncta, P, sm.cta_acc, sm.comb);
+          reduce_partials<(NW >= 12 ? 20 : 40)>(a.partials, ncta, P, sm.cta_acc, sm.comb);
         for (int c = tid; c <= P; c += kThreads) a.sums[c] = sm.cta_acc[c];
         if (tid == 0) *a.ticket = 0u;
       }
@@ -373,6 +460,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
       double* mine = a.partials + (static_cast<size_t>(bufsel) * ncta + blockIdx.x) * (P + 1);
       for (int c = tid; c <= P; c += kThreads) mine[c] = sm.cta_acc[c];
       __syncthreads();
+      EDHMC_TL(2, clock64());
       if (tid == 0) {
         // release (cumulative over the CTA's writes ordered by the bar.sync above) / acquire on one counter
         red_release_add_u64(a.bar, 1ull);
@@ -397,7 +485,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
         aborted = true;
         break;
       }
-      if (!wide) reduce_partials(a.partials + static_cast<size_t>(bufsel) * ncta * (P + 1), ncta, P, sm.cta_acc, sm.comb);
+      EDHMC_TL(3, clock64());
+      EDHMC_TL(7, global_timer_ns());
+      if (!wide) reduce_partials<(NW >= 12 ? 20 : 40)>(a.partials + static_cast<size_t>(bufsel) * ncta * (P + 1), ncta, P, sm.cta_acc, sm.comb);
       bufsel ^= 1;
       ++epoch;
     }
@@ -429,12 +519,20 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
       }
     }
 
+    EDHMC_TL(4, clock64());
+    load_chain(pass);
     // gradient and log joint at `pos`: likelihood totals + Normal prior (hmc.py:183-190)
     float* gout = in_init ? gc : g;
     double pl = 0.0;
     for (int c = tid; c < P && tid < CT; c += CT) {
-      const float loc = a.prior_loc[c], sc = a.prior_scale[c];
-      gout[c] = static_cast<float>(sm.cta_acc[c] + prior_grad(pos[c], loc, sc));
+      float loc = pl0, sc = ps0;
+      double iv = piv0;
+      if (c != tid) {  // models with more than kChainThreads latents: the further columns come from global memory
+        loc = a.prior_loc[c];
+        sc = a.prior_scale[c];
+        iv = prior_inv_var(sc);
+      }
+      gout[c] = static_cast<float>(sm.cta_acc[c] + prior_grad_iv(pos[c], loc, iv));
       if (want_lp) pl += prior_quad(pos[c], loc, sc);
     }
     if (want_lp) {
@@ -464,10 +562,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
         }
       }
     }
+    store_chain(pass + 1);
     __syncthreads();
+    EDHMC_TL(5, clock64());
   }
 
   if (aborted) return;
+  load_chain(n_passes);
   if (!single && blockIdx.x == 0) {
     if (guarded && tid == 0) *a.comm_seq = seq0 + static_cast<unsigned long long>(n_passes);
     for (int c = tid; c < P && tid < CT; c += CT) {

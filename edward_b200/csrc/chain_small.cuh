@@ -10,7 +10,7 @@ __device__ __forceinline__ double finish_gradient(const KArgs& a, const float* p
   double pl = 0.0;
   for (int c = threadIdx.x; c < a.P; c += kChainThreads) {
     const float loc = a.prior_loc[c], sc = a.prior_scale[c];
-    gout[c] = static_cast<float>(a.sums[c] + prior_grad(pos[c], loc, sc));
+    gout[c] = static_cast<float>(a.sums[c] + prior_grad_iv(pos[c], loc, prior_inv_var(sc)));
     pl += prior_quad(pos[c], loc, sc);
   }
   return (block_sum_f64(pl, red) - a.prior_const) + a.sums[a.P];

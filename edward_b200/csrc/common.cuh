@@ -13,6 +13,7 @@ constexpr int kMaxStages = 8;
 constexpr int kXwFloats = 2048;  // per-CTA scratch for the one-shot cross-warp reduction (8 KB)
 constexpr int kMaxFeatures = 2048;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kTlRec = 16;  // int64 slots per (pass, CTA) record of the development timeline
 
 // Inbox of the in-kernel all-reduce (row shards over the GPUs of one NVLink domain; also the second level of
 // the wide single-GPU reduction). One cudaMalloc per rank, exported with cudaIpc: flags[2][kMaxRanks] (u64) at
@@ -67,10 +68,12 @@ struct KArgs {
   int y_off;         // float offset of the y slice inside a stage
   int wpad;          // padded length of theta in shared memory (G*KMAX*V)
   int zigzag;        // 1: odd passes walk a warp's tiles backwards (L2 reuse)
-  int l2_hint;       // 0 none, 1 evict_last on all X tiles
+  int l2_hint;       // 0 none, 1 evict_last on all X tiles, 2 evict_last on the fraction l2_frac of X, evict_first on the rest
+  float l2_frac;
   int ldx_i;         // ldx as int
   int tl;            // floats per full tile = RT*ldx
   int tm;            // tl & 3: per-tile drift of the 16-byte alignment (non-zero only if ldx % 4 != 0)
+  int wpg;           // ring mode 1: warps per group (each group owns a row range and a ring of S stages)
   int interleave;    // 1: tile t belongs to warp t % (grid*NW) (moving window); 0: contiguous row range per warp
   // ---- launch mode ----
   int mode;               // 0: run n_iter transitions (cooperative launch); 1: one data pass at theta_in
@@ -108,6 +111,8 @@ struct KArgs {
   unsigned long long seed;
   double* trace_scalars;
   float* trace_pos;
+  long long* timeline;  // development: [tl_cap][grid][kTlRec] int64 per-pass stamps of the persistent plan, or nullptr
+  int tl_cap;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -130,6 +135,19 @@ __device__ __forceinline__ float row_resid(int family, float eta, float yv, floa
   } else {
     return __fsub_rn(yv, expf(eta));
   }
+}
+
+// Bernoulli-logit residual y - sigmoid(eta) for the gradient-only passes inside a trajectory, on the special-function
+// unit: e = 2^(-|eta| log2 e) (ex2.approx) and 1/(1+e) (rcp.approx) — 7 dependent instructions instead of the ~25 of
+// expf + division. Absolute error <= 4e-7 per row (ex2.approx and rcp.approx are good to ~2 ulp on (0,1] and (1,2]),
+// two orders of magnitude inside the 1e-5 gradient tolerance; the log joint that decides acceptance is always
+// evaluated with row_terms below.
+__device__ __forceinline__ float bernoulli_resid_fast(float eta, float yv) {
+  float e, inv;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * fabsf(eta)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.0f + e));
+  const float q = e * inv;                       // sigmoid(-|eta|)
+  return (eta >= 0.0f) ? (yv - 1.0f) + q : yv - q;  // y - sigmoid(eta)
 }
 
 __device__ __forceinline__ void row_terms(int family, float eta, float yv, float lik_scale, float& lp, float& r) {
@@ -170,6 +188,15 @@ __device__ __forceinline__ float y_from_bits(uint32_t bits, int y_dtype) {
 __device__ __forceinline__ double prior_quad(float zc, float loc, float scale) {
   const double t = (static_cast<double>(zc) - static_cast<double>(loc)) / static_cast<double>(scale);
   return -0.5 * t * t;
+}
+// Same gradient with the reciprocal variance precomputed (one multiply on the critical path between two data passes
+// instead of two float64 divisions). The persistent and the stepwise plan both use this form, so they stay bit-identical.
+__device__ __forceinline__ double prior_inv_var(float scale) {
+  const double s = static_cast<double>(scale);
+  return 1.0 / (s * s);
+}
+__device__ __forceinline__ double prior_grad_iv(float zc, float loc, double inv_var) {
+  return -((static_cast<double>(zc) - static_cast<double>(loc)) * inv_var);
 }
 __device__ __forceinline__ double prior_grad(float zc, float loc, float scale) {
   const double s = static_cast<double>(scale);

@@ -100,6 +100,8 @@ static const int kNcclFloat64 = 8, kNcclSum = 0;
 struct Plan {
   int G = 0, V = 0, K = 0, Kact = 0, NW = 0, J = 0, RT = 0, S = 0, stage_floats = 0, y_off = 0, wpad = 0, tl = 0, tm = 0;
   int grid = 0;
+  int WPG = 0;  // ring mode 1: warps per group
+  int RM = 0;  // ring mode: 0 = one ring per warp (stream.cuh), 1 = one ring per CTA (stream_cta.cuh, narrow rows)
   size_t smem = 0;
   const void* fn = nullptr;
 };
@@ -119,6 +121,7 @@ struct edhmc_handle {
   Plan plan;
   int zigzag = 1;
   int l2_hint = 0;
+  float l2_frac = 1.0f;
   int interleave = 0;
   // device buffers
   float* d_prior_loc = nullptr;
@@ -171,6 +174,9 @@ struct edhmc_handle {
   // stats
   long long passes_last = 0, launches_last = 0;
   int plan_in_use = 0;
+  bool no_cta_ring = false;  // y is not 16-byte aligned: the CTA-wide ring (bulk copies of y) cannot be used
+  long long* timeline = nullptr;
+  int tl_cap = 0;
 };
 
 // Shared-memory bank-conflict degree of the row loads for G lanes per row, vectors of V floats, row stride
@@ -203,6 +209,102 @@ static int conflict_degree(long long ldx, int V, int G) {
   return worst;
 }
 
+// Ring mode 1 (stream_cta.cuh) for narrow rows: a row fits one lane at <= 64 floats. The row is spread over the fewest
+// lanes (1, 2 or 4, split lane map) that bring the register footprint under 128 so that 16 warps per SM hide the
+// latency of the link function; a stage holds NW * (32/G) * J rows (~1/3 of the shared memory), one bulk copy of X and
+// one of y. Returns false if the shape is not eligible (the caller then plans ring mode 0).
+static bool make_plan_cta(edhmc_handle* h, Plan& out) {
+  const edhmc_cfg& c = h->cfg;
+  Plan p;
+  p.RM = 1;
+  const int D = c.n_features;
+  const long long ldx = c.ldx;
+  p.V = (ldx % 4 == 0) ? 4 : (ldx % 2 == 0 ? 2 : 1);
+  const int kmax = 64 / p.V;
+  const int chunks = (D + p.V - 1) / p.V;
+  if (chunks > kmax || ldx > 4096) return false;
+  static const int tiers4[] = {1, 2, 3, 4, 5, 6, 7, 8, 12, 16}, tiers2[] = {1, 2, 4, 6, 8, 10, 12, 14, 16, 24, 27, 32},
+                   tiers1[] = {1, 2, 4, 8, 16, 28, 32, 64};
+  const int* tiers = p.V == 4 ? tiers4 : (p.V == 2 ? tiers2 : tiers1);
+  const int ntier = p.V == 4 ? 10 : (p.V == 2 ? 12 : 8);
+  auto tier_for = [&](int kact) {
+    for (int i = 0; i < ntier; ++i)
+      if (tiers[i] >= kact) return tiers[i];
+    return 0;
+  };
+  int force_g = 0, force_nw = 0, force_j = 0, force_wpg = 0;
+  if (const char* e = getenv("EDHMC_FORCE_G")) force_g = atoi(e);
+  if (const char* e = getenv("EDHMC_FORCE_NW")) force_nw = atoi(e);
+  if (const char* e = getenv("EDHMC_FORCE_J")) force_j = atoi(e);
+  if (const char* e = getenv("EDHMC_FORCE_WPG")) force_wpg = atoi(e);
+  const int gs[3] = {1, 2, 4};
+  for (int g : gs) {
+    if (force_g > 0 && g != force_g) continue;
+    const int kact = (chunks + g - 1) / g;
+    const int k = tier_for(kact);
+    if (!k) continue;
+    p.G = g;
+    p.Kact = kact;
+    p.K = k;
+    if (force_g > 0 || warps_for(k * p.V) == 16) break;
+  }
+  if (!p.G) return false;
+  p.NW = force_nw > 0 ? force_nw : warps_for(p.K * p.V);
+  p.fn = lookup_kernel(p.G, p.V, p.K, p.NW, 1);
+  if (!p.fn) return false;
+  p.wpad = p.G * p.K * p.V;
+  const int RPS = 32 / p.G;
+  p.WPG = (force_wpg > 0 && p.NW % force_wpg == 0) ? force_wpg : p.NW;
+  const int ngrp = p.NW / p.WPG;
+  const long long r1 = static_cast<long long>(p.WPG) * RPS;  // rows per stage of a group and J
+  if ((r1 & 3) != 0) return false;  // tiles must start on 4-row boundaries
+  const size_t budget = static_cast<size_t>(h->smem_optin) - 1024;
+  size_t offs[8];
+  const size_t fixed = smem_layout_bytes(ngrp, 0, 0, h->P, p.wpad, offs);
+  if (fixed + 8192 > budget) return false;
+  auto stage_floats_for = [&](long long J, int* y_off) {
+    const long long R = r1 * J;
+    long long xf = (R - 1) * ldx + p.wpad;
+    if (xf < R * ldx) xf = R * ldx;
+    xf = (xf + 3) / 4 * 4;
+    *y_off = static_cast<int>(xf);
+    return static_cast<long long>((xf + R + 31) / 32 * 32);
+  };
+  long long target = static_cast<long long>((budget - fixed) / 3);
+  if (target > 65536) target = 65536;
+  target /= ngrp;
+  long long J = force_j > 0 ? force_j : (target - 512) / (r1 * (ldx * 4 + 4));
+  if (J < 1) J = 1;
+  int y_off = 0;
+  long long sf = stage_floats_for(J, &y_off);
+  int S = kMaxStages;
+  for (; S >= 1; --S)
+    if (smem_layout_bytes(ngrp, S, static_cast<int>(sf), h->P, p.wpad, offs) <= budget) break;
+  if (S < 2) return false;
+  p.J = static_cast<int>(J);
+  p.RT = static_cast<int>(r1 * J);
+  p.tl = static_cast<int>(p.RT * ldx);
+  p.tm = 0;
+  p.y_off = y_off;
+  p.stage_floats = static_cast<int>(sf);
+  p.S = S;
+  p.smem = smem_layout_bytes(ngrp, S, p.stage_floats, h->P, p.wpad, offs);
+  if (cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p.fn, p.NW * 32, p.smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return false;
+  }
+  long long want = (c.n_rows + 2ll * p.RT * ngrp - 1) / (2ll * p.RT * ngrp);  // >= two tiles per group before another SM is used
+  if (want < 1) want = 1;
+  p.grid = static_cast<int>(want < h->num_sms ? want : h->num_sms);
+  out = p;
+  return true;
+}
+
 // Chooses the streaming geometry (restated in csrc/gen_inst.py, which instantiates every reachable kernel):
 // V = widest vector the row stride allows; G = 1 lane per row while the row fits 64 floats per lane (measured:
 // large tiles amortise the per-tile bookkeeping best), else the fewest lanes whose slice is <= 32 floats;
@@ -210,6 +312,15 @@ static int conflict_degree(long long ldx, int V, int G) {
 // tiles sized so that >= 3 ring stages per warp fit in shared memory.
 static int make_plan(edhmc_handle* h) {
   const edhmc_cfg& c = h->cfg;
+  {
+    int ring = 1;  // EDHMC_RING=0 keeps the per-warp rings for every shape (A/B runs)
+    if (const char* e = getenv("EDHMC_RING")) ring = atoi(e);
+    Plan pc;
+    if (ring == 1 && !h->no_cta_ring && !h->interleave && make_plan_cta(h, pc)) {
+      h->plan = pc;
+      return 0;
+    }
+  }
   Plan p;
   const int D = c.n_features;
   const long long ldx = c.ldx;
@@ -354,10 +465,14 @@ static void fill_args(edhmc_handle* h, KArgs& a) {
   a.wpad = p.wpad;
   a.zigzag = h->zigzag;
   a.l2_hint = h->l2_hint;
+  a.l2_frac = h->l2_frac;
   a.ldx_i = static_cast<int>(c.ldx);
   a.tl = p.tl;
   a.tm = p.tm;
-  a.interleave = h->interleave;
+  a.interleave = p.RM == 1 ? 0 : h->interleave;
+  a.wpg = p.WPG > 0 ? p.WPG : 1;
+  a.timeline = h->timeline;
+  a.tl_cap = h->tl_cap;
   a.partials = h->d_partials;
   a.bar = h->d_bar;
   a.ticket = h->d_ticket;
@@ -428,6 +543,7 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   h->prior_const = pc;
   if (const char* e = getenv("EDHMC_ZIGZAG")) h->zigzag = atoi(e);
   if (const char* e = getenv("EDHMC_L2_HINT")) h->l2_hint = atoi(e);
+  if (const char* e = getenv("EDHMC_L2_FRAC")) h->l2_frac = static_cast<float>(atof(e));
   if (const char* e = getenv("EDHMC_INTERLEAVE")) h->interleave = atoi(e);
   cudaError_t e1 = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   cudaError_t e2 = cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
@@ -648,6 +764,10 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
   h->X = X;
   h->y = y;
   h->y_dtype = h->cfg.y_dtype;
+  if (h->plan.RM == 1 && h->cfg.y_dtype != EDHMC_Y_U8 && reinterpret_cast<uintptr_t>(y) % 16 != 0) {
+    h->no_cta_ring = true;  // the CTA-wide ring bulk-copies y: fall back to the per-warp rings
+    if (int rc = make_plan(h)) return rc;
+  }
   if (h->cfg.y_dtype == EDHMC_Y_U8 && h->cfg.n_rows > 0) {
     if (!h->y_owned) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->y_owned), static_cast<size_t>(h->cfg.n_rows) * 4));
     k_u8_to_i32<<<h->num_sms * 4, 256, 0, stream>>>(reinterpret_cast<const unsigned char*>(y), h->y_owned, h->cfg.n_rows);
@@ -789,6 +909,13 @@ int edhmc_set_trace(edhmc_t* h, double* trace_scalars, float* trace_pos) {
   if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
   h->trace_scalars = trace_scalars;
   h->trace_pos = trace_pos;
+  return 0;
+}
+
+int edhmc_set_timeline(edhmc_t* h, long long* buf, int32_t n_passes) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  h->timeline = buf;
+  h->tl_cap = buf ? n_passes : 0;
   return 0;
 }
 
@@ -1183,7 +1310,7 @@ int edhmc_chains_plan_probe(int64_t n_rows, int32_t n_features, int32_t n_chains
 
 int edhmc_plan_info(edhmc_t* h, int64_t* out, int32_t cap) {
   if (!h || !out) return fail(EDHMC_ERR_INVALID, "null argument");
-  const int64_t v[10] = {h->plan.grid,
+  const int64_t v[11] = {h->plan.grid,
                          h->plan.NW,
                          h->plan.S,
                          h->plan.RT,
@@ -1192,8 +1319,9 @@ int edhmc_plan_info(edhmc_t* h, int64_t* out, int32_t cap) {
                          static_cast<int64_t>(h->plan.smem),
                          h->plan_in_use,
                          h->passes_last,
-                         h->launches_last};
-  int n = cap < 10 ? cap : 10;
+                         h->launches_last,
+                         h->plan.RM};
+  int n = cap < 11 ? cap : 11;
   for (int i = 0; i < n; ++i) out[i] = v[i];
   return n;
 }

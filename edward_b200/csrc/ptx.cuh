@@ -123,6 +123,14 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// A fixed (address-hashed) fraction of the lines is kept with evict_last priority, the rest is marked evict_first: when
+// a working set is slightly larger than the L2, the pinned fraction stays resident from pass to pass instead of the
+// whole set thrashing.
+__device__ __forceinline__ uint64_t l2_policy_pin_fraction(float frac) {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(p) : "f"(frac));
+  return p;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));

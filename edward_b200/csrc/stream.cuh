@@ -247,7 +247,8 @@ __host__ __device__ inline size_t smem_layout_bytes(int nw, int S, int stage_flo
   off += static_cast<size_t>(nw) * S * stage_floats * 4;
   off = align_up(off, 128);
   offs[1] = off;
-  off += static_cast<size_t>(kMaxWarps) * kMaxStages * 8;
+  off += static_cast<size_t>(kMaxWarps) * kMaxStages * 8;  // mbarriers
+  off += static_cast<size_t>(kMaxWarps) * kMaxStages * 4;  // consumer counters of the warp-group rings (ring mode 1)
   offs[2] = off;
   off += align_up(static_cast<size_t>(P + 1) * 8, 16);
   offs[3] = off;
@@ -290,157 +291,30 @@ __device__ __forceinline__ void smem_setup(const SmemLayout& L, const KArgs& a, 
   __syncthreads();
 }
 
-// One pass of this CTA over its rows. On return cta_acc[0..D) = Σ r_n·X[n,:], cta_acc[D] = Σ r_n (if
-// has_bias), cta_acc[P] = Σ log p(y_n|eta_n) over the CTA's rows, all float64, reduced in a fixed
-// order (bitwise reproducible). Ends with a __syncthreads().
-// Register cap per thread for NW warps of 32 threads with one CTA per SM.
-__host__ __device__ constexpr int reg_cap(int nw) { return nw >= 16 ? 128 : (nw >= 12 ? 168 : 255); }
+// Lane map of a warp. Interleaved (SPLIT = false): lane = grp*G + lg — the G lanes of a row are adjacent (per-warp
+// rings). Split (SPLIT = true): lane = lg*RPS + grp — lanes of one shared-memory wavefront read the same chunk of
+// consecutive rows, so the bank pattern is that of one lane per row whatever G is (CTA-wide ring).
+template <int G, bool SPLIT>
+struct LaneMap {
+  static constexpr int RPS = 32 / G;
+  static __device__ __forceinline__ int lg(int lane) { return SPLIT ? lane / RPS : (lane & (G - 1)); }
+  static __device__ __forceinline__ int grp(int lane) { return SPLIT ? (lane & (RPS - 1)) : lane / G; }
+  // xor distance of lane bit `b` of lg
+  static __device__ __forceinline__ constexpr int lg_xor(int b) { return SPLIT ? b * RPS : b; }
+};
 
-template <int G, int V, int K, int NW>
-__device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, const WarpTiles& wt, Ring& ring,
-                                            const SmemLayout& sm, float bias, uint64_t policy, bool want_lp) {
-  constexpr int RPS = 32 / G;  // rows processed concurrently by a warp
+// End of a pass: sums the per-lane gradient accumulators g[], the bias gradient gb and the log-likelihood lp over the
+// warp (halving butterfly) and then over the warps of the CTA (fixed order, float64) into sm.cta_acc[0..P].
+template <int G, int V, int K, int NW, bool SPLIT, typename WT, typename RING>
+__device__ __forceinline__ void pass_reduce(const KArgs& a, const PlanRegs& pr, const WT& wt, RING& ring, const SmemLayout& sm,
+                                            const typename Acc<V>::type* g, float gb, double lp, bool park, bool deferred,
+                                            uint32_t park_s, uint64_t policy) {
+  constexpr int RPS = 32 / G;
   constexpr int KV = K * V;
-  constexpr int NA = (V == 1) ? KV : KV / 2;          // packed accumulators per lane
-  constexpr bool WREG = (3 * KV + 40 <= reg_cap(NW));  // theta slice held in registers, else re-read from smem
-  using acc_t = typename Acc<V>::type;
+  constexpr int NA = (V == 1) ? KV : KV / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lg = lane & (G - 1), grp = lane / G;
-  const int family = a.family;
-  const float lik_scale = a.lik_scale;
-  const int y_dtype = a.y_dtype;
-  const float* theta_s = sm.theta_s;
+  const int lg = LaneMap<G, SPLIT>::lg(lane), grp = LaneMap<G, SPLIT>::grp(lane);
   double* cta_acc = sm.cta_acc;
-
-  acc_t g[NA];
-  acc_t w[WREG ? NA : 1];
-#pragma unroll
-  for (int i = 0; i < NA; ++i) {
-    if constexpr (V == 1)
-      g[i] = 0.0f;
-    else
-      g[i] = make_float2(0.0f, 0.0f);
-  }
-  if constexpr (WREG) load_chunks<V, K>(theta_s + lg * V, G * V, w);
-  const uint32_t theta_lane_s = smem_u32(theta_s) + lg * V * 4;
-  float gb = 0.0f;
-  double lp = 0.0;
-
-  // Wide models (NW*D floats exceed the xw scratch): the cross-warp reduction parks each warp's column sums in
-  // the ring stage that warp consumed last, so the re-arm of that one stage waits until the sums are read.
-  constexpr bool kMayPark = NW * G * K * V > kXwFloats;  // D <= G*K*V: narrow kernels never park
-  const bool park = kMayPark && NW * pr.D > kXwFloats;
-  bool deferred = false;
-  uint32_t park_s = ring.base_s;  // a warp without tiles never arms its ring: stage 0 is free
-  const bool backward = pr.zigzag && (ring.cpass & 1);
-  const int row_bytes = pr.ldx * 4;
-  const uint32_t lane_off = grp * row_bytes + lg * V * 4;
-  for (int kt = 0; kt < wt.nt; ++kt) {
-    const int kk = backward ? (wt.nt - 1 - kt) : kt;
-    const int rows = (kk == wt.nt - 1) ? wt.rows_last : pr.RT;
-    const int m = static_cast<int>(reinterpret_cast<uintptr_t>(wt.x0 + kk * pr.xstride) >> 2) & 3;
-    const uint32_t sb = ring.base_s + ring.stage * pr.stage_bytes;
-    mbar_wait_s(ring.bars_s + ring.stage * 8, ring.parity);
-    const uint32_t ys = sb + pr.y_off_bytes;
-    uint32_t xaddr = sb + m * 4 + lane_off;
-
-    for (int j0 = 0; j0 < rows; j0 += RPS, xaddr += RPS * row_bytes) {  // warp-uniform
-      const int lr = j0 + grp;
-      acc_t x[NA];
-      ChunkLoader<V, K, G * V>::load(xaddr, x);
-      const bool valid = lr < rows;
-      const float yv = y_from_bits(lds_u32(ys + (valid ? lr : 0) * 4), y_dtype);
-      float dotv;
-      if constexpr (V == 1) {
-        float a0 = 0.0f, a1 = 0.0f;
-        float wl[WREG ? 1 : NA];
-        if constexpr (!WREG) ChunkLoader<V, K, G * V>::load(theta_lane_s, wl);
-#pragma unroll
-        for (int i = 0; i < NA; ++i) {
-          float wi;
-          if constexpr (WREG)
-            wi = w[i];
-          else
-            wi = wl[i];
-          if (i & 1)
-            a1 = fmaf(x[i], wi, a1);
-          else
-            a0 = fmaf(x[i], wi, a0);
-        }
-        dotv = a0 + a1;
-      } else {
-        float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
-        if constexpr (WREG) {
-#pragma unroll
-          for (int i = 0; i < NA; ++i) {
-            if (i & 1)
-              a1 = fma2(x[i], w[i], a1);
-            else
-              a0 = fma2(x[i], w[i], a0);
-          }
-        } else {
-          // theta re-read from shared memory in 4 batches (keeps the live range short)
-          constexpr int KB = (K + 3) / 4;
-#pragma unroll
-          for (int kb = 0; kb < K; kb += KB) {
-            constexpr int NB = KB * (V / 2);
-            acc_t wk[NB];
-#pragma unroll
-            for (int k = 0; k < KB; ++k)
-              if (kb + k < K) load_chunks<V, 1>(theta_s + ((kb + k) * G + lg) * V, 0, &wk[k * (V / 2)]);
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-              const int i = kb * (V / 2) + q;
-              if (i < NA) {
-                if (q & 1)
-                  a1 = fma2(x[i], wk[q], a1);
-                else
-                  a0 = fma2(x[i], wk[q], a0);
-              }
-            }
-          }
-        }
-        dotv = (a0.x + a0.y) + (a1.x + a1.y);
-      }
-#pragma unroll
-      for (int off = G / 2; off > 0; off >>= 1) dotv += __shfl_xor_sync(kFull, dotv, off);
-      const float eta = dotv + bias;
-      float lpv = 0.0f, rv;
-      if (want_lp)  // CTA-uniform
-        row_terms(family, eta, yv, lik_scale, lpv, rv);
-      else
-        rv = row_resid(family, eta, yv, lik_scale);
-      if (!valid) {
-        lpv = 0.0f;
-        rv = 0.0f;
-      }
-      if (lg == 0) {
-        if (want_lp) lp += static_cast<double>(lpv);
-        gb += rv;
-      }
-      if constexpr (V == 1) {
-#pragma unroll
-        for (int i = 0; i < NA; ++i) g[i] = fmaf(rv, x[i], g[i]);
-      } else {
-        const float2 r2 = make_float2(rv, rv);
-#pragma unroll
-        for (int i = 0; i < NA; ++i) g[i] = fma2(r2, x[i], g[i]);
-      }
-    }
-    __syncwarp();
-    if (++ring.stage == pr.S) {
-      ring.stage = 0;
-      ring.parity ^= 1u;
-    }
-    if (park && kt == wt.nt - 1) {
-      park_s = sb;
-      deferred = ring.qi < ring.q_total;
-    } else if (ring.qi < ring.q_total) {
-      ring_issue(pr, wt, ring, lane, policy);
-    }
-  }
-  ++ring.cpass;
-
   // ---- reduce across the RPS row groups of the warp with a halving butterfly: after stage `st` a lane
   //      keeps the half of the accumulators selected by its own bit, so 32+16+8+4+2 shuffles sum 64
   //      accumulators over 32 lanes (instead of 64*5). ----
@@ -452,7 +326,7 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, 
   for (int i = 0; i < LP; ++i) h[i] = (i < KV) ? flat<V, NA>(g, i) : 0.0f;
 #pragma unroll
   for (int st = 0; st < NST; ++st) {
-    const int off = 16 >> st;
+    const int off = SPLIT ? ((RPS >> 1) >> st) : (16 >> st);
     const int half = LP >> (st + 1);
     const bool upper = (lane & off) != 0;
 #pragma unroll
@@ -530,17 +404,214 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, 
     }
     fence_proxy_async_smem();  // the parked stages go back to the TMA (async proxy) after the barrier
     __syncthreads();
-    if (deferred) ring_issue(pr, wt, ring, lane, policy);
+    if constexpr (!SPLIT) {
+      if (deferred) ring_issue(pr, wt, ring, lane, policy);
+    }
   }
+}
+
+
+// One row group: the warp's 32/G concurrent rows at shared address xaddr (already offset to this lane's row and
+// chunk). Computes the linear predictor, the likelihood term and its residual, and accumulates residual * x.
+// FAM >= 0 / LPM >= 0 fix the likelihood family and whether the log-likelihood is accumulated at compile time (the
+// CTA-ring pass dispatches once per pass, so the tile loop carries no uniform branches); -1 = decided at run time.
+// FAST: gradient-only Bernoulli passes use the special-function-unit residual (common.cuh bernoulli_resid_fast).
+template <int G, int V, int K, bool WREG, bool SPLIT, bool CHECK = true, int NCH = 2, int FAM = -1, int LPM = -1,
+          bool FAST = false>
+__device__ __forceinline__ void row_group(uint32_t xaddr, uint32_t ys, int lr, int rows, int lg,
+                                          const typename Acc<V>::type* w, uint32_t theta_lane_s, const float* theta_s,
+                                          float bias, int family, float lik_scale, int y_dtype, bool want_lp,
+                                          typename Acc<V>::type* g, float& gb, double& lp) {
+  constexpr int KV = K * V;
+  constexpr int NA = (V == 1) ? KV : KV / 2;
+  using acc_t = typename Acc<V>::type;
+  acc_t x[NA];
+  ChunkLoader<V, K, G * V>::load(xaddr, x);
+  const bool valid = CHECK ? (lr < rows) : true;
+  const float yv = y_from_bits(lds_u32(ys + (valid ? lr : 0) * 4), y_dtype);
+  float dotv;
+  if constexpr (V == 1) {
+    float a0 = 0.0f, a1 = 0.0f;
+    float wl[WREG ? 1 : NA];
+    if constexpr (!WREG) ChunkLoader<V, K, G * V>::load(theta_lane_s, wl);
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      float wi;
+      if constexpr (WREG)
+        wi = w[i];
+      else
+        wi = wl[i];
+      if (i & 1)
+        a1 = fmaf(x[i], wi, a1);
+      else
+        a0 = fmaf(x[i], wi, a0);
+    }
+    dotv = a0 + a1;
+  } else {
+    float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+    if constexpr (WREG && NCH == 4) {
+      // four independent accumulation chains: halves the dependent-FMA latency of a long row slice
+      float2 a2 = make_float2(0.0f, 0.0f), a3 = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        if ((i & 3) == 0)
+          a0 = fma2(x[i], w[i], a0);
+        else if ((i & 3) == 1)
+          a1 = fma2(x[i], w[i], a1);
+        else if ((i & 3) == 2)
+          a2 = fma2(x[i], w[i], a2);
+        else
+          a3 = fma2(x[i], w[i], a3);
+      }
+      a0.x += a2.x;
+      a0.y += a2.y;
+      a1.x += a3.x;
+      a1.y += a3.y;
+    } else if constexpr (WREG) {
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        if (i & 1)
+          a1 = fma2(x[i], w[i], a1);
+        else
+          a0 = fma2(x[i], w[i], a0);
+      }
+    } else {
+      // theta re-read from shared memory in 4 batches (keeps the live range short)
+      constexpr int KB = (K + 3) / 4;
+#pragma unroll
+      for (int kb = 0; kb < K; kb += KB) {
+        constexpr int NB = KB * (V / 2);
+        acc_t wk[NB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k)
+          if (kb + k < K) load_chunks<V, 1>(theta_s + ((kb + k) * G + lg) * V, 0, &wk[k * (V / 2)]);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          const int i = kb * (V / 2) + q;
+          if (i < NA) {
+            if (q & 1)
+              a1 = fma2(x[i], wk[q], a1);
+            else
+              a0 = fma2(x[i], wk[q], a0);
+          }
+        }
+      }
+    }
+    dotv = (a0.x + a0.y) + (a1.x + a1.y);
+  }
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) dotv += __shfl_xor_sync(kFull, dotv, LaneMap<G, SPLIT>::lg_xor(off));
+  const float eta = dotv + bias;
+  float lpv = 0.0f, rv;
+  const int fam = FAM >= 0 ? FAM : family;
+  const bool wlp = LPM >= 0 ? (LPM != 0) : want_lp;
+  if (wlp)  // CTA-uniform
+    row_terms(fam, eta, yv, lik_scale, lpv, rv);
+  else if (FAST && fam == 0)
+    rv = bernoulli_resid_fast(eta, yv);
+  else
+    rv = row_resid(fam, eta, yv, lik_scale);
+  if (CHECK && !valid) {
+    lpv = 0.0f;
+    rv = 0.0f;
+  }
+  if (lg == 0) {
+    if (wlp) lp += static_cast<double>(lpv);
+    gb += rv;
+  }
+  if constexpr (V == 1) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) g[i] = fmaf(rv, x[i], g[i]);
+  } else {
+    const float2 r2 = make_float2(rv, rv);
+#pragma unroll
+    for (int i = 0; i < NA; ++i) g[i] = fma2(r2, x[i], g[i]);
+  }
+}
+
+// One pass of this CTA over its rows. On return cta_acc[0..D) = Σ r_n·X[n,:], cta_acc[D] = Σ r_n (if
+// has_bias), cta_acc[P] = Σ log p(y_n|eta_n) over the CTA's rows, all float64, reduced in a fixed
+// order (bitwise reproducible). Ends with a __syncthreads().
+// Register cap per thread for NW warps of 32 threads with one CTA per SM.
+__host__ __device__ constexpr int reg_cap(int nw) { return nw >= 16 ? 128 : (nw >= 12 ? 168 : 255); }
+
+template <int G, int V, int K, int NW>
+__device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, const WarpTiles& wt, Ring& ring,
+                                            const SmemLayout& sm, float bias, uint64_t policy, bool want_lp) {
+  constexpr int RPS = 32 / G;  // rows processed concurrently by a warp
+  constexpr int KV = K * V;
+  constexpr int NA = (V == 1) ? KV : KV / 2;          // packed accumulators per lane
+  constexpr bool WREG = (3 * KV + 40 <= reg_cap(NW));  // theta slice held in registers, else re-read from smem
+  using acc_t = typename Acc<V>::type;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane & (G - 1), grp = lane / G;
+  const int family = a.family;
+  const float lik_scale = a.lik_scale;
+  const int y_dtype = a.y_dtype;
+  const float* theta_s = sm.theta_s;
+  double* cta_acc = sm.cta_acc;
+
+  acc_t g[NA];
+  acc_t w[WREG ? NA : 1];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    if constexpr (V == 1)
+      g[i] = 0.0f;
+    else
+      g[i] = make_float2(0.0f, 0.0f);
+  }
+  if constexpr (WREG) load_chunks<V, K>(theta_s + lg * V, G * V, w);
+  const uint32_t theta_lane_s = smem_u32(theta_s) + lg * V * 4;
+  float gb = 0.0f;
+  double lp = 0.0;
+
+  // Wide models (NW*D floats exceed the xw scratch): the cross-warp reduction parks each warp's column sums in
+  // the ring stage that warp consumed last, so the re-arm of that one stage waits until the sums are read.
+  constexpr bool kMayPark = NW * G * K * V > kXwFloats;  // D <= G*K*V: narrow kernels never park
+  const bool park = kMayPark && NW * pr.D > kXwFloats;
+  bool deferred = false;
+  uint32_t park_s = ring.base_s;  // a warp without tiles never arms its ring: stage 0 is free
+  const bool backward = pr.zigzag && (ring.cpass & 1);
+  const int row_bytes = pr.ldx * 4;
+  const uint32_t lane_off = grp * row_bytes + lg * V * 4;
+  for (int kt = 0; kt < wt.nt; ++kt) {
+    const int kk = backward ? (wt.nt - 1 - kt) : kt;
+    const int rows = (kk == wt.nt - 1) ? wt.rows_last : pr.RT;
+    const int m = static_cast<int>(reinterpret_cast<uintptr_t>(wt.x0 + kk * pr.xstride) >> 2) & 3;
+    const uint32_t sb = ring.base_s + ring.stage * pr.stage_bytes;
+    mbar_wait_s(ring.bars_s + ring.stage * 8, ring.parity);
+    const uint32_t ys = sb + pr.y_off_bytes;
+    uint32_t xaddr = sb + m * 4 + lane_off;
+
+    for (int j0 = 0; j0 < rows; j0 += RPS, xaddr += RPS * row_bytes) {  // warp-uniform
+      row_group<G, V, K, WREG, false>(xaddr, ys, j0 + grp, rows, lg, w, theta_lane_s, theta_s, bias, family, lik_scale,
+                                      y_dtype, want_lp, g, gb, lp);
+    }
+    __syncwarp();
+    if (++ring.stage == pr.S) {
+      ring.stage = 0;
+      ring.parity ^= 1u;
+    }
+    if (park && kt == wt.nt - 1) {
+      park_s = sb;
+      deferred = ring.qi < ring.q_total;
+    } else if (ring.qi < ring.q_total) {
+      ring_issue(pr, wt, ring, lane, policy);
+    }
+  }
+  ++ring.cpass;
+
+  pass_reduce<G, V, K, NW, false>(a, pr, wt, ring, sm, g, gb, lp, park, deferred, park_s, policy);
 }
 
 // Sums the per-CTA partials [ncta][P+1] (global, float64) in a fixed order into cta_acc[0..P].
 // Every CTA that calls this gets bit-identical totals. `comb` holds blockDim.x doubles. The loads of a
-// thread are issued in independent batches of 12 so that one or two L2 round trips cover them all.
+// thread are issued in independent batches of 40: with 148 CTAs and >= 4 thread slices per column ONE L2 round trip
+// covers them all (the timeline of round 2 showed four dependent rounds of 12 costing 2.8 us per leapfrog step).
+template <int B = 40>
 __device__ __forceinline__ void reduce_partials(const double* part, int ncta, int P, double* cta_acc, double* comb) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int ncol = P + 1;
-  constexpr int B = 12;
   int cpad = 32;
   while (cpad < ncol && cpad < nthr) cpad <<= 1;
   if (cpad >= ncol && cpad <= nthr) {

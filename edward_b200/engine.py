@@ -260,6 +260,18 @@ class GLMSampler:
     _C.check(self.lib.edhmc_set_trace(self._h, sc.data_ptr(), pos.data_ptr()))
     return sc, pos
 
+  def set_timeline(self, n_passes: int):
+    """Development aid: per-CTA clock64 stamps of the first n_passes passes of the next persistent run()
+    ([n_passes, grid, 16] int64; see edhmc_set_timeline). n_passes = 0 switches it off."""
+    if not n_passes:
+      self._timeline = None
+      _C.check(self.lib.edhmc_set_timeline(self._h, None, 0))
+      return None
+    grid = self.plan_info()["grid_ctas"]
+    self._timeline = torch.zeros(n_passes, grid, 16, dtype=torch.int64, device=self.dev)
+    _C.check(self.lib.edhmc_set_timeline(self._h, self._timeline.data_ptr(), int(n_passes)))
+    return self._timeline
+
   def clear_trace(self):
     self._trace = None
     _C.check(self.lib.edhmc_set_trace(self._h, None, None))
@@ -279,10 +291,10 @@ class GLMSampler:
     _C.check(self.lib.edhmc_seed(self._h, C.c_uint64(int(seed) & (2**64 - 1))))
 
   def plan_info(self) -> dict:
-    out = (C.c_int64 * 10)()
-    n = _C.check(self.lib.edhmc_plan_info(self._h, out, 10))
+    out = (C.c_int64 * 11)()
+    n = _C.check(self.lib.edhmc_plan_info(self._h, out, 11))
     keys = ["grid_ctas", "warps_per_cta", "ring_stages", "tile_rows", "lanes_per_row", "vec_width", "smem_bytes",
-            "plan_in_use", "passes_last_run", "launches_last_run"]
+            "plan_in_use", "passes_last_run", "launches_last_run", "ring_mode"]
     return {k: int(out[i]) for i, k in enumerate(keys[:n])}
 
   def close(self):

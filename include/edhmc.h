@@ -189,9 +189,25 @@ int edhmc_set_chain_trace(edhmc_t* h, double* trace);
 /* Development aid: [64][16] int64 per-role clock64 timeline of one CTA of the pipelined tensor-core pass. */
 int edhmc_set_chain_debug(edhmc_t* h, long long* buf);
 
+/* Development aid for the persistent plan of edhmc_run: thread 0 of every CTA stamps its first `n_passes` data passes
+ * into buf [n_passes][grid_ctas][16] int64 (device): clock64 at {pass start, CTA sums ready, partials published, grid
+ * barrier passed, totals ready (after the peer exchange when sharded), integrator done}, then %globaltimer (ns) at
+ * {pass start, grid barrier passed}, then the cycles warps 0..7 spent waiting for their tiles to land (one-ring-per-CTA
+ * plans). NULL switches it off (default). bench.py reports the medians as `timeline`.
+ * Replaces: nothing in the reference (introspection). */
+int edhmc_set_timeline(edhmc_t* h, long long* buf, int32_t n_passes);
+
+/* Read-bandwidth probe for the roofline denominators (bench.py): queues `iters` read sweeps over buf[0..bytes) on
+ * `stream`; the caller times them with CUDA events. mode 0: LDG.128 grid-stride loads; mode 1: 1-D TMA bulk copies into
+ * a shared-memory ring (the access path of the sampler's data pass). A buffer that fits the L2 gives the L2 read
+ * throughput, one much larger than L2 the read-only HBM throughput. buf 16-byte aligned, bytes >= 1 MiB (mode 1 reads
+ * whole 32 KiB chunks), sink: 4 writable device bytes. Replaces: nothing in the reference (measurement aid). */
+int edhmc_probe_read(const void* buf, int64_t bytes, int32_t iters, int32_t mode, void* sink, void* stream);
+
 /* Introspection for benches/tests: fills up to `cap` int64 values:
  * {grid_ctas, warps_per_cta, ring_stages, tile_rows, lanes_per_row, vec_width, smem_bytes,
- *  plan_in_use, passes_last_run, launches_last_run}. Returns the number written. */
+ *  plan_in_use, passes_last_run, launches_last_run, ring_mode (0: one TMA ring per warp, 1: one ring per CTA)}.
+ * Returns the number written. */
 int edhmc_plan_info(edhmc_t* h, int64_t* out_host, int32_t cap);
 
 /* Host-only: the tiling edhmc_create would choose for the wide / row-sharded vectorised-chain path (two-GEMM
