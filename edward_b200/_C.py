@@ -22,7 +22,7 @@ EXPORTS = [
     "edhmc_version", "edhmc_last_error", "edhmc_create", "edhmc_destroy", "edhmc_bind_data",
     "edhmc_logp_grad", "edhmc_run", "edhmc_set_trace", "edhmc_read_state", "edhmc_reset", "edhmc_seed",
     "edhmc_comm_unique_id", "edhmc_comm_init", "edhmc_peer_export", "edhmc_peer_attach", "edhmc_peer_detach", "edhmc_plan_info",
-    "edhmc_sgmcmc_run", "edhmc_run_chains", "edhmc_logp_grad_chains", "edhmc_read_chain_state", "edhmc_set_chain_trace", "edhmc_set_chain_debug", "edhmc_chains_plan_probe", "edhmc_set_timeline", "edhmc_probe_read",
+    "edhmc_sgmcmc_run", "edhmc_run_chains", "edhmc_logp_grad_chains", "edhmc_read_chain_state", "edhmc_set_chain_trace", "edhmc_set_chain_debug", "edhmc_chains_plan_probe", "edhmc_set_timeline", "edhmc_probe_read", "edhmc_comm_cached", "edhmc_comm_release",
 ]
 
 
@@ -100,6 +100,8 @@ def lib():
   L.edhmc_chains_plan_probe.argtypes = [i64, i32, i32, i32, C.POINTER(i64)]
   L.edhmc_set_timeline.argtypes = [vp, vp, i32]
   L.edhmc_probe_read.argtypes = [vp, i64, i32, i32, vp, vp]
+  L.edhmc_comm_cached.argtypes = [i32, i32, i32]
+  L.edhmc_comm_release.argtypes = [i32]
   for name in EXPORTS:
     if name not in ("edhmc_last_error",):
       getattr(L, name).restype = C.c_int

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
     const float* pos = single ? a.theta_in : (in_init_p ? zc : z);
     const float bias = a.has_bias ? pos[D] : 0.0f;
     // the log likelihood is only consumed at the ends of a trajectory (initial evaluation, last leapfrog step)
-    const bool want_lp = single || in_init_p || s_cs2[pass & 1].s + 1 >= a.L;
+    const bool want_lp = single ? (a.single_lp != 0) : (in_init_p || s_cs2[pass & 1].s + 1 >= a.L);
     EDHMC_TL(0, clock64());
     EDHMC_TL(6, global_timer_ns());
     if constexpr (RM == 1)

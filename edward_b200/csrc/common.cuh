@@ -79,6 +79,8 @@ struct KArgs {
   int mode;               // 0: run n_iter transitions (cooperative launch); 1: one data pass at theta_in
   int gate;               // mode 1: return immediately unless sc->need_init
   int par0;               // mode 1: parity of this pass's global leapfrog-step index (zig-zag direction)
+  int single_lp;          // mode 1: 1 = accumulate the log-likelihood too, 0 = gradient-only pass (as the persistent plan
+                          // runs the leapfrog steps inside a trajectory, so that both plans stay bit-identical)
   const float* theta_in;  // mode 1: [P]
   // ---- row shards over several GPUs (persistent plan): one-shot all-reduce through peer memory ----
   int nranks;                        // 1: no exchange

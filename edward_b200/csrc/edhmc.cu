@@ -95,6 +95,34 @@ static int nccl_load() {
 static const int kNcclFloat64 = 8, kNcclSum = 0;
 
 // ------------------------------------------------------------------------------------------------
+// Process-wide communicator state, one per device: the NCCL communicator and the peer-mapped inboxes of the in-kernel
+// all-reduce are created by the FIRST handle of a (device, nranks, rank) and reused by every later one. ed.HMC builds a
+// handle per inference object; without the cache each construction paid ncclCommInitRank + cudaIpc export / attach +
+// three all-gathers (2.4 s of a 3.2 s call at 8 GPUs, round-1 verdict). The exchange sequence number lives with the
+// inboxes, so handles that share them continue one sequence; sharded runs of one process must not overlap in time.
+// ------------------------------------------------------------------------------------------------
+struct SharedComm {
+  void* comm = nullptr;
+  int nranks = 0, rank = -1;
+  unsigned char* inbox = nullptr;            // this rank's inbox (own cudaMalloc: cudaIpc exports whole allocations)
+  unsigned char** d_peer_ptrs = nullptr;     // device table [kMaxRanks]
+  unsigned long long* d_seq = nullptr;       // passes exchanged so far (identical on every rank)
+  void* mapped[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool peers_ready = false;
+};
+static SharedComm g_shared[64];
+
+static void shared_release(SharedComm& sc) {
+  if (sc.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(sc.comm);
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (sc.mapped[r]) cudaIpcCloseMemHandle(sc.mapped[r]);
+  if (sc.inbox) cudaFree(sc.inbox);
+  if (sc.d_peer_ptrs) cudaFree(sc.d_peer_ptrs);
+  if (sc.d_seq) cudaFree(sc.d_seq);
+  sc = SharedComm();
+}
+
+// ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
 struct Plan {
@@ -150,8 +178,11 @@ struct edhmc_handle {
   unsigned char** d_peer_ptrs = nullptr;
   void* peer_mapped[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned long long* d_comm_seq = nullptr;
+  unsigned char** own_peer_ptrs = nullptr;    // the handle's own table / counter (single-GPU wide reduction); d_peer_ptrs and
+  unsigned long long* own_comm_seq = nullptr;  // d_comm_seq point at g_shared[device] once peers are attached
   int* d_abort = nullptr;
   bool peers_ready = false;
+  bool shared_comm = false;  // comm / peer tables belong to g_shared[device]
   long long spin_limit = 0;
   // many chains
   int C = 0, mc_nrg = 0, mc_use_tc = 0, mc_Dp = 0;
@@ -197,6 +228,9 @@ static void h_free(edhmc_handle* h, void* p) {
   cudaFree(p);
 }
 
+
+// Shared-memory bank-conflict degree of the row loads for G lanes per row, vectors of V floats, row stride
+// ldx floats: lanes of one LDS phase (32/V lanes) hit bank groups of V words; returns the worst multiplicity.
 static int conflict_degree(long long ldx, int V, int G) {
   const int phase = 32 / V;  // lanes served together by one shared-memory wavefront
   int cnt[32] = {0};
@@ -209,10 +243,10 @@ static int conflict_degree(long long ldx, int V, int G) {
   return worst;
 }
 
-// Ring mode 1 (stream_cta.cuh) for narrow rows: a row fits one lane at <= 64 floats. The row is spread over the fewest
-// lanes (1, 2 or 4, split lane map) that bring the register footprint under 128 so that 16 warps per SM hide the
-// latency of the link function; a stage holds NW * (32/G) * J rows (~1/3 of the shared memory), one bulk copy of X and
-// one of y. Returns false if the shape is not eligible (the caller then plans ring mode 0).
+// Ring mode 1 (stream_cta.cuh) for narrow rows: a row fits one lane at <= 64 floats, ONE lane per row (spreading a row
+// over more lanes to raise the warp count measured slower, see gen_inst.py), warps from the register footprint; a
+// stage holds WPG * 32 * J rows (~1/3 of the shared memory per ring), one bulk copy of X and one of y. Returns false
+// if the shape is not eligible (the caller then plans ring mode 0).
 static bool make_plan_cta(edhmc_handle* h, Plan& out) {
   const edhmc_cfg& c = h->cfg;
   Plan p;
@@ -223,6 +257,10 @@ static bool make_plan_cta(edhmc_handle* h, Plan& out) {
   const int kmax = 64 / p.V;
   const int chunks = (D + p.V - 1) / p.V;
   if (chunks > kmax || ldx > 4096) return false;
+  // one lane per row needs a row stride that spreads the lanes of a wavefront over the banks (any odd multiple of the
+  // vector width does; 64-, 128-, 256-byte strides do not): those shapes keep ring mode 0, which spreads a row over
+  // more lanes instead
+  if (conflict_degree(ldx, p.V, 1) >= 2 && !getenv("EDHMC_FORCE_G")) return false;
   static const int tiers4[] = {1, 2, 3, 4, 5, 6, 7, 8, 12, 16}, tiers2[] = {1, 2, 4, 6, 8, 10, 12, 14, 16, 24, 27, 32},
                    tiers1[] = {1, 2, 4, 8, 16, 28, 32, 64};
   const int* tiers = p.V == 4 ? tiers4 : (p.V == 2 ? tiers2 : tiers1);
@@ -246,7 +284,7 @@ static bool make_plan_cta(edhmc_handle* h, Plan& out) {
     p.G = g;
     p.Kact = kact;
     p.K = k;
-    if (force_g > 0 || warps_for(k * p.V) == 16) break;
+    break;  // one lane per row unless EDHMC_FORCE_G says otherwise
   }
   if (!p.G) return false;
   p.NW = force_nw > 0 ? force_nw : warps_for(p.K * p.V);
@@ -678,6 +716,8 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
       return fail(EDHMC_ERR_NOMEM, "cudaMalloc failed (inbox)");
     }
     own[0] = h->d_inbox;
+    h->own_peer_ptrs = h->d_peer_ptrs;
+    h->own_comm_seq = h->d_comm_seq;
     cudaMemset(h->d_inbox, 0, kInboxBytes);
     cudaMemcpy(h->d_peer_ptrs, own, sizeof(own), cudaMemcpyHostToDevice);
     cudaMemset(h->d_comm_seq, 0, sizeof(unsigned long long));
@@ -705,12 +745,12 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
 int edhmc_destroy(edhmc_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
-  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->comm && !h->shared_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (int r = 0; r < kMaxRanks; ++r)
     if (h->peer_mapped[r]) cudaIpcCloseMemHandle(h->peer_mapped[r]);
   h_free(h, h->d_inbox);
-  h_free(h, h->d_peer_ptrs);
-  h_free(h, h->d_comm_seq);
+  h_free(h, h->own_peer_ptrs);
+  h_free(h, h->own_comm_seq);
   h_free(h, h->d_abort);
   h_free(h, h->d_prior_loc);
   h_free(h, h->d_prior_scale);
@@ -797,10 +837,12 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
   return 0;
 }
 
-static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int gate, long long gsi, cudaStream_t stream) {
+static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int gate, long long gsi, cudaStream_t stream,
+                       int want_lp = 1) {
   KArgs aa = a;
   aa.mode = 1;
   aa.gate = gate;
+  aa.single_lp = want_lp;
   aa.par0 = static_cast<int>(gsi & 1);
   aa.theta_in = theta;
   void* params[] = {&aa};
@@ -888,7 +930,8 @@ int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int
       CUDA_TRY(cudaGetLastError());
       ++h->launches_last;
       for (int s = 0; s < n_steps; ++s) {
-        if ((rc = launch_pass(h, a, h->d_z, 0, (t0 + it) * n_steps + s, stream))) return rc;
+        // the log joint is consumed only after the last leapfrog step (hmc.py:104-105)
+        if ((rc = launch_pass(h, a, h->d_z, 0, (t0 + it) * n_steps + s, stream, s == n_steps - 1 ? 1 : 0))) return rc;
         if ((rc = allreduce_sums(h, stream))) return rc;
         k_chain_leap<<<1, kChainThreads, 0, stream>>>(a, it, s, h->d_g);
         CUDA_TRY(cudaGetLastError());
@@ -960,54 +1003,111 @@ int edhmc_comm_unique_id(void* id128_host) {
   return 0;
 }
 
+int edhmc_comm_cached(int32_t device, int32_t nranks, int32_t rank) {
+  if (device < 0 || device >= 64) return 0;
+  const SharedComm& sc = g_shared[device];
+  if (!sc.comm || sc.nranks != nranks || sc.rank != rank) return 0;
+  return sc.peers_ready ? 2 : 1;
+}
+
+int edhmc_comm_release(int32_t device) {
+  if (device < 0 || device >= 64) return fail(EDHMC_ERR_INVALID, "device out of range");
+  cudaSetDevice(device);
+  shared_release(g_shared[device]);
+  return 0;
+}
+
 int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t rank) {
-  if (!h || !id128_host) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (!h) return fail(EDHMC_ERR_INVALID, "null argument");
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(EDHMC_ERR_INVALID, "bad nranks/rank");
+  if (h->cfg.device >= 64) return fail(EDHMC_ERR_INVALID, "device ordinal too large");
   int rc = nccl_load();
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  NcclUid id;
-  memcpy(&id, id128_host, sizeof(id));
-  NCCL_TRY(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+  SharedComm& sc = g_shared[h->cfg.device];
+  if (!id128_host) {  // reuse the communicator an earlier handle of this process created
+    if (!sc.comm || sc.nranks != nranks || sc.rank != rank)
+      return fail(EDHMC_ERR_STATE, "no cached communicator for device %d with nranks=%d rank=%d", h->cfg.device, nranks, rank);
+  } else {
+    if (sc.comm) shared_release(sc);  // a different world: start over
+    NcclUid id;
+    memcpy(&id, id128_host, sizeof(id));
+    NCCL_TRY(g_nccl.CommInitRank(&sc.comm, nranks, id, rank));
+    sc.nranks = nranks;
+    sc.rank = rank;
+  }
+  h->comm = sc.comm;
+  h->shared_comm = true;
   h->nranks = nranks;
   h->rank = rank;
+  return 0;
+}
+
+static int shared_inbox(SharedComm& sc) {
+  if (sc.inbox) return 0;
+  if (cudaMalloc(&sc.inbox, kInboxBytes) != cudaSuccess || cudaMalloc(&sc.d_peer_ptrs, sizeof(unsigned char*) * kMaxRanks) != cudaSuccess ||
+      cudaMalloc(&sc.d_seq, sizeof(unsigned long long)) != cudaSuccess)
+    return fail(EDHMC_ERR_NOMEM, "cudaMalloc failed (shared inbox)");
+  cudaMemset(sc.inbox, 0, kInboxBytes);
+  cudaMemset(sc.d_seq, 0, sizeof(unsigned long long));
   return 0;
 }
 
 int edhmc_peer_export(edhmc_t* h, void* handle64_host) {
   if (!h || !handle64_host) return fail(EDHMC_ERR_INVALID, "null argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (h->cfg.device >= 64) return fail(EDHMC_ERR_INVALID, "device ordinal too large");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  SharedComm& sc = g_shared[h->cfg.device];
+  if (int rc = shared_inbox(sc)) return rc;
   cudaIpcMemHandle_t ipc;
-  CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->d_inbox));
+  CUDA_TRY(cudaIpcGetMemHandle(&ipc, sc.inbox));
   memcpy(handle64_host, &ipc, sizeof(ipc));
   return 0;
 }
 
 int edhmc_peer_attach(edhmc_t* h, const void* handles_host, int32_t nranks, int32_t rank) {
-  if (!h || !handles_host) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (!h) return fail(EDHMC_ERR_INVALID, "null argument");
   if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks)
     return fail(EDHMC_ERR_INVALID, "peer exchange supports 1..%d ranks, got nranks=%d rank=%d", kMaxRanks, nranks, rank);
   if (h->comm && (nranks != h->nranks || rank != h->rank)) return fail(EDHMC_ERR_INVALID, "nranks/rank differ from edhmc_comm_init");
+  if (h->cfg.device >= 64) return fail(EDHMC_ERR_INVALID, "device ordinal too large");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  unsigned char* ptrs[kMaxRanks] = {nullptr};
-  for (int r = 0; r < nranks; ++r) {
-    if (r == rank) {
-      ptrs[r] = h->d_inbox;
-      continue;
+  SharedComm& sc = g_shared[h->cfg.device];
+  if (!handles_host) {  // reuse the mapping an earlier handle of this process made
+    if (!sc.peers_ready || sc.nranks != nranks || sc.rank != rank)
+      return fail(EDHMC_ERR_STATE, "no cached peer mapping for device %d with nranks=%d rank=%d", h->cfg.device, nranks, rank);
+  } else {
+    if (int rc = shared_inbox(sc)) return rc;
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (sc.mapped[r]) {
+        cudaIpcCloseMemHandle(sc.mapped[r]);
+        sc.mapped[r] = nullptr;
+      }
+    unsigned char* ptrs[kMaxRanks] = {nullptr};
+    for (int r = 0; r < nranks; ++r) {
+      if (r == rank) {
+        ptrs[r] = sc.inbox;
+        continue;
+      }
+      cudaIpcMemHandle_t ipc;
+      memcpy(&ipc, static_cast<const unsigned char*>(handles_host) + 64 * r, sizeof(ipc));
+      void* mapped = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&mapped, ipc, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(EDHMC_ERR_COMM, "cannot map the inbox of rank %d (cudaIpcOpenMemHandle: %s)", r, cudaGetErrorString(e));
+      }
+      sc.mapped[r] = mapped;
+      ptrs[r] = static_cast<unsigned char*>(mapped);
     }
-    cudaIpcMemHandle_t ipc;
-    memcpy(&ipc, static_cast<const unsigned char*>(handles_host) + 64 * r, sizeof(ipc));
-    void* mapped = nullptr;
-    cudaError_t e = cudaIpcOpenMemHandle(&mapped, ipc, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return fail(EDHMC_ERR_COMM, "cannot map the inbox of rank %d (cudaIpcOpenMemHandle: %s)", r, cudaGetErrorString(e));
-    }
-    h->peer_mapped[r] = mapped;
-    ptrs[r] = static_cast<unsigned char*>(mapped);
+    CUDA_TRY(cudaMemcpy(sc.d_peer_ptrs, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
+    sc.nranks = nranks;
+    sc.rank = rank;
+    sc.peers_ready = true;
   }
-  CUDA_TRY(cudaMemcpy(h->d_peer_ptrs, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
+  h->d_peer_ptrs = sc.d_peer_ptrs;
+  h->d_comm_seq = sc.d_seq;
   h->nranks = nranks;
   h->rank = rank;
   h->peers_ready = true;
@@ -1017,6 +1117,9 @@ int edhmc_peer_attach(edhmc_t* h, const void* handles_host, int32_t nranks, int3
 int edhmc_peer_detach(edhmc_t* h) {
   if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
   h->peers_ready = false;
+  h->d_peer_ptrs = h->own_peer_ptrs;
+  h->d_comm_seq = h->own_comm_seq;
+  if (h->cfg.device < 64) g_shared[h->cfg.device].peers_ready = false;
   return 0;
 }
 

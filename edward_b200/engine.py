@@ -106,46 +106,35 @@ class GLMSampler:
 
   # ---- row shards (extension) -----------------------------------------------------------------
   def init_comm(self, nranks: int, rank: int, group=None, peers=None):
-    """Creates the NCCL communicator of this handle; the unique id travels over torch.distributed."""
-    from .sharding import broadcast_bytes
-    buf = (C.c_char * 128)()
-    if rank == 0:
-      _C.check(self.lib.edhmc_comm_unique_id(C.cast(buf, C.c_void_p)))
-    uid = broadcast_bytes(bytes(buf), src=0, group=group)
-    idbuf = C.create_string_buffer(uid, 128)
-    with torch.cuda.device(self.dev):
-      _C.check(self.lib.edhmc_comm_init(self._h, C.cast(idbuf, C.c_void_p), int(nranks), int(rank)))
-    self.nranks = int(nranks)
-    self.peer_exchange = False
+    """Attaches this handle to the process-wide NCCL communicator of its device (created on first use; the unique id
+    travels over torch.distributed) and, unless `peers` is False, to the peer-mapped inboxes of the in-kernel
+    all-reduce. Later samplers of the same process reuse both without any collective call."""
+    from .sharding import allgather_bytes, broadcast_bytes
     if peers is None:
       peers = os.environ.get("EDHMC_COLLECTIVE", "peer") != "nccl"
-    if peers and nranks <= 8:
-      self.peer_exchange = self._attach_peers(nranks, rank, group)
-
-  def _attach_peers(self, nranks, rank, group):
-    """Maps every rank's inbox into this process (cudaIpc) so that edhmc_run can all-reduce the shard totals
-    inside its persistent kernel. If the mapping is impossible on this machine (no peer access between the
-    GPUs), every rank falls back together to the per-pass launch + ncclAllReduce plan — still all on the GPUs."""
-    import sys
-    from .sharding import allgather_bytes
-    hbuf = (C.c_char * 64)()
+    want_peers = bool(peers) and nranks <= 8
+    cached = int(self.lib.edhmc_comm_cached(self.dev.index, int(nranks), int(rank)))  # 0 none, 1 comm, 2 comm + peers
+    # every rank must take the same branch: one small all-gather settles on the lowest level any rank holds
+    level = min(allgather_bytes(bytes([cached]), group=group))
     with torch.cuda.device(self.dev):
-      rc = self.lib.edhmc_peer_export(self._h, C.cast(hbuf, C.c_void_p))
-    table = allgather_bytes(bytes(hbuf) if rc == 0 else b"\0" * 64, group=group)
-    ok = rc == 0
-    if ok:
-      tbuf = C.create_string_buffer(table, 64 * nranks)
-      with torch.cuda.device(self.dev):
-        ok = self.lib.edhmc_peer_attach(self._h, C.cast(tbuf, C.c_void_p), int(nranks), int(rank)) == 0
-    msg = None if ok else self.lib.edhmc_last_error().decode("utf-8", "replace")
-    votes = allgather_bytes(b"\x01" if ok else b"\x00", group=group)
-    all_ok = all(v == 1 for v in votes)
-    if not all_ok:
-      if msg:
-        sys.stderr.write("edhmc: peer exchange unavailable (%s); using ncclAllReduce per pass\n" % msg)
-      with torch.cuda.device(self.dev):
-        _C.check(self.lib.edhmc_peer_detach(self._h))
-    return all_ok
+      if level >= 1:
+        _C.check(self.lib.edhmc_comm_init(self._h, None, int(nranks), int(rank)))
+      else:
+        buf = (C.c_char * 128)()
+        if rank == 0:
+          _C.check(self.lib.edhmc_comm_unique_id(C.cast(buf, C.c_void_p)))
+        uid = broadcast_bytes(bytes(buf), src=0, group=group)
+        idbuf = C.create_string_buffer(uid, 128)
+        _C.check(self.lib.edhmc_comm_init(self._h, C.cast(idbuf, C.c_void_p), int(nranks), int(rank)))
+    self.nranks = int(nranks)
+    self.peer_exchange = False
+    if want_peers:
+      if level >= 2:
+        with torch.cuda.device(self.dev):
+          _C.check(self.lib.edhmc_peer_attach(self._h, None, int(nranks), int(rank)))
+        self.peer_exchange = True
+      else:
+        self.peer_exchange = self._attach_peers(nranks, rank, group)
 
   # ---- evaluation ------------------------------------------------------------------------------
   def logp_grad(self, theta):

@@ -224,7 +224,8 @@ class Variable(Tensor):
   def rebind(self, storage):
     """Adopt device storage (a torch tensor view of the right shape); current contents are copied in."""
     import torch
-    storage.copy_(torch.as_tensor(self._host).to(storage.device, storage.dtype).reshape(storage.shape))
+    cur = self.numpy()  # the CURRENT contents: after an earlier adoption they live on the device, not in _host
+    storage.copy_(torch.as_tensor(np.ascontiguousarray(cur)).to(storage.device, storage.dtype).reshape(storage.shape))
     self._storage = storage
 
   def value_tensor(self):

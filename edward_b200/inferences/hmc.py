@@ -52,53 +52,87 @@ class HMC(MonteCarlo):
                        "this. (if your variables already have unconstrained "
                        "support then doing this is a no-op).")
     import torch
-    from ..engine import GLMSampler
 
     model = recognize(self.latent_vars, self.data)
     self._model = model
     y_val = self.data[model.y_rv]
     if isinstance(y_val, _g.Tensor):
       y_val = _g.evaluate(y_val)
+    self._y_value = y_val
     self._x_value = self._current_x({})
+    self._x_key = self._x_identity(self._x_value)
     dev = self._device
     if dev is None:
       dev = "cuda:%d" % int(os.environ["LOCAL_RANK"]) if "LOCAL_RANK" in os.environ else "cuda"
+    self._dev = dev
+    self._seed_value = None
+    self._sampler = self._make_sampler(self._x_value)
 
-    import torch.distributed as dist
-    sharded = self._row_sharded
-    if sharded is None:
-      sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-    n_global = None
-    if sharded:
-      cnt = torch.tensor([int(np.shape(self._x_value)[0])], dtype=torch.int64,
-                         device=dev if dist.get_backend() == "nccl" else "cpu")
-      dist.all_reduce(cnt)
-      n_global = int(cnt.item())
-
-    self._sampler = GLMSampler(model.spec, self._x_value, y_val, device=dev,
-                               plan=self._plan, debug=self.debug,
-                               n_rows_global=n_global)
-    if sharded:
-      self._sampler.init_comm(dist.get_world_size(), dist.get_rank())
-    seed = get_seed()
-    if seed is not None:
-      self._sampler.seed(seed)
-
-    # Re-home the Empirical stores: one packed [T, P] device buffer, each latent's Variable a view of it.
-    T = self.n_iter
+    # Re-home the Empirical stores: one packed [T_max, P] device buffer, each latent's Variable a view of its own
+    # first rows (the reference allows stores of different lengths; n_iter is the shortest, monte_carlo.py:96-97).
     P = model.spec.n_params
-    self._packed = torch.zeros(T, P, dtype=torch.float32, device=self._sampler.dev)
+    rows_max = self.n_iter
     for slot in model.slots:
       variables = slot.qz.get_variables()
       if not variables:
         raise TypeError("Empirical random variables must be directly parameterized by a tf.Variable "
                         "for HMC to update them (hmc.py:66-70).")
-      var = variables[0]
+      rows_max = max(rows_max, int(variables[0].shape[0]))
+    self._packed = torch.zeros(rows_max, P, dtype=torch.float32, device=self._sampler.dev)
+    for slot in model.slots:
+      var = slot.qz.get_variables()[0]
       rows = int(var.shape[0])
       view = self._packed[:rows, slot.offset] if slot.scalar and len(var.shape) == 1 \
           else self._packed[:rows, slot.offset:slot.offset + slot.size]
       var.rebind(view)
     return self._train
+
+  def _make_sampler(self, x):
+    """Builds the device-side sampler for design matrix `x` with everything build_update decided: device, plan, debug,
+    the global row count and communicator when the rows are sharded, and the Philox seed. Used by build_update and by
+    _maybe_rebind, so that a re-bound sampler keeps the seed and stays one shard of the same global problem."""
+    import torch
+    import torch.distributed as dist
+    from ..engine import GLMSampler
+    from ..util.graphs import sampler_seed
+
+    dev = self._dev
+    sharded = self._row_sharded
+    if sharded is None:
+      sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    n_global = None
+    if sharded:
+      cnt = torch.tensor([int(np.shape(x)[0])], dtype=torch.int64,
+                         device=dev if dist.get_backend() == "nccl" else "cpu")
+      dist.all_reduce(cnt)
+      n_global = int(cnt.item())
+    sampler = GLMSampler(self._model.spec, x, self._y_value, device=dev, plan=self._plan, debug=self.debug,
+                         n_rows_global=n_global)
+    if sharded:
+      sampler.init_comm(dist.get_world_size(), dist.get_rank())
+    if self._seed_value is None:
+      bcast = None
+      if sharded:
+        def bcast(v):
+          box = [v]
+          dist.broadcast_object_list(box, src=0)
+          return box[0]
+      self._seed_value = sampler_seed(bcast)
+    sampler.seed(self._seed_value)
+    return sampler
+
+  @staticmethod
+  def _x_identity(x):
+    """What makes two design matrices 'the same binding': the storage they live in, not the Python object."""
+    try:
+      import torch
+      if isinstance(x, torch.Tensor):
+        return ("torch", x.data_ptr(), tuple(x.shape), str(x.dtype))
+    except ImportError:
+      pass
+    if isinstance(x, np.ndarray):
+      return ("numpy", x.__array_interface__["data"][0], x.shape, str(x.dtype))
+    return ("object", id(x))
 
   def _current_x(self, feed_dict):
     model = self._model
@@ -116,19 +150,22 @@ class HMC(MonteCarlo):
   def _train(self, feed_dict=None):
     """One transition at the current `t` — the op `sess.run(self.train)` executes in the reference."""
     self._maybe_rebind(feed_dict or {})
-    self._sampler.run(self._packed, self._t, 1, self.step_size, self.n_steps)
+    self._sampler.run(self._packed[:self.n_iter], self._t, 1, self.step_size, self.n_steps)
 
   def _maybe_rebind(self, feed_dict):
+    node = self._model.x_node
+    if node is None or not ("Placeholder" in node.op_type or node in feed_dict):
+      return  # X is a Variable / constant / computed node bound at initialize(): nothing can have been re-fed
     x = self._current_x(feed_dict)
-    if x is not self._x_value:
+    key = self._x_identity(x)
+    if key != self._x_key:
       # a different design matrix was fed for the placeholder (monte_carlo.py:134-136): upload it
-      from ..engine import GLMSampler
       old = self._sampler
-      self._x_value = x
-      self._sampler = GLMSampler(self._model.spec, x, old.y, device=old.dev, plan=self._plan, debug=self.debug)
+      self._x_value, self._x_key = x, key
       n_acc, _ = old.read_state()
       self._n_accept_base = getattr(self, "_n_accept_base", 0) + n_acc
       old.close()
+      self._sampler = self._make_sampler(x)
 
   # counters ----------------------------------------------------------------------------------
   def _get_n_accept(self):
@@ -155,12 +192,13 @@ class HMC(MonteCarlo):
       else:
         nxt = min(self.n_iter, (t // self.n_print + 1) * self.n_print)
       self._maybe_rebind({})
-      self._sampler.run(self._packed, t, nxt - t, self.step_size, self.n_steps)
+      self._sampler.run(self._packed[:self.n_iter], t, nxt - t, self.step_size, self.n_steps)
       with np.errstate(divide='ignore', invalid='ignore'):
         accept_rate = np.float64(self._get_n_accept()) / np.float64(nxt - 1) if self.n_print != 0 else None
       t = nxt
       self._t = t
       if self.n_print != 0:
+        self._log_scalars(t)
         self.print_progress({'t': t, 'accept_rate': accept_rate})
     if self.n_print == 0:
       self._sampler.read_state()  # synchronise: run() returns with the samples written
@@ -171,7 +209,7 @@ class HMC(MonteCarlo):
     """The resumable chain state: the Empirical store, the iteration counter, n_accept and the Philox seed.
     Device draws are a pure function of (seed, t, element), so a resumed chain continues bit-identically."""
     return {"params": self._packed.detach().cpu().numpy().copy(), "t": int(self._t),
-            "n_accept": int(self._get_n_accept()), "seed": get_seed(),
+            "n_accept": int(self._get_n_accept()), "seed": self._seed_value,
             "step_size": float(self.step_size), "n_steps": int(self.n_steps)}
 
   def load_state_dict(self, state):
@@ -184,7 +222,8 @@ class HMC(MonteCarlo):
     self._n_accept_base = int(state["n_accept"])
     self._t = int(state["t"])
     if state.get("seed") is not None:
-      self._sampler.seed(int(state["seed"]))
+      self._seed_value = int(state["seed"])
+      self._sampler.seed(self._seed_value)
 
   def finalize(self):
     super(HMC, self).finalize()

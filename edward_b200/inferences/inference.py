@@ -115,11 +115,18 @@ class Inference(abc.ABC):
       del latent_vars
 
     if logdir is not None:
+      # TensorBoard event files, as the reference's tf.summary.FileWriter writes them (inference.py:266-277): scalars
+      # registered by the subclass (MonteCarlo: "n_accept", monte_carlo.py:106-109) and, per log_vars, one
+      # "parameter/<name>" scalar or histogram per variable (inference.py:340-376), every n_print iterations.
       self.logging = True
+      logdir = os.path.expanduser(logdir)
       if log_timestamp:
-        logdir = os.path.join(os.path.expanduser(logdir), datetime.strftime(datetime.utcnow(), "%Y%m%d_%H%M%S"))
+        logdir = os.path.join(logdir, datetime.strftime(datetime.utcnow(), "%Y%m%d_%H%M%S"))
       os.makedirs(logdir, exist_ok=True)
-      self._logfile = open(os.path.join(logdir, "scalars.jsonl"), "w")
+      from torch.utils.tensorboard import SummaryWriter
+      self.logdir = logdir
+      self.train_writer = SummaryWriter(log_dir=logdir)
+      self._set_log_variables(log_vars)
     else:
       self.logging = False
     self.debug = debug
@@ -127,6 +134,41 @@ class Inference(abc.ABC):
 
   def _reset_t(self):
     self._t = 0
+
+  def _set_log_variables(self, log_vars=None):
+    """inference.py:340-376: None = every variable of the data and of the latent variables / their posteriors
+    (for MonteCarlo: the Empirical stores), [] = none."""
+    if log_vars is None:
+      log_vars = []
+      for key, value in self.latent_vars.items():
+        for rv in (key, value):
+          if hasattr(rv, "get_variables"):
+            log_vars += list(rv.get_variables())
+      seen, uniq = set(), []
+      for v in log_vars:
+        if id(v) not in seen:
+          seen.add(id(v))
+          uniq.append(v)
+      log_vars = uniq
+    self._log_vars = list(log_vars)
+
+  def _summary_scalars(self):
+    """Scalars a subclass adds to every summary (name -> value)."""
+    return {}
+
+  def _log_scalars(self, t):
+    """What `sess.run(self.summarize)` + `train_writer.add_summary(summary, t)` do (monte_carlo.py:143-146)."""
+    if not self.logging or self.n_print == 0 or not (t == 1 or t % self.n_print == 0):
+      return
+    for name, value in self._summary_scalars().items():
+      self.train_writer.add_scalar(name, value, global_step=t)
+    for i, var in enumerate(self._log_vars):
+      name = (getattr(var, "name", None) or "Variable_%d" % i).replace(':', '/')
+      val = np.asarray(var.numpy() if hasattr(var, "numpy") else _g.evaluate(var))
+      if val.ndim == 0 or (val.ndim == 1 and val.shape[0] == 1):
+        self.train_writer.add_scalar("parameter/{}".format(name), float(val.reshape(-1)[0]), global_step=t)
+      else:
+        self.train_writer.add_histogram("parameter/{}".format(name), val, global_step=t)
 
   @abc.abstractmethod
   def update(self, feed_dict=None):
@@ -142,4 +184,4 @@ class Inference(abc.ABC):
   def finalize(self):
     """inference.py:334-338."""
     if self.logging:
-      self._logfile.close()
+      self.train_writer.close()

@@ -54,9 +54,12 @@ class MonteCarlo(Inference):
       accept_rate = np.float64(self._get_n_accept()) / np.float64(self._t)
     self._t += 1
     t = self._t
-    if self.logging and self.n_print != 0 and (t == 1 or t % self.n_print == 0):
-      self._logfile.write('{"t": %d, "n_accept": %d}\n' % (t, self._get_n_accept()))
+    self._log_scalars(t)
     return {'t': t, 'accept_rate': accept_rate}
+
+  def _summary_scalars(self):
+    """tf.summary.scalar("n_accept", self.n_accept) — monte_carlo.py:106-109."""
+    return {"n_accept": float(self._get_n_accept())}
 
   def print_progress(self, info_dict):
     """monte_carlo.py:152-158."""

@@ -51,7 +51,7 @@ class _SGMCMC(HMC):
     return train
 
   def _step(self, t, n):
-    self._sampler.sgmcmc_run(self._kind, self._packed, t, n, self.step_size, getattr(self, "friction", 0.0),
+    self._sampler.sgmcmc_run(self._kind, self._packed[:self.n_iter], t, n, self.step_size, getattr(self, "friction", 0.0),
                              self._lik_factor, self._prior_factor, self._velocity, None, self._batch_size)
 
   def _train(self, feed_dict=None):
@@ -74,9 +74,29 @@ class _SGMCMC(HMC):
       t = nxt
       self._t = t
       if self.n_print != 0:
+        self._log_scalars(t)
         self.print_progress({'t': t, 'accept_rate': accept_rate})
     if self.n_print == 0:
       self._sampler.read_state()
+
+  def state_dict(self):
+    """HMC.state_dict plus what the stochastic-gradient samplers carry between iterations: the SGHMC velocity, the
+    friction and the mini-batch size (the batch of iteration t is a function of t, so nothing else is needed)."""
+    state = super(_SGMCMC, self).state_dict()
+    state["velocity"] = self._velocity.detach().cpu().numpy().copy()
+    state["friction"] = float(getattr(self, "friction", 0.0))
+    state["batch_size"] = int(self._batch_size)
+    return state
+
+  def load_state_dict(self, state):
+    import torch
+    super(_SGMCMC, self).load_state_dict(state)
+    if "velocity" in state:
+      self._velocity.copy_(torch.as_tensor(np.asarray(state["velocity"], np.float32)).to(self._velocity.device))
+    if "friction" in state and hasattr(self, "friction"):
+      self.friction = float(state["friction"])
+    if "batch_size" in state:
+      self._batch_size = int(state["batch_size"])
 
 
 class SGLD(_SGMCMC):

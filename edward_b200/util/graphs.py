@@ -21,8 +21,29 @@ def set_seed(x):
 
 
 def get_seed():
-  s = _g.get_default_graph().seed
-  return s if s is not None else _seed
+  """The seed given to ed.set_seed for the CURRENT default graph, or None (as in the reference, where a reset graph is
+  unseeded again: graphs.py:59-73 seeds tf's current default graph)."""
+  return _g.get_default_graph().seed
+
+
+def sampler_seed(rank0_broadcast=None):
+  """64-bit Philox seed for a new sampler. Seeded graph: derived from the user's seed and the number of samplers this
+  graph has seeded so far, so that several inference objects of one seeded program draw different, reproducible
+  streams (the first one keeps the plain seed). Unseeded (the reference's default: random every run): 64 fresh bits
+  from the OS, agreed across ranks through `rank0_broadcast` when the rows are sharded (every rank must draw the same
+  momenta)."""
+  import os
+  seed = get_seed()
+  graph = _g.get_default_graph()
+  k = getattr(graph, "seed_uses", 0)
+  graph.seed_uses = k + 1
+  if seed is not None:
+    x = (int(seed) & (2 ** 64 - 1)) ^ ((k * 0x9E3779B97F4A7C15) & (2 ** 64 - 1))
+    return x if k else int(seed) & (2 ** 64 - 1)  # the first sampler of a seeded program keeps the plain seed
+  fresh = int.from_bytes(os.urandom(8), "little")
+  if rank0_broadcast is not None:
+    fresh = int(rank0_broadcast(fresh))
+  return fresh
 
 
 class _Session(object):

@@ -147,6 +147,14 @@ int edhmc_seed(edhmc_t* h, uint64_t seed);
  * all-reduce (sum, float64) the per-shard [grad, logp] once per data pass over NVLink. */
 int edhmc_comm_unique_id(void* id128_host);
 int edhmc_comm_init(edhmc_t* h, const void* id128_host, int32_t nranks, int32_t rank);
+/* The communicator (and the peer mapping below) belongs to the PROCESS, one per device: the first handle creates it,
+ * later handles of the same (device, nranks, rank) attach to it by passing id128_host == NULL (edhmc_peer_attach:
+ * handles_host == NULL) — ed.HMC builds one handle per inference object and must not pay ncclCommInitRank + cudaIpc
+ * mapping each time. edhmc_comm_cached returns 0 (nothing cached), 1 (communicator) or 2 (communicator + peer
+ * mapping); every rank must take the same branch. Handles that share the peer inboxes continue one exchange sequence:
+ * sharded runs of one process must not overlap in time. edhmc_comm_release frees the cached state of a device. */
+int edhmc_comm_cached(int32_t device, int32_t nranks, int32_t rank);
+int edhmc_comm_release(int32_t device);
 
 /* In-kernel all-reduce over peer memory (NVLink / NVSwitch), used by edhmc_run's persistent plan when rows are
  * sharded: edhmc_peer_export allocates this rank's inbox and returns its 64-byte cudaIpcMemHandle; the caller

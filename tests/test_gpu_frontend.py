@@ -216,3 +216,123 @@ def test_smoke_entry():
   sys.path.insert(0, ROOT)
   import __graft_entry__ as ge
   ge.smoke()
+
+
+def _logreg(ed, tf, Bernoulli, Empirical, Normal, N=400, D=6, T=30, seed=0, x_as="placeholder"):
+  rng = np.random.default_rng(seed)
+  X = rng.standard_normal((N, D)).astype(np.float32)
+  y = (rng.random(N) < 0.5).astype(np.int32)
+  if x_as == "placeholder":
+    xs = tf.placeholder(tf.float32, [N, D])
+    data_x = {xs: X}
+  else:
+    xs = tf.Variable(X)
+    data_x = {}
+  w = Normal(loc=tf.zeros(D), scale=tf.ones(D))
+  yrv = Bernoulli(logits=ed.dot(xs, w))
+  qw = Empirical(params=tf.Variable(tf.zeros([T, D])))
+  data = dict(data_x)
+  data[yrv] = y
+  return X, y, xs, w, yrv, qw, data
+
+
+def test_tensorboard_event_files(tmp_path):
+  """inference.py:266-277, monte_carlo.py:106-109,143-146: logdir gets TensorBoard event files with the `n_accept`
+  scalar and one `parameter/...` histogram per logged variable at t == 1 and every n_print iterations — from update()
+  loops and from run() alike."""
+  from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  for mode in ("run", "update"):
+    from edward_b200 import graph as g
+    g.reset_default_graph()
+    X, y, xs, w, yrv, qw, data = _logreg(ed, tf, Bernoulli, Empirical, Normal)
+    logdir = str(tmp_path / mode)
+    inference = ed.HMC({w: qw}, data=data)
+    if mode == "run":
+      inference.run(step_size=0.01, n_steps=3, n_print=10, logdir=logdir, log_timestamp=False)
+    else:
+      inference.initialize(step_size=0.01, n_steps=3, n_print=10, logdir=logdir, log_timestamp=False)
+      tf.global_variables_initializer().run()
+      for _ in range(inference.n_iter):
+        inference.update()
+      inference.finalize()
+    acc = EventAccumulator(logdir, size_guidance={"scalars": 0, "histograms": 0})
+    acc.Reload()
+    assert "n_accept" in acc.Tags()["scalars"]
+    steps = [e.step for e in acc.Scalars("n_accept")]
+    assert steps == [1, 10, 20, 30], (mode, steps)
+    vals = [e.value for e in acc.Scalars("n_accept")]
+    assert vals == sorted(vals) and vals[-1] == float(inference.n_accept.eval())
+    assert any(t.startswith("parameter/") for t in acc.Tags()["histograms"])
+
+
+def test_unseeded_samplers_draw_different_streams_and_seeded_ones_repeat():
+  """The reference is unseeded and random by default; ed.set_seed makes a program reproducible (graphs.py:59-73)."""
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  from edward_b200 import graph as g
+
+  def chain(seed):
+    g.reset_default_graph()
+    if seed is not None:
+      ed.set_seed(seed)
+    X, y, xs, w, yrv, qw, data = _logreg(ed, tf, Bernoulli, Empirical, Normal, T=8)
+    inference = ed.HMC({w: qw}, data=data)
+    inference.run(step_size=0.02, n_steps=3, n_print=0)
+    return qw.params.eval().copy()
+
+  a, b = chain(None), chain(None)
+  assert not np.array_equal(a, b)  # two unseeded runs of one process differ
+  c, d = chain(7), chain(7)
+  np.testing.assert_array_equal(c, d)
+  assert not np.array_equal(c, chain(8))
+
+
+def test_variable_design_matrix_is_not_rebound_and_fed_matrix_is():
+  """X held in a tf.Variable must not trigger a re-bind (the chain keeps its seed and state); feeding a
+  different matrix for a placeholder re-binds through the same factory (seed kept)."""
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  ed.set_seed(3)
+  X, y, xs, w, yrv, qw, data = _logreg(ed, tf, Bernoulli, Empirical, Normal, T=6, x_as="variable")
+  inference = ed.HMC({w: qw}, data=data)
+  inference.initialize(step_size=0.02, n_steps=2, n_print=0)
+  tf.global_variables_initializer().run()
+  first = inference._sampler
+  for _ in range(6):
+    inference.update()
+  assert inference._sampler is first
+  from edward_b200 import graph as g
+  g.reset_default_graph()
+  ed.set_seed(3)
+  X, y, xs, w, yrv, qw, data = _logreg(ed, tf, Bernoulli, Empirical, Normal, T=6)
+  inference = ed.HMC({w: qw}, data=data)
+  inference.initialize(step_size=0.02, n_steps=2, n_print=0)
+  tf.global_variables_initializer().run()
+  inference.update()
+  s0, seed0 = inference._sampler, inference._seed_value
+  inference.update(feed_dict={xs: X})       # same storage: no re-bind
+  assert inference._sampler is s0
+  inference.update(feed_dict={xs: X.copy()})  # another buffer: re-bind, same seed
+  assert inference._sampler is not s0 and inference._seed_value == seed0
+  assert int(inference.t.eval()) == 3
+
+
+def test_empirical_stores_of_different_lengths():
+  """monte_carlo.py:96-97: n_iter is the shortest store; longer stores keep their extra rows untouched."""
+  ed, tf, Bernoulli, Empirical, Normal = _imports()
+  rng = np.random.default_rng(0)
+  N = 60
+  Xd = rng.standard_normal((N, 1)).astype(np.float32)
+  yd = (rng.random(N) < 0.5).astype(np.int32)
+  xs = tf.placeholder(tf.float32, [N, 1])
+  w = Normal(loc=tf.zeros(1), scale=3.0 * tf.ones(1))
+  b = Normal(loc=tf.zeros([]), scale=3.0 * tf.ones([]))
+  yrv = Bernoulli(logits=ed.dot(xs, w) + b)
+  qw = Empirical(params=tf.Variable(tf.zeros([12, 1])))
+  qb = Empirical(params=tf.Variable(7.0 * tf.ones([20])))
+  inference = ed.HMC({w: qw, b: qb}, data={xs: Xd, yrv: yd})
+  inference.run(step_size=0.3, n_steps=2, n_print=0)
+  assert inference.n_iter == 12 and int(inference.t.eval()) == 12
+  pb = qb.params.eval()
+  assert pb.shape == (20,) and np.all(pb[12:] == 7.0) and not np.all(pb[:12] == 7.0)
+  with pytest.raises(IndexError):
+    inference.update()

@@ -94,3 +94,42 @@ def test_sgld_minibatch_front_end_with_scale():
   for _ in range(200):  # posterior mode by gradient ascent on the oracle
     z = z + 2e-4 * o.grad_log_joint(X_train, y_train, z, spec)
   assert np.max(np.abs(est - z)) < 0.15, (est, z)
+
+
+def test_sghmc_checkpoint_resume_is_bit_identical():
+  """the SGHMC velocity is part of the resumable state."""
+  import edward_b200 as ed
+  from edward_b200 import graph as g
+  from edward_b200 import tfshim as tf
+  from edward_b200.models import Bernoulli, Empirical, Normal
+
+  def build(T):
+    g.reset_default_graph()
+    ed.set_seed(5)
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((256, 5)).astype(np.float32)
+    y = (rng.random(256) < 0.5).astype(np.int32)
+    xs = tf.placeholder(tf.float32, [256, 5])
+    w = Normal(loc=tf.zeros(5), scale=tf.ones(5))
+    yrv = Bernoulli(logits=ed.dot(xs, w))
+    qw = Empirical(params=tf.Variable(tf.zeros([T, 5])))
+    inf = ed.SGHMC({w: qw}, data={xs: X, yrv: y})
+    inf.initialize(step_size=0.05, friction=0.2, n_print=0)
+    tf.global_variables_initializer().run()
+    return inf, qw
+
+  T = 20
+  full, qfull = build(T)
+  for _ in range(T):
+    full.update()
+  want = qfull.params.eval().copy()
+  a, qa = build(T)
+  for _ in range(9):
+    a.update()
+  state = a.state_dict()
+  assert "velocity" in state and np.any(state["velocity"] != 0)
+  b, qb = build(T)
+  b.load_state_dict(state)
+  for _ in range(T - 9):
+    b.update()
+  np.testing.assert_array_equal(qb.params.eval(), want)
