@@ -17,6 +17,14 @@ leapfrog steps of one chain over the whole (synthetic, resident) design matrix.
 `value` times edhmc_run with CUDA events on the launching stream, inputs resident in HBM, L2 flushed
 between steps. `e2e` times the public call chain ed.HMC(...).run() from pinned host arrays, including
 the H2D copy of X and y and the D2H read of the samples. One JSON line on stdout (rank 0).
+
+Beside the contract keys the line carries: `roofline` (HBM copy peak from MEASURED_PEAKS.json; `l2_peak` / `hbm_read_peak`
+= read throughput of an L2-resident 100 MB buffer and of a 2 GiB buffer measured in this run with edhmc_probe_read),
+`timeline` (per-pass clock64 stamps of the persistent kernel, medians over CTAs and passes), `parity_check` (the run's
+own results against a float64 torch evaluation on the same device data; at N>1 also that every rank holds the same
+chain), `chains` (cfg 3 on the N=1 line, cfg 5 on the N=8 line: the vectorised-chain tensor-core paths), `cfg1` (the
+reference example as shipped, transitions/s), and the same-workload scaling references (`scale_series_n1` at N=1,
+`n1_same_workload` + `efficiency_same_workload` at N>1, timed over the same number of steps).
 """
 from __future__ import annotations
 
@@ -54,6 +62,8 @@ def parse():
   ap.add_argument("--rows", type=int, default=None, help="override the row count (debugging)")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-extras", action="store_true", help="skip the chains / cfg1 / probe / timeline / parity blocks")
+  ap.add_argument("--scale-steps", type=int, default=None, help="steps of the same-workload scaling reference (default min(steps, 5))")
   return ap.parse_args()
 
 
@@ -217,29 +227,170 @@ def run_reference(args, wl, wl_key):
   print(json.dumps(line))
 
 
-def tf32_peak():
-  p = os.path.join(ROOT, "profiles", "r01_tf32_peak.json")
-  if os.path.exists(p):
-    with open(p) as f:
-      return float(json.load(f)["tf32_tflops"]), "measured on this pool (profiles/r01_tf32_peak.json, tools/tf32_peak.py)"
+def tf32_peak(torch=None, dev=None):
+  """Dense TF32 GEMM throughput of this GPU (the tensor roofline denominator; 3xTF32 executes 3 MMA flops per
+  algorithmic flop): measured in this run with the protocol of MEASURED_PEAKS.json (torch.matmul 8192^3, best of 10)
+  when a device is given, else the figure recorded in profiles/."""
+  if torch is not None:
+    try:
+      old = torch.backends.cuda.matmul.allow_tf32
+      torch.backends.cuda.matmul.allow_tf32 = True
+      n = 8192
+      a = torch.randn(n, n, device=dev)
+      b = torch.randn(n, n, device=dev)
+      for _ in range(3):
+        a @ b
+      torch.cuda.synchronize(dev)
+      best = None
+      for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+      torch.backends.cuda.matmul.allow_tf32 = old
+      del a, b
+      return 2.0 * n ** 3 / best / 1e9, "measured in this run (torch.matmul TF32 8192^3, best of 10)"
+    except Exception:  # noqa: BLE001
+      pass
+  for name in ("r02_tf32_peak.json", "r01_tf32_peak.json"):
+    p = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(p):
+      with open(p) as f:
+        return float(json.load(f)["tf32_tflops"]), "measured on this pool (profiles/%s, tools/tf32_peak.py)" % name
   return 1100.0, "nominal dense TF32 (no measurement available)"
 
 
-def run_chains(args, wl):
-  """cfg 3: C vectorised chains on one GPU, tensor-core bound. value = chain leapfrog steps/s."""
-  import torch
-  import torch.distributed as dist
-  from edward_b200 import engine
-  rank = int(os.environ.get("RANK", "0"))
-  world = int(os.environ.get("WORLD_SIZE", "1"))
-  dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-  torch.cuda.set_device(dev)
+def read_peaks(torch, dev):
+  """Read throughput of an L2-resident buffer (100 MB, re-read in place) and of an HBM-sized one (2 GiB) with
+  edhmc_probe_read, best of 5 launches timed with CUDA events; LDG.128 and TMA bulk-copy paths, the better one counts."""
+  from edward_b200 import _C
+  lib = _C.lib()
+  out = {}
+  st = torch.cuda.current_stream(dev).cuda_stream
+  sink = torch.zeros(4, dtype=torch.float32, device=dev)
+  for key, nbytes, iters in (("l2", 100 * 1000 * 1000 // 32768 * 32768, 100), ("hbm_read", 2 * 1024 ** 3, 4)):
+    buf = torch.ones(nbytes // 4, dtype=torch.float32, device=dev)
+    best = 0.0
+    for mode in (0, 1):
+      _C.check(lib.edhmc_probe_read(buf.data_ptr(), nbytes, 2, mode, sink.data_ptr(), st))
+      torch.cuda.synchronize(dev)
+      for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _C.check(lib.edhmc_probe_read(buf.data_ptr(), nbytes, iters, mode, sink.data_ptr(), st))
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = max(best, nbytes * iters / e0.elapsed_time(e1) / 1e6)
+    out[key] = best
+    del buf
+  return out
+
+
+def timeline_of(torch, s, run_once, n_passes=48):
+  """Medians (over CTAs and steady-state passes) of the persistent kernel's per-pass stamps, in SM cycles."""
+  import numpy as np
+  tl = s.set_timeline(n_passes)
+  run_once()
+  torch.cuda.synchronize()
+  t = tl.cpu().numpy().astype(np.int64)[8:n_passes]
+  s.set_timeline(0)
+  if t.shape[0] < 4 or not np.any(t[:, :, 1]):
+    return None
+  wait = t[:, :, 8:16]
+  d = {
+      "unit": "SM cycles (clock64), median over CTAs and passes 8..%d of one launch" % (n_passes - 1),
+      "pass_tiles_and_cta_reduce": float(np.median(t[:, :, 1] - t[:, :, 0])),
+      "publish_partials": float(np.median(t[:, :, 2] - t[:, :, 1])),
+      "grid_barrier_wait_median": float(np.median(t[:, :, 3] - t[:, :, 2])),
+      "grid_barrier_wait_fastest_cta": float(np.median((t[:, :, 3] - t[:, :, 2]).min(axis=1))),
+      "grid_barrier_wait_slowest_cta": float(np.median((t[:, :, 3] - t[:, :, 2]).max(axis=1))),
+      "totals_ready_after_barrier": float(np.median(t[:, :, 4] - t[:, :, 3])),
+      "integrator": float(np.median(t[:, :, 5] - t[:, :, 4])),
+      "serial_section": float(np.median(t[:, :, 5] - t[:, :, 1])),
+      "step": float(np.median(t[1:, :, 0] - t[:-1, :, 0])),
+      "step_ns_globaltimer": float(np.median(t[1:, 0, 6] - t[:-1, 0, 6])),
+      "tile_wait_per_warp": float(np.median(wait[wait > 0])) if np.any(wait > 0) else 0.0,
+  }
+  d["serial_fraction_of_step"] = d["serial_section"] / d["step"] if d["step"] > 0 else None
+  return d
+
+
+def float64_logp_grad(torch, X, y, theta, world, dist):
+  """log joint (Normal(0,1) priors) and gradient of the Bernoulli-logit model in float64 on the device data of this
+  rank, summed over ranks: an evaluation independent of libedhmc (plain torch ops, 65,536-row chunks)."""
+  th = theta.double()
+  D = X.shape[1]
+  g = torch.zeros(D, dtype=torch.float64, device=X.device)
+  ll = torch.zeros((), dtype=torch.float64, device=X.device)
+  for lo in range(0, X.shape[0], 65536):
+    xb = X[lo:lo + 65536].double()
+    yb = y[lo:lo + 65536].double()
+    eta = xb @ th
+    ll += (yb * eta - torch.nn.functional.softplus(eta)).sum()
+    g += xb.t() @ (yb - torch.sigmoid(eta))
+  pack = torch.cat([g, ll.reshape(1)])
   if world > 1:
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", device_id=dev)
+    dist.all_reduce(pack)
+  g, ll = pack[:D], pack[D]
+  lp = ll + (-0.5 * th * th).sum() - D * 0.9189385332046727
+  return float(lp), g - th
+
+
+def parity_check(torch, s, X, y, params, world, rank, dist):
+  """After the timed region: (1) log joint and gradient of the handle at theta = 0 and at a random theta against the
+  float64 torch evaluation (1e-5 relative); (2) every rank holds bit-identical samples (N>1)."""
+  D = X.shape[1]
+  gen = torch.Generator(device=X.device).manual_seed(99)
+  out = {"tolerance": 1e-5, "checks": []}
+  ok = True
+  for name, th in (("zero", torch.zeros(D, device=X.device)),
+                   ("random", torch.randn(D, device=X.device, generator=gen) / D ** 0.5)):
+    lp, g = s.logp_grad(th)
+    lp64, g64 = float64_logp_grad(torch, X, y, th, world, dist)
+    e_lp = abs(float(lp[0]) - lp64) / abs(lp64)
+    e_g = float((g.double() - g64).abs().max() / g64.abs().max())
+    out["checks"].append({"theta": name, "logp_rel_err": e_lp, "grad_rel_err": e_g})
+    ok = ok and e_lp <= 1e-5 and e_g <= 1e-5
+  if world > 1:
+    h = params.view(torch.int32).to(torch.int64)
+    sig = torch.stack([h.sum(), (h * torch.arange(1, h.numel() + 1, device=h.device).reshape(h.shape)).sum()])
+    sigs = [torch.zeros_like(sig) for _ in range(world)]
+    dist.all_gather(sigs, sig)
+    same = all(bool(torch.equal(sigs[0], q)) for q in sigs)
+    out["ranks_hold_identical_samples"] = same
+    ok = ok and same
+  out["samples_finite"] = bool(torch.isfinite(params).all())
+  out["ok"] = bool(ok and out["samples_finite"])
+  return out
+
+
+def time_single_chain(torch, s, params, T, eps, L, steps, warmup, flush, barrier):
+  """W warm-up + K timed steps of edhmc_run (CUDA events on the launching stream, L2 flushed between steps)."""
+  def one_step():
+    if flush is not None:
+      flush.fill_(1.0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s.run(params, 0, T, eps, L)
+    e1.record()
+    return e0, e1
+  for _ in range(warmup):
+    one_step()
+  barrier()
+  evs = [one_step() for _ in range(steps)]
+  barrier()
+  return sum(a.elapsed_time(b) for a, b in evs)
+
+
+def bench_chains(torch, dist, args, wl, dev, world, rank, steps, with_e2e=True, cpu_single=None):
+  """Vectorised chains (cfg 3 on one GPU, cfg 5 row-sharded): value = chain leapfrog steps/s, tensor roofline."""
+  from edward_b200 import engine
   n_loc, D, T, L, C = wl["N"], wl["D"], wl["T"], wl["L"], wl["C"]
   N = n_loc * world if world > 1 else n_loc  # rows are per GPU for the sharded workload (weak scaling)
-  r_lo, r_hi = shard_bounds(N, world, rank)  # block-aligned shards: the data do not depend on the world size
+  r_lo, r_hi = shard_bounds(N, world, rank)
   X, y = gen_device_rows(torch, dev, r_lo, r_hi - r_lo, D)
   s = engine.GLMSampler(engine.GLMSpec(D), X, y, device=dev, n_chains=C, n_rows_global=N)
   if world > 1:
@@ -247,16 +398,17 @@ def run_chains(args, wl):
   s.seed(1234)
   params = torch.zeros(T, C, D, device=dev)
   flush = torch.empty(512 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
-  for _ in range(max(args.warmup, 3)):
+  for _ in range(3):
     s.run_chains(params, 0, T, 0.5 / N, L)
   torch.cuda.synchronize(dev)
   if world > 1:
     dist.barrier()
     torch.cuda.synchronize(dev)
-  sampler = ClockSampler(dev.index)
-  sampler.start()
+  sampler = ClockSampler(dev.index) if rank == 0 else None
+  if sampler:
+    sampler.start()
   evs = []
-  for _ in range(args.steps):
+  for _ in range(steps):
     flush.fill_(1.0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -267,16 +419,15 @@ def run_chains(args, wl):
   if world > 1:
     dist.barrier()
     torch.cuda.synchronize(dev)
-  clocks = sampler.stop()
+  clocks = sampler.stop() if sampler else None
   ms = sum(a.elapsed_time(b) for a, b in evs)
   per_rank_ms, allreduce_us = None, None
   if world > 1:
     mine = torch.tensor([ms], dtype=torch.float64, device=dev)
     gathered = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(gathered, mine)
-    per_rank_ms = [float(g.item()) / args.steps for g in gathered]
+    per_rank_ms = [float(g.item()) / steps for g in gathered]
     ms = max(float(g.item()) for g in gathered)
-    # the collective alone, same payload as one leapfrog step ([grad, logp] of all chains, float64)
     buf = torch.zeros(C * (D + 1), dtype=torch.float64, device=dev)
     for _ in range(3):
       dist.all_reduce(buf)
@@ -289,32 +440,115 @@ def run_chains(args, wl):
     torch.cuda.synchronize(dev)
     allreduce_us = a0.elapsed_time(a1) * 100.0
   info = s.plan_info()
+  # parity spot check: chains 0, C/2, C-1 of one gradient evaluation against the float64 torch evaluation
+  gen = torch.Generator(device=dev).manual_seed(5)
+  th = torch.randn(C, D, device=dev, generator=gen) / D ** 0.5
+  lpc, gc = s.logp_grad_chains(th)
+  worst_lp = worst_g = 0.0
+  for c in (0, C // 2, C - 1):
+    lp64, g64 = float64_logp_grad(torch, X, y, th[c], world, dist)
+    worst_lp = max(worst_lp, abs(float(lpc[c]) - lp64) / abs(lp64))
+    worst_g = max(worst_g, float((gc[c].double() - g64).abs().max() / g64.abs().max()))
+  parity = {"chains_checked": [0, C // 2, C - 1], "logp_rel_err": worst_lp, "grad_rel_err": worst_g, "tolerance": 1e-5,
+            "ok": bool(worst_lp <= 1e-5 and worst_g <= 1e-5)}
+  # end to end through the public chains call: pinned host arrays -> GLMSampler(n_chains=C).run_chains -> samples on the host
+  e2e = None
+  if with_e2e and world == 1:
+    Xh = torch.empty(X.shape, dtype=X.dtype, pin_memory=True)
+    Xh.copy_(X)
+    yh = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+    yh.copy_(y)
+    times = []
+    for i in range(4):
+      flush.fill_(1.0)
+      torch.cuda.synchronize(dev)
+      t0 = time.perf_counter()
+      s2 = engine.GLMSampler(engine.GLMSpec(D), Xh, yh, device=dev, n_chains=C)
+      s2.seed(1234)
+      p2 = torch.zeros(T, C, D, device=dev)
+      s2.run_chains(p2, 0, T, 0.5 / N, L)
+      host = p2.cpu()
+      dt = time.perf_counter() - t0
+      if i > 0:
+        times.append(dt)
+      assert host.shape == (T, C, D)
+      s2.close()
+    e2e = {"value": 3 * C * T * L / sum(times), "unit": "chain leapfrog steps/s", "h2d_bytes_per_step": Xh.numel() * 4 + yh.numel() * 4,
+           "d2h_bytes_per_step": T * C * D * 4, "steps": 3,
+           "call": "engine.GLMSampler(spec, pinned host X, y, n_chains=C).run_chains(params, 0, T, step_size, n_steps) + params.cpu() "
+                   "(includes the one-off re-lay of X into the tensor-core operand layout)"}
+    del Xh, yh
+  s.close()
+  del X, y, flush
+  torch.cuda.empty_cache()
   if rank != 0:
-    dist.destroy_process_group()
-    return
-  steps = args.steps * T * L
-  alg = 4.0 * (float(N) / world) * D * C * steps / (ms * 1e-3) / 1e12  # per GPU (mean shard)
-  peak, src = tf32_peak()
+    return None
+  nsteps = steps * T * L
+  alg = 4.0 * (float(N) / world) * D * C * nsteps / (ms * 1e-3) / 1e12  # per GPU (mean shard)
+  peak, src = tf32_peak(torch, dev)
   wide = D > 64
-  line = {
-      "metric": "hmc_leapfrog_steps_per_s", "value": C * steps / (ms * 1e-3), "unit": "chain leapfrog steps/s", "n_gpus": world,
-      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-      "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 accumulate)", "data": "synthetic",
-      "config": {"workload": wl["name"], "rows": N, "rows_per_gpu": n_loc, "features": D, "chains": C, "transitions_per_step": T,
-                 "leapfrog_per_transition": L, "l2": "L2 flushed between steps", "rng": "device Philox",
+  cpu = None
+  if cpu_single is not None:
+    cpu = {"value": cpu_single["value"], "unit": "chain leapfrog steps/s", "cores": cpu_single["cores"], "kind": "port",
+           "sample": "C independent chains cost C single-chain runs on the CPU port, so its chain-steps/s equal the "
+                     "single-chain figure measured in this run (" + cpu_single["sample"][:120] + " ...)"}
+  return {
+      "workload": wl["name"], "metric": "hmc_chain_leapfrog_steps_per_s", "value": C * nsteps / (ms * 1e-3), "unit": "chain leapfrog steps/s",
+      "n_gpus": world, "steps": steps, "ms_per_step": ms / steps, "scaling": "weak", "dtype": "tf32x3 (fp32 accumulate)",
+      "config": {"rows": N, "rows_per_gpu": n_loc, "features": D, "chains": C, "transitions_per_step": T, "leapfrog_per_transition": L,
+                 "l2": "L2 flushed between steps", "rng": "device Philox",
                  "parallelism": "rows sharded over %d GPUs, ncclAllReduce of [grad, logp] (%d float64) per leapfrog step" % (world, C * (D + 1)) if world > 1 else "1 GPU"},
-      "leapfrog_steps_of_all_chains_per_s": steps / (ms * 1e-3),
-      "rows_steps_per_s": float(N) * C * steps / (ms * 1e-3),
+      "leapfrog_steps_of_all_chains_per_s": nsteps / (ms * 1e-3), "rows_steps_per_s": float(N) * C * nsteps / (ms * 1e-3),
       "per_rank_ms_per_step": per_rank_ms, "allreduce_us_same_payload": allreduce_us,
-      "rows_per_rank": [shard_bounds(N, world, q)[1] - shard_bounds(N, world, q)[0] for q in range(world)],
       "roofline": {"bound": "tensor", "achieved": 3.0 * alg, "peak": peak, "unit": "TFLOP/s", "frac": 3.0 * alg / peak,
                    "traffic": None, "peak_source": src, "algorithmic_tflops": alg,
                    "kernel": ("edhmc::k_mcw_gemm<1> + k_mcw_gemm<2>" if wide else "edhmc::k_mc_pass_tc3") + " (3xTF32: 3 executed MMA flops per algorithmic flop); per GPU"},
-      "cpu_baseline": None, "e2e": None, "gpu_launches": info["launches_last_run"] * args.steps, "clocks": clocks,
+      "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": info["launches_last_run"] * steps, "clocks": clocks, "parity_check": parity,
   }
-  print(json.dumps(line))
+
+
+def run_chains(args, wl):
+  """--workload cfg3 / cfg5 as the headline of the line (development runs; the driver's lines carry them as `chains`)."""
+  import torch
+  import torch.distributed as dist
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+  torch.cuda.set_device(dev)
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+  blk = bench_chains(torch, dist, args, wl, dev, world, rank, args.steps)
+  if rank == 0:
+    line = dict(blk)
+    line["metric"] = "hmc_leapfrog_steps_per_s"
+    line.update({"warmup": 3, "higher_is_better": True, "vs_baseline": None, "data": "synthetic"})
+    line["config"] = dict(blk["config"], workload=blk["workload"])
+    print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
+
+
+def bench_cfg1():
+  """BASELINE config 1: the reference's example script as shipped (tools/run_reference_example.py) — 5,000 update()
+  calls with a progress line and a posterior-predictive evaluation every 10 iterations; launch-latency bound."""
+  try:
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import run_reference_example as rre
+    script = rre.find_script()
+    import contextlib
+    import io
+    if script is None:
+      return {"unavailable": "the reference example is not staged under baseline/_ref (run __graft_entry__.build() where /root/reference exists)"}
+    with contextlib.redirect_stdout(io.StringIO()):
+      rre.run(["--T", "300"], script)  # warm-up: first launch, allocator
+      r = rre.run([], script)
+    return {"workload": "cfg1: examples/bayesian_logistic_regression.py as shipped (N=40, D=1 + bias, T=5000, step_size=0.6, n_steps=2), "
+                        "update() loop with print_progress and a 50-draw posterior-predictive evaluation every 10 iterations",
+            "script": "reference file executed unchanged through module aliases (tools/run_reference_example.py)",
+            "transitions_per_s": r["transitions_per_s"], "seconds": r["seconds"], "transitions": r["t"], "n_accept": r["n_accept"]}
+  except Exception as e:  # noqa: BLE001
+    return {"error": str(e)[:200]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -346,6 +580,8 @@ def main():
   if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
+  extras = not args.no_extras and not args.rows
+  warmup = max(args.warmup, 3)
 
   N, D, T, L = wl["N"], wl["D"], wl["T"], wl["L"]
   eps = 0.5 / N
@@ -364,27 +600,19 @@ def main():
       dist.barrier()
     torch.cuda.synchronize(dev)
 
-  def one_step(timed):
-    flush.fill_(1.0)  # flush L2 between steps (outside the timed events)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+  # ---- the timed region: W warm-up steps, then exactly K steps between barriers; device time, max over ranks ----
+  for _ in range(warmup):
+    flush.fill_(1.0)
     s.run(params, 0, T, eps, L)
-    e1.record()
-    return e0, e1
-
-  for _ in range(max(args.warmup, 3)):
-    one_step(False)
   barrier()
   sampler = ClockSampler(local_rank) if rank == 0 else None
   if sampler:
     sampler.start()
   barrier()
   wall0 = time.perf_counter()
-  evs = [one_step(True) for _ in range(args.steps)]
-  barrier()
+  dev_ms = time_single_chain(torch, s, params, T, eps, L, args.steps, 0, flush, barrier)
   wall = time.perf_counter() - wall0
   clocks = sampler.stop() if sampler else None
-  dev_ms = sum(a.elapsed_time(b) for a, b in evs)
   t_ms = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
   if world > 1:
     dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -395,8 +623,26 @@ def main():
   value = steps_total / (dev_ms * 1e-3)
   launches = info["launches_last_run"] * args.steps
 
-  # ---- strong-scaling reference: the same workload on rank 0 alone (only when sharded) ----
+  # ---- parity self-check on the data and handle that were just timed ----
+  parity = parity_check(torch, s, X, y, params, world, rank, dist) if extras or world > 1 else None
+
+  # ---- per-pass timeline of the persistent kernel (one extra launch, outside the timed region) ----
+  timeline = None
+  if (extras or world > 1) and info["plan_in_use"] == 1:
+    try:
+      tl = timeline_of(torch, s, lambda: s.run(params, 0, T, eps, L))
+      if world > 1:
+        box = [None] * world
+        dist.all_gather_object(box, tl)
+        timeline = {"per_rank": box}
+      else:
+        timeline = tl
+    except Exception as e:  # noqa: BLE001
+      timeline = {"error": str(e)[:200]}
+
+  # ---- strong-scaling reference: the same workload on rank 0 alone, same number of steps (only when sharded) ----
   n1_same = None
+  scale_steps = args.scale_steps or min(args.steps, 5)
   if world > 1:
     if rank == 0:
       try:
@@ -404,20 +650,11 @@ def main():
         s1 = engine.GLMSampler(engine.GLMSpec(D), X1, y1, device=dev)
         s1.seed(1234)
         p1 = torch.zeros(T, D, device=dev)
-        s1.run(p1, 0, T, eps, L)
-        torch.cuda.synchronize(dev)
-        ms1 = 0.0
-        for _ in range(1):
-          flush.fill_(1.0)
-          a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-          a.record()
-          s1.run(p1, 0, T, eps, L)
-          b.record()
-          torch.cuda.synchronize(dev)
-          ms1 += a.elapsed_time(b)
-        n1_same = {"value": 1 * T * L / (ms1 * 1e-3), "unit": "leapfrog steps/s", "plan": "persistent, 1 GPU, same job"}
+        ms1 = time_single_chain(torch, s1, p1, T, eps, L, scale_steps, 1, flush, lambda: torch.cuda.synchronize(dev))
+        n1_same = {"value": scale_steps * T * L / (ms1 * 1e-3), "unit": "leapfrog steps/s", "steps": scale_steps, "warmup": 1,
+                   "ms_per_step": ms1 / scale_steps, "plan": "persistent, 1 GPU (rank 0 alone), same job, same data"}
         s1.close()
-        del X1, y1
+        del X1, y1, p1
       except Exception as e:  # noqa: BLE001
         n1_same = {"error": str(e)[:200]}
     dist.barrier()
@@ -434,7 +671,7 @@ def main():
     Xh.copy_(X)
     yh = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
     yh.copy_(y)
-    e2e_steps = max(3, min(args.steps, 20)) if world == 1 else 2
+    e2e_steps = max(3, min(args.steps, 20)) if world == 1 else max(2, min(args.steps, 4))
     times = []
     h2d = Xh.numel() * 4 + yh.numel() * 4
     d2h = T * D * 4 + 16
@@ -465,40 +702,66 @@ def main():
       inference._sampler.close()
       del inference, qbeta
     e2e = {"value": e2e_steps * T * L / sum(times), "unit": "leapfrog steps/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps, "seconds_per_step": sum(times) / e2e_steps,
            "call": "ed.HMC({beta: qbeta}, data={X: pinned host array%s, y: ...}).run(step_size, n_steps) + qbeta.params.eval()"
                    % (" (this rank's row shard; bytes are per rank)" if world > 1 else "")}
     del Xh, yh
 
-  # ---- the N=1 point of the row-sharded scaling series (cfg 4 on this GPU alone), so that the scale-out lines
-  #      (--gpus 2/4/8 run cfg 4) have their single-GPU reference from the same protocol ----
+  peaks = None
+  if extras and world == 1:
+    try:
+      peaks = read_peaks(torch, dev)
+    except Exception as e:  # noqa: BLE001
+      peaks = {"error": str(e)[:200]}
+  s.close()
+  del X, y, flush, params
+  torch.cuda.empty_cache()
+
+  # ---- CPU baseline (rank 0, N=1): the reference's schedule in C/OpenMP on a bounded sample ----
+  cpu = None
+  if world == 1 and rank == 0 and not args.no_cpu_baseline:
+    rows_cap = N if wl_key == "cfg2" else N // 64
+    probe, nrows, threads = time_reference(wl, 1, rows_cap)
+    n_tr = int(max(2, min(60, 12.0 / max(probe * nrows / N, 1e-3))))
+    dt, nrows, threads = time_reference(wl, n_tr, rows_cap)
+    cpu = {"value": n_tr * L / dt, "unit": "leapfrog steps/s", "cores": threads, "kind": "port",
+           "sample": "%d transitions x (L+1 gradient + 2 forward evaluations, CheckNumerics on) on %d of %d rows%s; "
+                     "C/OpenMP restatement of the reference's TensorFlow schedule (oracle/hmc_ref.c), host has %d logical CPUs"
+                     % (n_tr, nrows, N, "" if nrows == N else ", time scaled linearly", os.cpu_count())}
+
+  # ---- vectorised chains: cfg 3 on the N=1 line, cfg 5 on the N=8 line ----
+  chains = None
+  if extras and wl_key in ("cfg2", "cfg4"):
+    try:
+      if world == 1 and wl_key == "cfg2":
+        chains = bench_chains(torch, dist, args, dict(WORKLOADS["cfg3"]), dev, 1, 0, max(3, min(args.steps, 10)), cpu_single=cpu)
+      elif world == 8:
+        chains = bench_chains(torch, dist, args, dict(WORKLOADS["cfg5"]), dev, world, rank, max(2, min(args.steps, 5)))
+    except Exception as e:  # noqa: BLE001
+      chains = {"error": str(e)[:300]}
+
+  # ---- the N=1 point of the row-sharded scaling series (cfg 4 on this GPU alone) ----
   scale_n1 = None
   if world == 1 and wl_key == "cfg2" and not args.no_scale_ref and not args.rows:
     try:
       w4 = WORKLOADS["cfg4"]
-      del flush
-      torch.cuda.empty_cache()
       X4, y4 = gen_device_rows(torch, dev, 0, w4["N"], w4["D"])
       s4 = engine.GLMSampler(engine.GLMSpec(w4["D"]), X4, y4, device=dev)
       s4.seed(1234)
       p4 = torch.zeros(w4["T"], w4["D"], device=dev)
-      s4.run(p4, 0, w4["T"], 0.5 / w4["N"], w4["L"])
-      torch.cuda.synchronize(dev)
-      ms4 = 0.0
-      for _ in range(1):
-        a4, b4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a4.record()
-        s4.run(p4, 0, w4["T"], 0.5 / w4["N"], w4["L"])
-        b4.record()
-        torch.cuda.synchronize(dev)
-        ms4 += a4.elapsed_time(b4)
-      v4 = 1 * w4["T"] * w4["L"] / (ms4 * 1e-3)
-      scale_n1 = {"workload": w4["name"], "value": v4, "unit": "leapfrog steps/s",
-                  "hbm_frac": (4.0 * w4["N"] * w4["D"] + 4.0 * w4["N"]) * v4 / 1e9 / measured_peaks()[0]}
+      ms4 = time_single_chain(torch, s4, p4, w4["T"], 0.5 / w4["N"], w4["L"], scale_steps, 1, None, lambda: torch.cuda.synchronize(dev))
+      v4 = scale_steps * w4["T"] * w4["L"] / (ms4 * 1e-3)
+      scale_n1 = {"workload": w4["name"], "value": v4, "unit": "leapfrog steps/s", "steps": scale_steps, "warmup": 1,
+                  "ms_per_step": ms4 / scale_steps,
+                  "hbm_frac": (4.0 * w4["N"] * w4["D"] + 4.0 * w4["N"]) * v4 / 1e9 / measured_peaks()[0],
+                  "note": "X (40 GB) is far larger than L2: every leapfrog step streams it from HBM"}
       s4.close()
-      del X4, y4
+      del X4, y4, p4
+      torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
       scale_n1 = {"error": str(e)[:200]}
+
+  cfg1 = bench_cfg1() if (extras and world == 1 and rank == 0 and wl_key == "cfg2") else None
 
   if rank != 0:
     if world > 1:
@@ -509,35 +772,36 @@ def main():
   alg_bytes_step = 4.0 * (r_hi - r_lo) * D + 4.0 * (r_hi - r_lo)  # this rank's shard: X once + y once per leapfrog step
   launch_ms = dev_ms / args.steps if info["plan_in_use"] == 1 else None
   achieved = alg_bytes_step * T * L / (dev_ms / args.steps * 1e-3) / 1e9
-  traffic = None
+  traffic, traffic_src = None, None
   try:
     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
       tj = json.load(f)
     if wl_key in tj and info["plan_in_use"] == 1 and not args.rows:
       traffic = tj[wl_key]["bytes_per_launch"]
+      traffic_src = "static capture: %s (ncu --set full of the same launch; not measured in this run)" % tj[wl_key]["source"]
   except Exception:
     pass
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-              "traffic": traffic, "peak_source": peak_src,
+              "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
               "kernel": "edhmc::k_hmc (one persistent launch = T*L passes)" if info["plan_in_use"] == 1
               else "edhmc::k_hmc mode 1 (one pass per launch) + NCCL all-reduce + chain kernels",
               "algorithmic_bytes_per_launch": alg_bytes_step * T * L if info["plan_in_use"] == 1 else alg_bytes_step,
               "launch_ms": launch_ms}
-
-  cpu = None
-  if world == 1 and not args.no_cpu_baseline:
-    rows_cap = N if wl_key == "cfg2" else N // 64
-    probe, nrows, threads = time_reference(wl, 1, rows_cap)
-    n_tr = int(max(2, min(60, 12.0 / max(probe * nrows / N, 1e-3))))
-    dt, nrows, threads = time_reference(wl, n_tr, rows_cap)
-    cpu = {"value": n_tr * L / dt, "unit": "leapfrog steps/s", "cores": threads, "kind": "port",
-           "sample": "%d transitions x (L+1 gradient + 2 forward evaluations, CheckNumerics on) on %d of %d rows%s; "
-                     "C/OpenMP restatement of the reference's TensorFlow schedule (oracle/hmc_ref.c), host has %d logical CPUs"
-                     % (n_tr, nrows, N, "" if nrows == N else ", time scaled linearly", os.cpu_count())}
+  if peaks and "l2" in peaks:
+    x_mb = 4e-6 * (r_hi - r_lo) * (D + 1)
+    roofline.update({
+        "l2_peak": peaks["l2"], "l2_frac": achieved / peaks["l2"], "hbm_read_peak": peaks["hbm_read"],
+        "hbm_read_frac": achieved / peaks["hbm_read"],
+        "peaks_measured_here": "edhmc_probe_read, best of LDG.128 / TMA bulk paths, best of 5 launches: 100 MB re-read in place "
+                               "(L2-resident) and 2 GiB (HBM)",
+        "residency": "the pass re-reads %.1f MB per leapfrog step; the L2 holds 126 MB, so most of it is served from L2 "
+                     "(DRAM traffic %s of the algorithmic bytes) and `frac` above 1 is against the HBM COPY peak, not a "
+                     "bandwidth bound: the pass is bound by per-row latency at 8 warps per SM (profiles/README round 2)"
+                     % (x_mb, ("%.0f %%" % (100.0 * traffic / roofline["algorithmic_bytes_per_launch"])) if traffic else "a fraction")})
 
   line = {
       "metric": "hmc_leapfrog_steps_per_s", "value": value, "unit": "leapfrog steps/s", "n_gpus": world,
-      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+      "steps": args.steps, "warmup": warmup, "ms_per_step": dev_ms / args.steps,
       "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
       "data": "synthetic",
       "config": {"workload": wl["name"], "rows": N, "features": D, "transitions_per_step": T, "leapfrog_per_transition": L,
@@ -545,15 +809,27 @@ def main():
                  "parallelism": ("rows sharded over %d GPUs, %s" % (world, "one persistent launch per GPU, in-kernel all-reduce of [grad, logp] through peer inboxes over NVLink each leapfrog step"
                                   if info["plan_in_use"] == 1 else "NCCL all-reduce per leapfrog step")) if world > 1 else "1 GPU",
                  "l2": "L2 flushed between steps (512 MiB write); within a step X (%.1f MB) is re-streamed every leapfrog step" % (4e-6 * (r_hi - r_lo) * D),
-                 "rng": "device Philox", "grid_ctas": info["grid_ctas"], "ring_stages": info["ring_stages"], "tile_rows": info["tile_rows"]},
+                 "rng": "device Philox", "grid_ctas": info["grid_ctas"], "ring_stages": info["ring_stages"], "tile_rows": info["tile_rows"],
+                 "ring_mode": info.get("ring_mode"), "warps_per_cta": info["warps_per_cta"]},
       "rows_steps_per_s": value * N,
       "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
       "clocks": clocks, "n_accept_total": n_accept, "wall_s": wall,
   }
+  if parity is not None:
+    line["parity_check"] = parity
+  if timeline is not None:
+    line["timeline"] = timeline
   if n1_same is not None:
     line["n1_same_workload"] = n1_same
+    if "value" in n1_same:
+      line["efficiency_same_workload"] = value / (world * n1_same["value"])
+      line["speedup_same_workload"] = value / n1_same["value"]
   if scale_n1 is not None:
     line["scale_series_n1"] = scale_n1
+  if chains is not None:
+    line["chains"] = chains
+  if cfg1 is not None:
+    line["cfg1"] = cfg1
   print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
