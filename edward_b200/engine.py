@@ -136,6 +136,31 @@ class GLMSampler:
       else:
         self.peer_exchange = self._attach_peers(nranks, rank, group)
 
+  def _attach_peers(self, nranks, rank, group):
+    """Maps every rank's inbox into this process (cudaIpc) so that edhmc_run can all-reduce the shard totals
+    inside its persistent kernel. If the mapping is impossible on this machine (no peer access between the
+    GPUs), every rank falls back together to the per-pass launch + ncclAllReduce plan — still all on the GPUs."""
+    import sys
+    from .sharding import allgather_bytes
+    hbuf = (C.c_char * 64)()
+    with torch.cuda.device(self.dev):
+      rc = self.lib.edhmc_peer_export(self._h, C.cast(hbuf, C.c_void_p))
+    table = allgather_bytes(bytes(hbuf) if rc == 0 else b"\0" * 64, group=group)
+    ok = rc == 0
+    if ok:
+      tbuf = C.create_string_buffer(table, 64 * nranks)
+      with torch.cuda.device(self.dev):
+        ok = self.lib.edhmc_peer_attach(self._h, C.cast(tbuf, C.c_void_p), int(nranks), int(rank)) == 0
+    msg = None if ok else self.lib.edhmc_last_error().decode("utf-8", "replace")
+    votes = allgather_bytes(b"\x01" if ok else b"\x00", group=group)
+    all_ok = all(v == 1 for v in votes)
+    if not all_ok:
+      if msg:
+        sys.stderr.write("edhmc: peer exchange unavailable (%s); using ncclAllReduce per pass\n" % msg)
+      with torch.cuda.device(self.dev):
+        _C.check(self.lib.edhmc_peer_detach(self._h))
+    return all_ok
+
   # ---- evaluation ------------------------------------------------------------------------------
   def logp_grad(self, theta):
     """log p(y, theta) (float64 scalar tensor) and its gradient (float32 [P]) — hmc.py:161-192,199."""
