@@ -1,6 +1,6 @@
 // chains.cu — many vectorised HMC chains over one design matrix (see chains.cuh).
 //
-//   k_mc_pass_tc      the dense contraction on the 5th-generation tensor cores, hand-written tcgen05:
+//   k_mc_pass_tc3     the dense contraction on the 5th-generation tensor cores, hand-written tcgen05:
 //                       Sᵀ[chain, row] = Wᵀ·Xᵀ      tcgen05.mma kind::tf32, A = Wᵀ (smem), B = X tile (smem),
 //                                                    accumulator in TMEM (chains on lanes, rows on columns)
 //                       R = y − σ(Sᵀ)                epilogue: tcgen05.ld → CUDA cores → tcgen05.st (R stays in TMEM)
@@ -76,639 +76,15 @@ __global__ void __launch_bounds__(kMcChainsPerCta, 1) k_mc_pass_simple(const McA
         if (d < D) g[d] = fmaf(rv, xs[m][d], g[d]);
     }
   }
-  float* pg = a.part_g + (static_cast<size_t>(blockIdx.x) * a.C + c) * a.Dp;
+  double* pg = a.part_g + static_cast<size_t>(blockIdx.x) * a.Dp * a.C + c;  // [row group][feature][chain]
 #pragma unroll
   for (int d = 0; d < kMcMaxD; ++d)
-    if (d < a.Dp) pg[d] = d < D ? g[d] : 0.0f;
+    if (d < a.Dp) pg[static_cast<size_t>(d) * a.C] = d < D ? static_cast<double>(g[d]) : 0.0;
   a.part_lp[static_cast<size_t>(blockIdx.x) * a.C + c] = lp;
 }
 
-// ------------------------------------------------------------------------------------------------
-// tensor-core pass. grid (n_rowgroups, C/128), block 256 (8 warps), one CTA per SM.
-// Shared memory (dynamic), all operand tiles in the no-swizzle K-major core-matrix layout:
-//   raw   [128][ldx] f32      the X tile as it lies in HBM (one TMA bulk copy)
-//   A1h/l [Dp/4][128][4]      Wᵀ block: off(c,d) = (d/4)*2048 + c*16 + (d%4)*4          (M=128 chains, K=Dp)
-//   B1h/l [Dp/4][128][4]      X tile:   off(m,d) = (d/4)*2048 + m*16 + (d%4)*4          (N=128 rows,   K=Dp)
-//   B2h/l [128/4][64][4]      X tileᵀ:  off(d,m) = (m/4)*1024 + d*16 + (m%4)*4          (N=64 feats,   K=128 rows)
-// TMEM (512 columns allocated): [0,128) Sᵀ then R_hi in place, [128,256) R_lo, [256,320) G' accumulator.
-// ------------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 256;
-constexpr int kTcN2 = 64;
-
-__host__ __device__ inline int tc_smem_layout(int Dp, int ldx, int* off /*8*/) {
-  int o = 0;
-  off[0] = o;  // raw
-  o += kMcTileRows * ldx * 4;
-  o = (o + 127) / 128 * 128;
-  off[1] = o;  // ys
-  o += kMcTileRows * 4;
-  off[2] = o;  // A1 hi, lo
-  o += 2 * (Dp / 4) * 2048;
-  off[3] = o;  // B1 hi, lo
-  o += 2 * (Dp / 4) * 2048;
-  off[4] = o;  // B2 hi, lo
-  o += 2 * (kMcTileRows / 4) * 1024;
-  off[5] = o;  // mbarriers (3) + tmem address
-  o += 64;
-  off[6] = o;  // logp combine [2][128] doubles
-  o += 2 * 128 * 8;
-  return o;
-}
-
-__global__ void __launch_bounds__(kTcThreads, 1) k_mc_pass_tc(const McArgs a, const float* theta, int gate) {
-  if (gate && !*a.need_init) return;
-  extern __shared__ __align__(128) unsigned char smem[];
-  int off[8];
-  const int ldx = static_cast<int>(a.ldx);
-  const int Dp = a.Dp, D = a.D;
-  tc_smem_layout(Dp, ldx, off);
-  float* raw = reinterpret_cast<float*>(smem + off[0]);
-  float* ys = reinterpret_cast<float*>(smem + off[1]);
-  unsigned char* A1 = smem + off[2];
-  unsigned char* B1 = smem + off[3];
-  unsigned char* B2 = smem + off[4];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off[5]);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off[5] + 32);
-  double* lpc = reinterpret_cast<double*>(smem + off[6]);
-  const int kc1 = Dp / 4;
-  const int a1_half = kc1 * 2048, b2_half = (kMcTileRows / 4) * 1024;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int cb = blockIdx.y * kMcChainsPerCta;  // first chain of this CTA
-  const uint32_t bar_raw = smem_u32(&bars[0]), bar_m1 = smem_u32(&bars[1]), bar_m2 = smem_u32(&bars[2]);
-
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
-  // A1 = Wᵀ block, split hi/lo: item (c, kc) → 16 bytes
-  for (int i = tid; i < kMcChainsPerCta * kc1; i += kTcThreads) {
-    const int c = i % kMcChainsPerCta, kc = i / kMcChainsPerCta;
-    float4 h, l;
-    float* hp = &h.x;
-    float* lp_ = &l.x;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int d = kc * 4 + e;
-      const float v = d < D ? theta[static_cast<size_t>(cb + c) * D + d] : 0.0f;
-      split_tf32(v, hp[e], lp_[e]);
-    }
-    *reinterpret_cast<float4*>(A1 + kc * 2048 + c * 16) = h;
-    *reinterpret_cast<float4*>(A1 + a1_half + kc * 2048 + c * 16) = l;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tm = *tmem_slot;
-  const uint32_t tm_s = tm, tm_lo = tm + 128, tm_g = tm + 256;
-
-  long long t0, t1;
-  tile_range(a.n_rows, a.n_rowgroups, blockIdx.x, t0, t1);
-  const int ntiles = static_cast<int>(t1 - t0);
-  const uint32_t id1 = idesc_tf32(128, 128), id2 = idesc_tf32(128, kTcN2);
-  const int q = warp & 3, hf = warp >> 2;  // TMEM lane quadrant (chains 32q..), column half (tile rows 64hf..)
-  double lp = 0.0;
-
-  // raw tile loader: one TMA bulk copy (full tiles) or cooperative plain loads (the ragged last tile of X)
-  auto load_raw = [&](int it) {
-    const long long row0 = (t0 + it) * kMcTileRows;
-    const long long left = a.n_rows - row0;
-    const int rows = left < kMcTileRows ? static_cast<int>(left) : kMcTileRows;
-    if (rows == kMcTileRows) {
-      if (tid == 0) {
-        const uint32_t bytes = kMcTileRows * ldx * 4;
-        fence_proxy_async_smem();
-        mbar_arrive_expect_tx_s(bar_raw, bytes);
-        bulk_g2s_s(smem_u32(raw), a.X + row0 * a.ldx, bytes, bar_raw);
-      }
-    } else {
-      for (int i = tid; i < rows * ldx; i += kTcThreads) {
-        const int m = i / ldx, d = i - m * ldx;
-        raw[i] = d < D ? a.X[(row0 + m) * a.ldx + d] : 0.0f;
-      }
-      __syncthreads();
-      if (tid == 0) mbar_arrive(&bars[0]);
-    }
-  };
-
-  if (ntiles > 0) load_raw(0);
-  for (int it = 0; it < ntiles; ++it) {
-    const uint32_t par = it & 1;
-    const long long row0 = (t0 + it) * kMcTileRows;
-    const long long left = a.n_rows - row0;
-    const int rows = left < kMcTileRows ? static_cast<int>(left) : kMcTileRows;
-    // MMA2 of the previous tile must be done before B1/B2/S are overwritten
-    if (it > 0) mbar_wait_s(bar_m2, (it - 1) & 1);
-    mbar_wait_s(bar_raw, par);
-    if (tid < kMcTileRows) ys[tid] = tid < rows ? ld_y(a.y, a.y_dtype, row0 + tid) : 0.0f;
-    // ---- build B1 (rows x K=Dp) and B2 (feats x K=rows), hi/lo ----
-    for (int i = tid; i < kMcTileRows * kc1; i += kTcThreads) {
-      const int m = i % kMcTileRows, kc = i / kMcTileRows;
-      float4 h, l;
-      float* hp = &h.x;
-      float* lq = &l.x;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int d = kc * 4 + e;
-        const float v = (m < rows && d < D) ? raw[m * ldx + d] : 0.0f;
-        split_tf32(v, hp[e], lq[e]);
-      }
-      *reinterpret_cast<float4*>(B1 + kc * 2048 + m * 16) = h;
-      *reinterpret_cast<float4*>(B1 + a1_half + kc * 2048 + m * 16) = l;
-    }
-    for (int i = tid; i < kTcN2 * (kMcTileRows / 4); i += kTcThreads) {
-      const int d = i % kTcN2, mc = i / kTcN2;
-      float4 h, l;
-      float* hp = &h.x;
-      float* lq = &l.x;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int m = mc * 4 + e;
-        const float v = (m < rows && d < D) ? raw[m * ldx + d] : 0.0f;
-        split_tf32(v, hp[e], lq[e]);
-      }
-      *reinterpret_cast<float4*>(B2 + mc * 1024 + d * 16) = h;
-      *reinterpret_cast<float4*>(B2 + b2_half + mc * 1024 + d * 16) = l;
-    }
-    fence_proxy_async_smem();  // generic-proxy writes of the operand tiles → visible to the tensor core (async proxy)
-    __syncthreads();
-    // raw is consumed: prefetch the next tile while the tensor core and the epilogue work
-    if (it + 1 < ntiles) load_raw(it + 1);
-
-    // ---- MMA1: Sᵀ[128 chains x 128 rows] = Wᵀ·Xᵀ, K = Dp, 3xTF32 ----
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t a_h = smem_u32(A1), a_l = a_h + a1_half, b_h = smem_u32(B1), b_l = b_h + a1_half;
-      for (int ks = 0; ks < Dp / 8; ++ks) {
-        const uint32_t o = ks * 4096;  // 2 core matrices along K per MMA (K = 8 tf32)
-        tc_mma_ss(tm_s, smem_desc(a_h + o, 2048, 128), smem_desc(b_h + o, 2048, 128), id1, ks > 0);
-        tc_mma_ss(tm_s, smem_desc(a_h + o, 2048, 128), smem_desc(b_l + o, 2048, 128), id1, 1);
-        tc_mma_ss(tm_s, smem_desc(a_l + o, 2048, 128), smem_desc(b_h + o, 2048, 128), id1, 1);
-      }
-      tc_commit(bar_m1);
-    }
-    mbar_wait_s(bar_m1, par);
-    tc_fence_after();
-
-    // ---- epilogue: R = dlogp/deta, written back to TMEM as the A operand of MMA2 (hi in place, lo beside) ----
-    {
-      const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int col = hf * 64 + cc * 16;
-        uint32_t v[16], vh[16], vl[16];
-        tmem_ld16(tm_s + lane_base + col, v);
-        tmem_wait_ld();
-        if (a.want_logp || a.family != 0) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = col + j;
-            float lpv, rv;
-            row_terms(a.family, __uint_as_float(v[j]), ys[m], a.lik_scale, lpv, rv);
-            if (m >= rows) {
-              lpv = 0.0f;
-              rv = 0.0f;
-            }
-            lp += static_cast<double>(lpv);
-            float h, l;
-            split_tf32(rv, h, l);
-            vh[j] = __float_as_uint(h);
-            vl[j] = __float_as_uint(l);
-          }
-        } else {
-          // inside a trajectory only the residual y - sigmoid(eta) is needed (the log joint enters the
-          // Metropolis–Hastings ratio at the trajectory's end only): one exp and one reciprocal per element
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = col + j;
-            const float eta = __uint_as_float(v[j]);
-            const float e = expf(-fabsf(eta));
-            const float qv = __fdividef(e, 1.0f + e);
-            const float yv = ys[m];
-            float rv = eta >= 0.0f ? (yv - 1.0f) + qv : yv - qv;
-            if (m >= rows) rv = 0.0f;
-            float h, l;
-            split_tf32(rv, h, l);
-            vh[j] = __float_as_uint(h);
-            vl[j] = __float_as_uint(l);
-          }
-        }
-        tmem_st16(tm_s + lane_base + col, vh);
-        tmem_st16(tm_lo + lane_base + col, vl);
-      }
-      tmem_wait_st();
-    }
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- MMA2: G'[128 chains x 64 feats] += R·X, K = 128 rows, A from TMEM, 3xTF32 ----
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t b_h = smem_u32(B2), b_l = b_h + b2_half;
-      for (int ks = 0; ks < kMcTileRows / 8; ++ks) {
-        const uint32_t o = ks * 2048;
-        tc_mma_ts(tm_g, tm_s + ks * 8, smem_desc(b_h + o, 1024, 128), id2, (it > 0 || ks > 0));
-        tc_mma_ts(tm_g, tm_s + ks * 8, smem_desc(b_l + o, 1024, 128), id2, 1);
-        tc_mma_ts(tm_g, tm_lo + ks * 8, smem_desc(b_h + o, 1024, 128), id2, 1);
-      }
-      tc_commit(bar_m2);
-    }
-  }
-
-  // ---- write this row group's partial sums ----
-  if (ntiles > 0) {
-    mbar_wait_s(bar_m2, (ntiles - 1) & 1);
-    tc_fence_after();
-  }
-  {
-    const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
-    const int chain = cb + 32 * q + lane;
-    float* pg = a.part_g + (static_cast<size_t>(blockIdx.x) * a.C + chain) * Dp;
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col = hf * 32 + cc * 16;
-      uint32_t v[16];
-      if (ntiles > 0) {
-        tmem_ld16(tm_g + lane_base + col, v);
-        tmem_wait_ld();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0u;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (col + j < Dp) pg[col + j] = __uint_as_float(v[j]);
-    }
-    lpc[hf * 128 + 32 * q + lane] = lp;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (tid < kMcChainsPerCta) a.part_lp[static_cast<size_t>(blockIdx.x) * a.C + cb + tid] = lpc[tid] + lpc[128 + tid];
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tm, 512);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Pipelined tensor-core pass (default). Same mathematics as k_mc_pass_tc, restructured so that the tensor
-// pipe, the operand builders and the epilogue work on different tiles at the same time:
-//   warp 0      control: TMA bulk loads of the raw X tiles + MMA1 issue (one thread); warp 13: MMA2 issue
-//   warps 1-4   builders: raw tile → B1 (rows x K=Dp) and B2 (feats x K=rows) operand tiles, hi/lo split
-//   warps 5-12  epilogue: Sᵀ (TMEM) → residual R (TMEM, hi in place + lo), log-likelihood
-// 64-row tiles, every per-tile resource double-buffered (b = tile & 1):
-//   TMEM  S[b] 64 cols at 64*b, R_lo[b] 64 cols at 128+64*b, G' 64 cols at 256   (512 allocated)
-//   mbarriers  raw_full[b] (TMA) → b_ready[b] (128 builder arrivals) → s_ready[b] (tcgen05.commit after MMA1)
-//              → r_ready[b] (256 epilogue arrivals) → mma2_done[b] (tcgen05.commit after MMA2, frees B[b])
-// MMA1(i+2) may overwrite S[b] only after MMA2(i) has read R[b]: b_ready[b](i+2) implies it, because the
-// builders wait for mma2_done[b](i) before they rebuild B[b].
-// ------------------------------------------------------------------------------------------------
-#define MC_DBG(slot) do { if (dbgp && i < 64) dbgp[i * 16 + (slot)] = clock64(); } while (0)
-constexpr int kT2Rows = 64;
-constexpr int kT2Threads = 14 * 32;  // control/MMA1, 4 builders, 8 epilogue, MMA2 issuer
-constexpr int kT2Builders = 128;
-constexpr int kT2Epilogue = 256;
-
-__host__ __device__ inline int tc2_smem_layout(int Dp, int ldx, int* off /*8*/) {
-  int o = 0;
-  off[0] = o;  // raw[2] (also reused for the final logp combine)
-  const int raw_bytes = (kT2Rows * ldx * 4 + 32 + 127) / 128 * 128;  // + slack: masked over-read of the last row
-  o += 2 * raw_bytes;
-  off[1] = o;  // ys[2][64]
-  o += 2 * kT2Rows * 4;
-  off[2] = o;  // A1 hi, lo
-  o += 2 * (Dp / 4) * 2048;
-  off[3] = o;  // B1[2] {hi, lo}
-  o += 2 * 2 * (Dp / 4) * 1024;
-  off[4] = o;  // B2[2] {hi, lo}
-  o += 2 * 2 * (kT2Rows / 4) * 1024;
-  off[5] = o;  // 10 mbarriers + tmem slot
-  o += 128;
-  off[6] = raw_bytes;
-  return o;
-}
-
-__global__ void __launch_bounds__(kT2Threads, 1) k_mc_pass_tc2(const McArgs a, const float* theta, int gate) {
-  if (gate && !*a.need_init) return;
-  extern __shared__ __align__(128) unsigned char smem[];
-  int off[8];
-  const int ldx = static_cast<int>(a.ldx);
-  const int Dp = a.Dp, D = a.D;
-  tc2_smem_layout(Dp, ldx, off);
-  const int raw_bytes = off[6];
-  unsigned char* raw0 = smem + off[0];
-  float* ysm = reinterpret_cast<float*>(smem + off[1]);
-  unsigned char* A1 = smem + off[2];
-  unsigned char* B1 = smem + off[3];
-  unsigned char* B2 = smem + off[4];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off[5]);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off[5] + 96);
-  const int kc1 = Dp / 4;
-  const int a1_half = kc1 * 2048;
-  const int b1_half = kc1 * 1024, b1_buf = 2 * b1_half;
-  const int b2_half = (kT2Rows / 4) * 1024, b2_buf = 2 * b2_half;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int cb = blockIdx.y * kMcChainsPerCta;
-  // barrier indices: 0,1 raw_full  2,3 b_ready  4,5 s_ready  6,7 r_ready  8,9 mma2_done
-  const uint32_t bar0 = smem_u32(bars);
-  auto BAR = [&](int kind, int b) { return bar0 + static_cast<uint32_t>((kind * 2 + b) * 8); };
-
-  if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bars[0 + b], 1);
-      mbar_init(&bars[2 + b], kT2Builders);
-      mbar_init(&bars[4 + b], 1);
-      mbar_init(&bars[6 + b], kT2Epilogue);
-      mbar_init(&bars[8 + b], 1);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
-  for (int i = tid; i < kMcChainsPerCta * kc1; i += kT2Threads) {
-    const int c = i % kMcChainsPerCta, kc = i / kMcChainsPerCta;
-    float4 h, l;
-    float* hp = &h.x;
-    float* lq = &l.x;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int d = kc * 4 + e;
-      const float v = d < D ? theta[static_cast<size_t>(cb + c) * D + d] : 0.0f;
-      split_tf32(v, hp[e], lq[e]);
-    }
-    *reinterpret_cast<float4*>(A1 + kc * 2048 + c * 16) = h;
-    *reinterpret_cast<float4*>(A1 + a1_half + kc * 2048 + c * 16) = l;
-  }
-  for (int i = tid; i < 2 * b2_buf / 16; i += kT2Threads) reinterpret_cast<float4*>(B2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tm = *tmem_slot;
-  const uint32_t tm_g = tm + 256;
-
-  // this row group's tiles of 64 rows (two per 128-row unit of the shared partition)
-  long long u0, u1;
-  tile_range(a.n_rows, a.n_rowgroups, blockIdx.x, u0, u1);
-  const long long row_begin = u0 * kMcTileRows;
-  long long row_end = u1 * kMcTileRows;
-  if (row_end > a.n_rows) row_end = a.n_rows;
-  const int nt = row_end > row_begin ? static_cast<int>((row_end - row_begin + kT2Rows - 1) / kT2Rows) : 0;
-  const uint32_t id12 = idesc_tf32(128, kT2Rows);  // MMA1: N = 64 rows;  MMA2: N = 64 features
-  double lp = 0.0;
-  long long* dbgp = (a.dbg && !a.want_logp && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? a.dbg : nullptr;
-
-  if (warp == 0) {
-    // ================= control warp: TMA loads of raw tiles + MMA1 issue =================
-    // The whole warp runs the loop (converged); one elected lane issues. Descriptors are built once; per
-    // k-step only the 14-bit start-address field moves (+bytes/16).
-    auto issue_raw = [&](int i) {
-      const long long r0 = row_begin + static_cast<long long>(i) * kT2Rows;
-      if (row_end - r0 >= kT2Rows) {
-        if (elect_one()) {
-          const int b = i & 1;
-          const uint32_t bytes = kT2Rows * ldx * 4;
-          fence_proxy_async_smem();
-          mbar_arrive_expect_tx_s(BAR(0, b), bytes);
-          bulk_g2s_s(smem_u32(raw0 + b * raw_bytes), a.X + r0 * a.ldx, bytes, BAR(0, b));
-        }
-        __syncwarp();
-      }
-    };
-    for (int i = 0; i < nt && i < 2; ++i) issue_raw(i);
-    const uint64_t da_h = smem_desc(smem_u32(A1), 2048, 128), da_l = smem_desc(smem_u32(A1) + a1_half, 2048, 128);
-    const uint64_t db_h0 = smem_desc(smem_u32(B1), 1024, 128), db_l0 = smem_desc(smem_u32(B1) + b1_half, 1024, 128);
-    const int nks = Dp / 8;
-    for (int i = 0; i < nt; ++i) {
-      const int b = i & 1;
-      const uint32_t par = (i >> 1) & 1;
-      mbar_wait_s(BAR(1, b), par);  // b_ready: operand tiles built, raw[b] consumed
-      MC_DBG(0);
-      if (i + 2 < nt) issue_raw(i + 2);
-      tc_fence_after();
-      const uint64_t db_h = db_h0 + static_cast<uint64_t>((b * b1_buf) >> 4), db_l = db_l0 + static_cast<uint64_t>((b * b1_buf) >> 4);
-      const uint32_t ts = tm + 64 * b;
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // Sᵀ[b] = Wᵀ·X(i)ᵀ, K = Dp = 8*nks
-          if (ks < nks) {
-            const uint64_t oa = static_cast<uint64_t>(ks * (4096 >> 4)), ob = static_cast<uint64_t>(ks * (2048 >> 4));
-            tc_mma_ss(ts, da_h + oa, db_h + ob, id12, ks > 0);
-            tc_mma_ss(ts, da_h + oa, db_l + ob, id12, 1);
-            tc_mma_ss(ts, da_l + oa, db_h + ob, id12, 1);
-          }
-        }
-        tc_commit(BAR(2, b));  // s_ready[b]
-      }
-      __syncwarp();
-      MC_DBG(1);
-    }
-  } else if (warp == 13) {
-    // ================= MMA2 issuer warp: G' += R(i)·X(i), A = R from TMEM =================
-    const uint64_t d2_h0 = smem_desc(smem_u32(B2), 1024, 128), d2_l0 = smem_desc(smem_u32(B2) + b2_half, 1024, 128);
-    for (int i = 0; i < nt; ++i) {
-      const int b = i & 1;
-      mbar_wait_s(BAR(3, b), (i >> 1) & 1);  // r_ready[b]
-      MC_DBG(2);
-      tc_fence_after();
-      const uint64_t d2_h = d2_h0 + static_cast<uint64_t>((b * b2_buf) >> 4), d2_l = d2_l0 + static_cast<uint64_t>((b * b2_buf) >> 4);
-      const uint32_t r_h = tm + 64 * b, r_l = tm + 128 + 64 * b;
-      const uint32_t first = (i > 0) ? 1u : 0u;
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < kT2Rows / 8; ++ks) {
-          const uint64_t o = static_cast<uint64_t>(ks * (2048 >> 4));
-          tc_mma_ts(tm_g, r_h + ks * 8, d2_h + o, id12, ks > 0 ? 1u : first);
-          tc_mma_ts(tm_g, r_h + ks * 8, d2_l + o, id12, 1);
-          tc_mma_ts(tm_g, r_l + ks * 8, d2_h + o, id12, 1);
-        }
-        tc_commit(BAR(4, b));  // mma2_done[b]: B[b], ys[b], S[b] are free again
-      }
-      __syncwarp();
-      MC_DBG(3);
-    }
-    if (nt > 0) mbar_wait_s(BAR(4, (nt - 1) & 1), ((nt - 1) >> 1) & 1);  // the last commit covers every MMA2
-  } else if (warp <= 4) {
-    // ================= builders =================
-    // Each work item is a 4x4 block (rows 4*mb.., features 4*kc..): loaded once from the raw tile, split once
-    // into hi/lo, and written both as 4 row-chunks of B1 and as 4 feature-chunks of B2.
-    const int bt = tid - 32;
-    for (int i = 0; i < nt; ++i) {
-      const int b = i & 1;
-      const uint32_t par = (i >> 1) & 1;
-      const long long r0 = row_begin + static_cast<long long>(i) * kT2Rows;
-      const int rows = row_end - r0 >= kT2Rows ? kT2Rows : static_cast<int>(row_end - r0);
-      if (i >= 2) mbar_wait_s(BAR(4, b), par ^ 1u);  // MMA2(i-2) has finished reading B[b] / ys[b]
-      if (warp == 1) MC_DBG(4);
-      float* rawb = reinterpret_cast<float*>(raw0 + b * raw_bytes);
-      if (rows == kT2Rows) {
-        mbar_wait_s(BAR(0, b), par);
-      } else {  // ragged last tile: stage it through the (idle) raw buffer with plain loads
-        for (int e = bt; e < rows * ldx; e += kT2Builders) {
-          const int m = e / ldx, d = e - m * ldx;
-          rawb[e] = d < D ? a.X[(r0 + m) * a.ldx + d] : 0.0f;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kT2Builders) : "memory");
-      }
-      if (warp == 1) MC_DBG(5);
-      if (bt < kT2Rows) ysm[b * kT2Rows + bt] = bt < rows ? ld_y(a.y, a.y_dtype, r0 + bt) : 0.0f;
-      unsigned char* b1 = B1 + b * b1_buf;
-      unsigned char* b2 = B2 + b * b2_buf;
-      // thread → (row block mb = bt & 15, feature chunks kc = (bt >> 4) + 8j): no divisions, 64-bit shared loads
-      const int mb = bt & 15;
-      for (int kc = bt >> 4; kc < kc1; kc += 8) {
-        float v[4][4];
-        const bool even = (ldx & 1) == 0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int m = mb * 4 + r;
-          const float* rp = rawb + m * ldx + kc * 4;
-          if (even) {
-            const float2 p0 = *reinterpret_cast<const float2*>(rp);
-            const float2 p1 = *reinterpret_cast<const float2*>(rp + 2);
-            v[r][0] = p0.x;
-            v[r][1] = p0.y;
-            v[r][2] = p1.x;
-            v[r][3] = p1.y;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[r][e] = rp[e];
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (m >= rows || kc * 4 + e >= D) v[r][e] = 0.0f;
-        }
-        float hi[4][4], lo[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) split_tf32(v[r][e], hi[r][e], lo[r][e]);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {  // B1: row 4mb+r, features 4kc..4kc+3
-          const int o = kc * 1024 + (mb * 4 + r) * 16;
-          *reinterpret_cast<float4*>(b1 + o) = make_float4(hi[r][0], hi[r][1], hi[r][2], hi[r][3]);
-          *reinterpret_cast<float4*>(b1 + b1_half + o) = make_float4(lo[r][0], lo[r][1], lo[r][2], lo[r][3]);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {  // B2: feature 4kc+e, rows 4mb..4mb+3
-          const int o = mb * 1024 + (kc * 4 + e) * 16;
-          *reinterpret_cast<float4*>(b2 + o) = make_float4(hi[0][e], hi[1][e], hi[2][e], hi[3][e]);
-          *reinterpret_cast<float4*>(b2 + b2_half + o) = make_float4(lo[0][e], lo[1][e], lo[2][e], lo[3][e]);
-        }
-      }
-      // features Dp..63 of B2 are never written by the loop above: they stay zero from the one-time fill
-      if (warp == 1) MC_DBG(6);
-      fence_proxy_async_smem();
-      mbar_arrive(&bars[2 + b]);
-      if (warp == 1) MC_DBG(7);
-    }
-  } else {
-    // ================= epilogue =================
-    const int q = warp & 3, hf = (warp - 5) >> 2;
-    const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
-    for (int i = 0; i < nt; ++i) {
-      const int b = i & 1;
-      const uint32_t par = (i >> 1) & 1;
-      const long long r0 = row_begin + static_cast<long long>(i) * kT2Rows;
-      const int rows = row_end - r0 >= kT2Rows ? kT2Rows : static_cast<int>(row_end - r0);
-      mbar_wait_s(BAR(2, b), par);
-      if (warp == 5) MC_DBG(8);
-      tc_fence_after();
-      const float* ys = ysm + b * kT2Rows;
-      uint32_t vv[2][16];
-      tmem_ld16(tm + 64 * b + lane_base + hf * 32, vv[0]);
-      tmem_ld16(tm + 64 * b + lane_base + hf * 32 + 16, vv[1]);
-      tmem_wait_ld();
-      if (warp == 5) MC_DBG(9);
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col = hf * 32 + cc * 16;
-        uint32_t vh[16], vl[16];
-        const uint32_t* v = vv[cc];
-        if (a.want_logp || a.family != 0) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = col + j;
-            float lpv, rv;
-            row_terms(a.family, __uint_as_float(v[j]), ys[m], a.lik_scale, lpv, rv);
-            if (m >= rows) {
-              lpv = 0.0f;
-              rv = 0.0f;
-            }
-            lp += static_cast<double>(lpv);
-            float h, l;
-            split_tf32(rv, h, l);
-            vh[j] = __float_as_uint(h);
-            vl[j] = __float_as_uint(l);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = col + j;
-            const float eta = __uint_as_float(v[j]);
-            const float e = expf(-fabsf(eta));
-            const float qv = __fdividef(e, 1.0f + e);
-            const float yv = ys[m];
-            float rv = eta >= 0.0f ? (yv - 1.0f) + qv : yv - qv;
-            if (m >= rows) rv = 0.0f;
-            float h, l;
-            split_tf32(rv, h, l);
-            vh[j] = __float_as_uint(h);
-            vl[j] = __float_as_uint(l);
-          }
-        }
-        tmem_st16(tm + 64 * b + lane_base + col, vh);
-        tmem_st16(tm + 128 + 64 * b + lane_base + col, vl);
-      }
-      if (warp == 5) MC_DBG(10);
-      tmem_wait_st();
-      if (warp == 5) MC_DBG(11);
-      tc_fence_before();
-      mbar_arrive(&bars[6 + b]);
-      if (warp == 5) MC_DBG(12);
-    }
-  }
-
-  // ---- write this row group's partial sums ----
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  double* lpc = reinterpret_cast<double*>(raw0);  // [2][128], the raw buffers are idle now
-  if (warp >= 5 && warp <= 12) {
-    const int q = warp & 3, hf = (warp - 5) >> 2;
-    const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
-    const int chain = cb + 32 * q + lane;
-    float* pg = a.part_g + (static_cast<size_t>(blockIdx.x) * a.C + chain) * Dp;
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col = hf * 32 + cc * 16;
-      uint32_t v[16];
-      if (nt > 0) {
-        tmem_ld16(tm_g + lane_base + col, v);
-        tmem_wait_ld();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0u;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (col + j < Dp) pg[col + j] = __uint_as_float(v[j]);
-    }
-    lpc[hf * 128 + 32 * q + lane] = lp;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (tid < kMcChainsPerCta) a.part_lp[static_cast<size_t>(blockIdx.x) * a.C + cb + tid] = lpc[tid] + lpc[128 + tid];
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tm, 512);
-  }
-}
+constexpr int kTcN2 = 64;     // N of the second contraction: features, padded to 64
+constexpr int kT2Rows = 64;    // rows of X per tile of the pipelined pass
 
 // ------------------------------------------------------------------------------------------------
 // Tensor-core pass, version 3 (default): no per-pass hi/lo splitting, no builder warps.
@@ -736,6 +112,13 @@ constexpr int kT3Pitch = 1040;      // bytes between feature chunks (kc) of a pr
 constexpr int kT3B2Sbo = 144;       // bytes between 8-feature groups of B2T
 constexpr int kT3B2Lbo = 8 * 144;   // bytes between 4-row groups of B2T
 constexpr int kT3B2Plane = 16 * kT3B2Lbo;
+// The tensor core accumulates in fp32 with truncation: every tcgen05.mma into the same TMEM accumulator loses up to an
+// ulp of the running sum, always toward zero. Over a CTA's whole row range (cfg 3: 7,851 rows = 2,900 accumulations) that
+// is a systematic 2.4e-5 shrink of the gradient (found by tests/test_gpu_fullsize.py); G' is therefore flushed into a
+// float64 partial every kT3Seg tiles (512 rows, 192 accumulations; measured gradient error 4.2e-6 at cfg 3 against 5.9e-5
+// without the flush, 4 % of the pass time) from one of two TMEM buffers while
+// the MMAs of the next segment run into the other.
+constexpr int kT3Seg = 8;  // default of McArgs::seg_tiles
 
 __host__ __device__ inline int tc3_tile_bytes(int Dp) { return 2 * (Dp / 4) * kT3Pitch; }
 __host__ __device__ inline int tc3_stages(int Dp) { return Dp > 56 ? 2 : 3; }
@@ -821,6 +204,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
   auto XEMPTY = [&](int s) { return bar0 + static_cast<uint32_t>((3 + s) * 8); };
   auto SREADY = [&](int b) { return bar0 + static_cast<uint32_t>((6 + b) * 8); };
   auto RREADY = [&](int b) { return bar0 + static_cast<uint32_t>((8 + b) * 8); };
+  auto GFULL = [&](int g) { return bar0 + static_cast<uint32_t>((10 + g) * 8); };   // segment's MMAs into G'[g] are done
+  auto GEMPTY = [&](int g) { return bar0 + static_cast<uint32_t>((12 + g) * 8); };  // G'[g] has been flushed
 
   if (tid == 0) {
     for (int s = 0; s < kT3MaxStages; ++s) {
@@ -830,6 +215,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars[6 + b], 1);
       mbar_init(&bars[8 + b], kT3Epilogue);
+      mbar_init(&bars[10 + b], 1);
+      mbar_init(&bars[12 + b], kT3Epilogue);
     }
     fence_mbar_init();
   }
@@ -856,7 +243,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
-  const uint32_t tm_g = tm + 256;
+  const uint32_t tm_g = tm + 256;  // G'[0] at +256, G'[1] at +320
 
   long long u0, u1;
   tile_range(a.n_rows, a.n_rowgroups, blockIdx.x, u0, u1);
@@ -866,6 +253,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
   const long long tile0 = row_begin / kT2Rows;  // row_begin is a multiple of 128
   const int nt = row_end > row_begin ? static_cast<int>((row_end - row_begin + kT2Rows - 1) / kT2Rows) : 0;
   double lp = 0.0;
+  const int seg_tiles = a.seg_tiles > 0 ? a.seg_tiles : kT3Seg;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -912,21 +300,26 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
     const uint32_t id2 = idesc_tf32(128, kTcN2);
     for (int i = 0; i < nt; ++i) {
       const int s = i % NS, b = i & 1;
+      const int sg = i / seg_tiles, gb = sg & 1;
+      const bool seg_first = (i % seg_tiles) == 0, seg_last = (i % seg_tiles) == seg_tiles - 1 || i == nt - 1;
       mbar_wait_s(RREADY(b), (i >> 1) & 1);
+      if (seg_first && sg >= 2) mbar_wait_s(GEMPTY(gb), ((sg >> 1) - 1) & 1);  // the epilogue has flushed segment sg-2
       tc_fence_after();
       const uint32_t bs = smem_u32(B2T + b * 2 * kT3B2Plane);
       const uint64_t d2_h = smem_desc(bs, kT3B2Lbo, kT3B2Sbo), d2_l = smem_desc(bs + kT3B2Plane, kT3B2Lbo, kT3B2Sbo);
       const uint32_t r_h = tm + 64 * b, r_l = tm + 128 + 64 * b;
-      const uint32_t first = (i > 0) ? 1u : 0u;
+      const uint32_t acc = tm_g + 64 * gb;
+      const uint32_t first = seg_first ? 0u : 1u;
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < kT2Rows / 8; ++ks) {
           const uint64_t o = static_cast<uint64_t>(ks * ((2 * kT3B2Lbo) >> 4));  // 8 rows = 2 row groups
-          tc_mma_ts(tm_g, r_h + ks * 8, d2_h + o, id2, ks > 0 ? 1u : first);
-          tc_mma_ts(tm_g, r_h + ks * 8, d2_l + o, id2, 1);
-          tc_mma_ts(tm_g, r_l + ks * 8, d2_h + o, id2, 1);
+          tc_mma_ts(acc, r_h + ks * 8, d2_h + o, id2, ks > 0 ? 1u : first);
+          tc_mma_ts(acc, r_h + ks * 8, d2_l + o, id2, 1);
+          tc_mma_ts(acc, r_l + ks * 8, d2_h + o, id2, 1);
         }
         tc_commit(XEMPTY(s));  // stage s, ys[s], S[b]/R[b] and B2T[b] are free again
+        if (seg_last) tc_commit(GFULL(gb));
       }
       __syncwarp();
     }
@@ -942,8 +335,35 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
     const int pk = et % npk, mbt = et / npk;  // valid when mbt < 16
     const int tp = pk / kc1, tkc = pk - tp * kc1;
     const bool has_item = mbt < 16;
+    // float64 running sums of this thread's (chain, 16 features) in global memory (L2-resident), laid out
+    // [row group][feature][chain] so that the 32 chains of a warp are 256 contiguous bytes per feature: segment 0
+    // stores, later segments add with fire-and-forget reductions (no load round trip in the epilogue warps)
+    double* pg = a.part_g + static_cast<size_t>(blockIdx.x) * Dp * a.C + cb + 32 * q + lane;
+    const size_t pgs = static_cast<size_t>(a.C);
+    auto flush_segment = [&](int sg) {
+      const int gb = sg & 1;
+      mbar_wait_s(GFULL(gb), (sg >> 1) & 1);
+      tc_fence_after();
+      uint32_t gv[16];
+      tmem_ld16(tm_g + 64 * gb + lane_base + col, gv);
+      tmem_wait_ld();
+      if (a.seg_mode == 1) {
+        // (development) synchronisation only
+      } else if (sg == 0 || a.seg_mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (col + j < Dp) pg[(col + j) * pgs] = static_cast<double>(__uint_as_float(gv[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (col + j < Dp) atomicAdd(pg + (col + j) * pgs, static_cast<double>(__uint_as_float(gv[j])));
+      }
+      tc_fence_before();
+      mbar_arrive(&bars[12 + gb]);
+    };
     for (int i = 0; i < nt; ++i) {
       const int s = i % NS, b = i & 1;
+      if (i > 0 && (i % seg_tiles) == 0) flush_segment(i / seg_tiles - 1);
       const long long r0 = row_begin + static_cast<long long>(i) * kT2Rows;
       const int rows = row_end - r0 >= kT2Rows ? kT2Rows : static_cast<int>(row_end - r0);
       mbar_wait_s(XFULL(s), (i / NS) & 1);
@@ -988,11 +408,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int m = col + j;
-          const float eta = __uint_as_float(v[j]);
-          const float e = expf(-fabsf(eta));
-          const float qv = __fdividef(e, 1.0f + e);
-          const float yv = ys[m];
-          float rv = eta >= 0.0f ? (yv - 1.0f) + qv : yv - qv;
+          float rv = bernoulli_resid_fast(__uint_as_float(v[j]), ys[m]);  // ex2.approx + rcp.approx, error <= 4e-7
           if (m >= rows) rv = 0.0f;
           float h, l;
           split_tf32(rv, h, l);
@@ -1006,6 +422,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
       tc_fence_before();
       mbar_arrive(&bars[8 + b]);  // R[b] and B2T[b] are ready
     }
+    if (nt > 0) flush_segment((nt - 1) / seg_tiles);
   }
 
   // ---- write this row group's partial sums ----
@@ -1016,19 +433,14 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
     const int q = warp & 3, cg = (warp - 4) >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
     const int chain = cb + 32 * q + lane;
-    float* pg = a.part_g + (static_cast<size_t>(blockIdx.x) * a.C + chain) * Dp;
     const int col = cg * 16;
-    uint32_t v[16];
-    if (nt > 0) {
-      tmem_ld16(tm_g + lane_base + col, v);
-      tmem_wait_ld();
-    } else {
+    (void)lane_base;
+    if (nt == 0) {  // a row group without rows still publishes its (zero) partial
+      double* pgz = a.part_g + static_cast<size_t>(blockIdx.x) * Dp * a.C + chain;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = 0u;
+      for (int j = 0; j < 16; ++j)
+        if (col + j < Dp) pgz[static_cast<size_t>(col + j) * a.C] = 0.0;
     }
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (col + j < Dp) pg[col + j] = __uint_as_float(v[j]);
     lpc[cg * 128 + 32 * q + lane] = lp;
   }
   tc_fence_before();
@@ -1057,7 +469,7 @@ __device__ __forceinline__ double chain_sum(double v, double* sh) {  // 64 threa
 // sums the row-group partials of (chain c, feature d) in a fixed order, float64
 __device__ __forceinline__ double sum_part_g(const McArgs& a, int c, int d) {
   double s = 0.0;
-  for (int rg = 0; rg < a.n_rowgroups; ++rg) s += static_cast<double>(a.part_g[(static_cast<size_t>(rg) * a.C + c) * a.Dp + d]);
+  for (int rg = 0; rg < a.n_rowgroups; ++rg) s += a.part_g[(static_cast<size_t>(rg) * a.Dp + d) * a.C + c];
   return s;
 }
 __device__ __forceinline__ double sum_part_lp(const McArgs& a, int c) {
@@ -1213,11 +625,6 @@ __global__ void __launch_bounds__(kMcChainThreads) k_mc_logp_grad_finish(const M
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-int mc_smem_bytes_tc(int Dp) {
-  int off[8];
-  return tc_smem_layout(Dp, kMcMaxD, off);
-}
-
 size_t mc_pretile_bytes(long long n_rows, int Dp, size_t* yt_bytes) {
   const long long ntiles = (n_rows + kT2Rows - 1) / kT2Rows;
   *yt_bytes = static_cast<size_t>(ntiles) * kT2Rows * sizeof(float);
@@ -1240,10 +647,7 @@ cudaError_t mc_prepare_tc() {
     cudaError_t e3 = cudaFuncSetAttribute(k_mc_pass_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (e3 != cudaSuccess) return e3;
   }
-  cudaError_t e = cudaFuncSetAttribute(k_mc_pass_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       tc2_smem_layout(kMcMaxD, kMcMaxD, off));
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_mc_pass_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, mc_smem_bytes_tc(kMcMaxD));
+  return cudaSuccess;
 }
 
 cudaError_t mc_launch_pass(const McArgs& a, const float* theta, int use_tc, int gate, cudaStream_t s) {
@@ -1252,14 +656,6 @@ cudaError_t mc_launch_pass(const McArgs& a, const float* theta, int use_tc, int 
     int off[8];
     const int smem = tc3_smem_layout(a.Dp, off);
     k_mc_pass_tc3<<<grid, kT3Threads, smem, s>>>(a, theta, gate);
-  } else if (use_tc == 2) {
-    int off[8];
-    const int smem = tc2_smem_layout(a.Dp, static_cast<int>(a.ldx), off);
-    k_mc_pass_tc2<<<grid, kT2Threads, smem, s>>>(a, theta, gate);
-  } else if (use_tc == 1) {
-    int off[8];
-    const int smem = tc_smem_layout(a.Dp, static_cast<int>(a.ldx), off);
-    k_mc_pass_tc<<<grid, kTcThreads, smem, s>>>(a, theta, gate);
   } else {
     k_mc_pass_simple<<<grid, kMcChainsPerCta, 0, s>>>(a, theta, gate);
   }

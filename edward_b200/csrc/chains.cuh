@@ -2,7 +2,7 @@
 // chain per ed.HMC object, hmc.py:14-130). Shared declarations between chains.cu (kernels) and edhmc.cu.
 //
 // Per leapfrog step the C chains need  S = X·W  (N×D · D×C),  R = y − σ(S)  and  G = Xᵀ·R  (D×C): a dense
-// contraction, executed on the tcgen05 tensor cores in 3xTF32 (k_mc_pass_tc) with TMEM accumulators, or
+// contraction, executed on the tcgen05 tensor cores in 3xTF32 (k_mc_pass_tc3) with TMEM accumulators, or
 // on the CUDA cores (k_mc_pass_simple, the bring-up / cross-check path). The O(C·P) integrator, prior,
 // kinetic energy and Metropolis–Hastings step of every chain run in small per-chain kernels between passes.
 #pragma once
@@ -31,6 +31,8 @@ struct McArgs {
   double prior_const;
   int C;           // chains (multiple of 128)
   int n_rowgroups;  // CTAs along the rows
+  int seg_mode;     // development: 0 = float64 flush, 1 = synchronisation only, 2 = store only
+  int seg_tiles;    // tensor-core pass: 64-row tiles accumulated in TMEM before a float64 flush (0 = default)
   int want_logp;    // 1: the pass also accumulates the log-likelihood (only needed at the end of a trajectory)
   // state, all [C][D] float32 unless noted
   float* z;
@@ -44,8 +46,8 @@ struct McArgs {
   long long* n_accept;  // [C]
   int* valid;           // [1]
   int* need_init;       // [1]
-  // pass output: per row group partial sums, [n_rowgroups][C][Dp+1] float32 gradient + [n_rowgroups][C] float64 logp
-  float* part_g;
+  // pass output: per row group partial sums, [n_rowgroups][Dp][C] float64 gradient + [n_rowgroups][C] float64 logp
+  double* part_g;
   double* part_lp;
   // run
   float* params;  // [T][C][D]
@@ -64,7 +66,6 @@ struct McArgs {
 };
 
 // host launchers (chains.cu)
-int mc_smem_bytes_tc(int Dp);
 cudaError_t mc_prepare_tc();
 cudaError_t mc_launch_pass(const McArgs& a, const float* theta, int use_tc, int gate, cudaStream_t s);
 cudaError_t mc_launch_pretile(const McArgs& a, float* xt, float* yt, cudaStream_t s);

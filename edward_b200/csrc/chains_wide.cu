@@ -1,8 +1,12 @@
 // chains_wide.cu — many vectorised chains for wide models / row shards (see chains_wide.cuh): two hand-written
 // tcgen05 GEMMs in 3xTF32 per leapfrog step, operands as pre-tiled hi/lo planes moved by TMA bulk copies.
 //
-// k_mcw_gemm<1>   Sᵀ[128 chains x 256 rows] per tile: A = Wᵀ planes, B = X planes (K = features, 16 per stage);
-//                 accumulator double-buffered in TMEM (2 x 256 columns); epilogue R = y − σ(Sᵀ) (one thread per
+// k_mcw_gemm<1>   Sᵀ[128 chains x 128 rows] per tile: A = Wᵀ planes, B = X planes (K = features, 16 per stage);
+//                 TWO accumulators per tile — hi·hi into the main one, the 3xTF32 correction terms hi·lo + lo·hi into a
+//                 second one, summed in the epilogue — because the tensor core truncates the fp32 accumulator after
+//                 every instruction: with all three terms in one accumulator K = 1,000 features are 375 truncations
+//                 of the logit (a systematic 8e-6 shrink, 1e-5 gradient error at 1.25M rows); now 125;
+//                 both double-buffered in TMEM (2 x (128 + 128) columns); epilogue R = y − σ(Sᵀ) (one thread per
 //                 chain = TMEM lane, so the per-chain log-likelihood needs no cross-thread reduction), written as
 //                 hi/lo planes in the K-major layout GEMM 2 reads as its A operand.
 // k_mcw_gemm<2>   G'[128 chains x NB2 features] per (chain tile, feature tile, K split): A = R planes, B = Xᵀ planes
@@ -233,9 +237,15 @@ __global__ void __launch_bounds__(kMwThreads, 1) k_mcw_gemm(const McwArgs a, int
 #pragma unroll
           for (int ks = 0; ks < kMwKC / 8; ++ks) {
             const uint64_t oa = static_cast<uint64_t>(ks * (4096 >> 4)), ob = static_cast<uint64_t>(ks * ((2 * b_lbo) >> 4));
-            tc_mma_ss(d, a_h + oa, b_h + ob, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-            tc_mma_ss(d, a_h + oa, b_l + ob, idesc, 1);
-            tc_mma_ss(d, a_l + oa, b_h + ob, idesc, 1);
+            const uint32_t accf = (c > 0 || ks > 0) ? 1u : 0u;
+            tc_mma_ss(d, a_h + oa, b_h + ob, idesc, accf);
+            if (MODE == 1) {  // correction terms into their own accumulator (columns 128..255 of the buffer)
+              tc_mma_ss(d + 128, a_h + oa, b_l + ob, idesc, accf);
+              tc_mma_ss(d + 128, a_l + oa, b_h + ob, idesc, 1);
+            } else {
+              tc_mma_ss(d, a_h + oa, b_l + ob, idesc, 1);
+              tc_mma_ss(d, a_l + oa, b_h + ob, idesc, 1);
+            }
           }
           tc_commit(EMPTY(s));
           if (c == nch - 1) tc_commit(ACCF(b));
@@ -258,11 +268,14 @@ __global__ void __launch_bounds__(kMwThreads, 1) k_mcw_gemm(const McwArgs a, int
         const long long t = blockIdx.y + static_cast<long long>(i) * gridDim.y;
         const size_t rplane = static_cast<size_t>(a.rowsP) * 128;
         float* rbase = a.rp + static_cast<size_t>(ct) * 2 * rplane + static_cast<size_t>(cl) * 4;
-        for (int gq = 0; gq < 8; ++gq) {
-          const int col0 = hf * 128 + gq * 16;
-          uint32_t v[16];
+        for (int gq = 0; gq < kMwRowTile / 32; ++gq) {
+          const int col0 = hf * (kMwRowTile / 2) + gq * 16;
+          uint32_t v[16], vc[16];
           tmem_ld16(acc + col0, v);
+          tmem_ld16(acc + 128 + col0, vc);
           tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vc[j]));
           const long long row0 = t * kMwRowTile + col0;
           float rv[16];
           float lps = 0.0f;  // 16 terms in fp32, then one float64 add: the FP64 pipe is narrow
@@ -297,18 +310,21 @@ __global__ void __launch_bounds__(kMwThreads, 1) k_mcw_gemm(const McwArgs a, int
         }
       } else {
         const int ncg = NB / 16;
-        double* out = a.part_g64 + (static_cast<size_t>(blockIdx.z) * a.C + ct * 128 + cl) * a.Dp2 + static_cast<size_t>(blockIdx.y) * NB;
+        // float64 partial of (split, feature, chain), chain fastest: the 32 chains of a warp are 256 contiguous bytes per
+        // feature. The first segment stores, later ones add with fire-and-forget reductions (no load round trip).
+        const size_t cs = static_cast<size_t>(a.C);
+        double* out = a.part_g64 + (static_cast<size_t>(blockIdx.z) * a.Dp2 + static_cast<size_t>(blockIdx.y) * NB) * cs + ct * 128 + cl;
         for (int gq = hf; gq < ncg; gq += 2) {
           uint32_t v[16];
           tmem_ld16(acc + gq * 16, v);
           tmem_wait_ld();
-          double* o = out + gq * 16;
+          double* o = out + static_cast<size_t>(gq * 16) * cs;
           if (i == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = static_cast<double>(__uint_as_float(v[j]));
+            for (int j = 0; j < 16; ++j) o[j * cs] = static_cast<double>(__uint_as_float(v[j]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] += static_cast<double>(__uint_as_float(v[j]));
+            for (int j = 0; j < 16; ++j) atomicAdd(o + j * cs, static_cast<double>(__uint_as_float(v[j])));
           }
         }
       }
@@ -319,9 +335,10 @@ __global__ void __launch_bounds__(kMwThreads, 1) k_mcw_gemm(const McwArgs a, int
       lpc[hf * 128 + cl] = lp;
     } else if (n_items == 0) {
       const int ncg = NB / 16;
-      double* out = a.part_g64 + (static_cast<size_t>(blockIdx.z) * a.C + ct * 128 + cl) * a.Dp2 + static_cast<size_t>(blockIdx.y) * NB;
+      const size_t cs = static_cast<size_t>(a.C);
+      double* out = a.part_g64 + (static_cast<size_t>(blockIdx.z) * a.Dp2 + static_cast<size_t>(blockIdx.y) * NB) * cs + ct * 128 + cl;
       for (int gq = hf; gq < ncg; gq += 2)
-        for (int j = 0; j < 16; ++j) out[gq * 16 + j] = 0.0;
+        for (int j = 0; j < 16; ++j) out[static_cast<size_t>(gq * 16 + j) * cs] = 0.0;
     }
   }
   tc_fence_before();
@@ -340,7 +357,7 @@ __global__ void __launch_bounds__(kMwChainThreads) k_mcw_fold(const McwArgs a, i
   double* out = a.gsum + static_cast<size_t>(c) * (a.D + 1);
   for (int d = threadIdx.x; d < a.D; d += kMwChainThreads) {
     double s = 0.0;
-    for (int sp = 0; sp < a.splits; ++sp) s += a.part_g64[(static_cast<size_t>(sp) * a.C + c) * a.Dp2 + d];
+    for (int sp = 0; sp < a.splits; ++sp) s += a.part_g64[(static_cast<size_t>(sp) * a.Dp2 + d) * a.C + c];
     out[d] = s;
   }
   if (threadIdx.x == 0) {

@@ -14,9 +14,10 @@
 
 namespace edhmc {
 
-constexpr int kMwRowTile = 256;   // rows of X per GEMM-1 tile (MMA N)
+constexpr int kMwRowTile = 128;   // rows of X per GEMM-1 tile (MMA N): main + correction accumulator, double-buffered = 512 TMEM columns
 constexpr int kMwKC = 16;         // K elements per pipeline stage (two k-steps of 8)
-constexpr int kMwSegChunks = 512; // GEMM 2: stages accumulated in TMEM (fp32) before a float64 flush: 8,192 rows
+constexpr int kMwSegChunks = 32;  // GEMM 2: stages accumulated in TMEM (fp32, truncating) before a float64 flush: 512 rows =
+                                  // 192 accumulations (8,192 rows left a systematic 2e-5 shrink of the gradient at 1.25M rows)
 
 struct McwArgs {
   // problem
@@ -48,7 +49,7 @@ struct McwArgs {
   float* wt;   // [nct][2][Kp1/4][128][4]
   float* rp;   // [nct][2][rowsP/4][128][4]
   // reduction buffers
-  double* part_g64;  // [splits][C][Dp2]
+  double* part_g64;  // [splits][Dp2][C]
   double* part_lp;   // [g1][C]
   double* gsum;      // [C][D+1]: likelihood gradient sums and log-likelihood, all-reduced over row shards
   // chain state, [C][D] float32 unless noted

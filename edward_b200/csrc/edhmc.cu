@@ -186,8 +186,8 @@ struct edhmc_handle {
   long long spin_limit = 0;
   // many chains
   int C = 0, mc_nrg = 0, mc_use_tc = 0, mc_Dp = 0;
-  float *mc_z = nullptr, *mc_r = nullptr, *mc_g = nullptr, *mc_zcur = nullptr, *mc_gcur = nullptr, *mc_part_g = nullptr;
-  double *mc_logp = nullptr, *mc_kold = nullptr, *mc_logu = nullptr, *mc_part_lp = nullptr;
+  float *mc_z = nullptr, *mc_r = nullptr, *mc_g = nullptr, *mc_zcur = nullptr, *mc_gcur = nullptr;
+  double *mc_part_g = nullptr, *mc_logp = nullptr, *mc_kold = nullptr, *mc_logu = nullptr, *mc_part_lp = nullptr;
   long long* mc_nacc = nullptr;
   int* mc_flags = nullptr;  // [0] valid, [1] need_init
   double* mc_trace = nullptr;
@@ -634,18 +634,14 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
     if (nrg < 1) nrg = 1;
     if (nrg > ntiles) nrg = ntiles > 0 ? ntiles : 1;
     h->mc_nrg = static_cast<int>(nrg);
-    // pass implementation: 3 = pre-tiled pipelined tcgen05 (default), 2 = pipelined with per-pass operand
-    // builders, 1 = sequential tcgen05, 0 = CUDA cores
+    // pass implementation: 3 = pre-tiled pipelined tcgen05 (default), 0 = CUDA cores (cross-check)
     h->mc_use_tc = 3;
     h->mc_wide = cfg->n_features > kMcMaxD;
     if (const char* e = getenv("EDHMC_MC_IMPL")) {
       if (strcmp(e, "wide") == 0) h->mc_wide = true;
       if (strcmp(e, "simple") == 0) h->mc_use_tc = 0;
-      else if (strcmp(e, "tc1") == 0) h->mc_use_tc = 1;
-      else if (strcmp(e, "tc2") == 0) h->mc_use_tc = 2;
       else if (strcmp(e, "tc") == 0) h->mc_use_tc = 3;
     }
-    if ((h->mc_use_tc == 1 || h->mc_use_tc == 2) && cfg->ldx > kMcMaxD) h->mc_use_tc = 3;
     memset(&h->mcw, 0, sizeof(h->mcw));
     if (h->mc_wide) {
       McwArgs& w = h->mcw;
@@ -686,7 +682,7 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
     ALLOC(h->mc_logu, h->C * sizeof(double));
     ALLOC(h->mc_nacc, h->C * sizeof(long long));
     ALLOC(h->mc_flags, 4 * sizeof(int));
-    ALLOC(h->mc_part_g, static_cast<size_t>(h->mc_nrg) * h->C * h->mc_Dp * sizeof(float));
+    ALLOC(h->mc_part_g, static_cast<size_t>(h->mc_nrg) * h->C * h->mc_Dp * sizeof(double));
     ALLOC(h->mc_part_lp, static_cast<size_t>(h->mc_nrg) * h->C * sizeof(double));
     cudaMemset(h->mc_zcur, 0, cd);
     cudaMemset(h->mc_gcur, 0, cd);
@@ -1195,6 +1191,8 @@ static void fill_mc_args(edhmc_handle* h, McArgs& a) {
   a.prior_const = h->prior_const;
   a.C = h->C;
   a.n_rowgroups = h->mc_nrg;
+  if (const char* e = getenv("EDHMC_MC_SEG_MODE")) a.seg_mode = atoi(e);
+  if (const char* e = getenv("EDHMC_MC_SEG")) a.seg_tiles = atoi(e);  // development: TMEM accumulation length (tiles)
   a.want_logp = 1;
   a.z = h->mc_z;
   a.r = h->mc_r;

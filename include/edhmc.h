@@ -220,7 +220,7 @@ int edhmc_plan_info(edhmc_t* h, int64_t* out_host, int32_t cap);
 
 /* Host-only: the tiling edhmc_create would choose for the wide / row-sharded vectorised-chain path (two-GEMM
  * plan, csrc/chains_wide.cu) on a device with num_sms multiprocessors. out[0..7] = {chain tiles, K of GEMM 1
- * (features rounded to 16), row tiles of 256, feature tiles of GEMM 2, feature-tile width, CTAs per chain tile in
+ * (features rounded to 16), row tiles of 128, feature tiles of GEMM 2, feature-tile width, CTAs per chain tile in
  * GEMM 1, K splits of GEMM 2, padded feature count of GEMM 2}. No CUDA call is made (usable without a GPU).
  * Replaces: nothing in the reference (introspection for tests and capacity planning). */
 int edhmc_chains_plan_probe(int64_t n_rows, int32_t n_features, int32_t n_chains, int32_t num_sms, int64_t* out8);

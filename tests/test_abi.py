@@ -122,13 +122,13 @@ def test_wide_chain_tiling_probe():
     return dict(zip(["nct", "Kp1", "nrt", "nft", "NB2", "g1", "splits", "Dp2"], list(out)))
 
   p = probe(1_250_000, 1000, 1024)  # config 5, one GPU's shard
-  assert p["nct"] == 8 and p["Kp1"] == 1008 and p["nrt"] == 4883
+  assert p["nct"] == 8 and p["Kp1"] == 1008 and p["nrt"] == 9766  # 128-row tiles of GEMM 1
   assert (p["nft"], p["NB2"], p["splits"], p["Dp2"]) == (6, 176, 3, 1056)  # 144 of 148 SMs instead of 128
   assert p["g1"] == 18
   for n, d, c in [(300, 1000, 128), (2111, 1000, 256), (5000, 200, 128), (20000, 72, 128), (1000, 54, 128), (7, 2048, 256)]:
     p = probe(n, d, c)
     assert p["NB2"] % 16 == 0 and 16 <= p["NB2"] <= 256 and p["nft"] * p["NB2"] == p["Dp2"] >= d
-    assert p["Kp1"] % 16 == 0 and p["Kp1"] >= d and p["nrt"] * 256 >= n
+    assert p["Kp1"] % 16 == 0 and p["Kp1"] >= d and p["nrt"] * 128 >= n
     assert 1 <= p["g1"] <= max(1, p["nrt"]) and p["nct"] * p["g1"] <= 148
     assert p["splits"] >= 1 and p["nct"] * p["nft"] * p["splits"] <= max(148, p["nct"] * p["nft"])
   assert L.edhmc_chains_plan_probe(100, 8, 100, 148, out) == _C.ERR_INVALID
