@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("EDHMC_LIB_PATH") or os.path.join(HERE, "lib", "libedh
 EDHMC_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NONFINITE, ERR_RANGE, ERR_STATE, ERR_COMM, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 BERNOULLI_LOGIT, NORMAL_IDENTITY, POISSON_LOG = 0, 1, 2
+PRIOR_NORMAL, PRIOR_BETA_LOGIT = 0, 1
 Y_I32, Y_F32, Y_U8 = 0, 1, 2
 PLAN_AUTO, PLAN_PERSISTENT, PLAN_STEPWISE = 0, 1, 2
 
@@ -22,7 +23,7 @@ EXPORTS = [
     "edhmc_version", "edhmc_last_error", "edhmc_create", "edhmc_destroy", "edhmc_bind_data",
     "edhmc_logp_grad", "edhmc_run", "edhmc_set_trace", "edhmc_read_state", "edhmc_reset", "edhmc_seed",
     "edhmc_comm_unique_id", "edhmc_comm_init", "edhmc_peer_export", "edhmc_peer_attach", "edhmc_peer_detach", "edhmc_plan_info",
-    "edhmc_sgmcmc_run", "edhmc_run_chains", "edhmc_logp_grad_chains", "edhmc_read_chain_state", "edhmc_set_chain_trace", "edhmc_set_chain_debug", "edhmc_chains_plan_probe", "edhmc_set_timeline", "edhmc_probe_read", "edhmc_comm_cached", "edhmc_comm_release",
+    "edhmc_sgmcmc_run", "edhmc_run_chains", "edhmc_logp_grad_chains", "edhmc_read_chain_state", "edhmc_set_chain_trace", "edhmc_set_chain_debug", "edhmc_chains_plan_probe", "edhmc_set_timeline", "edhmc_probe_read", "edhmc_comm_cached", "edhmc_comm_release", "edhmc_set_prior_kinds",
 ]
 
 
@@ -102,6 +103,7 @@ def lib():
   L.edhmc_probe_read.argtypes = [vp, i64, i32, i32, vp, vp]
   L.edhmc_comm_cached.argtypes = [i32, i32, i32]
   L.edhmc_comm_release.argtypes = [i32]
+  L.edhmc_set_prior_kinds.argtypes = [vp, C.POINTER(i32)]
   for name in EXPORTS:
     if name not in ("edhmc_last_error",):
       getattr(L, name).restype = C.c_int

@@ -11,6 +11,6 @@ from .criticisms import evaluate, ppc  # noqa: F401
 from .util.copying import copy  # noqa: F401
 from .inferences import HMC, SGHMC, SGLD, Inference, MonteCarlo  # noqa: F401
 from .models import RandomVariable  # noqa: F401
-from .util import Progbar, check_data, check_latent_vars, dot, get_session, random_variables, set_seed  # noqa: F401
+from .util import Progbar, check_data, check_latent_vars, dot, get_session, random_variables, set_seed, transform  # noqa: F401
 
 __version__ = "0.1.0"

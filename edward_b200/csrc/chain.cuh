@@ -273,10 +273,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   // serial section between two data passes
   float pl0 = 0.0f, ps0 = 1.0f;
   double piv0 = 1.0;
+  int pk0 = 0;
   if (tid < P && tid < CT) {
     pl0 = a.prior_loc[tid];
     ps0 = a.prior_scale[tid];
     piv0 = prior_inv_var(ps0);
+    pk0 = a.prior_kind ? a.prior_kind[tid] : 0;
   }
 
   // ---- chain registers (uniform across threads and CTAs) ----
@@ -527,13 +529,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
     for (int c = tid; c < P && tid < CT; c += CT) {
       float loc = pl0, sc = ps0;
       double iv = piv0;
+      int kind = pk0;
       if (c != tid) {  // models with more than kChainThreads latents: the further columns come from global memory
         loc = a.prior_loc[c];
         sc = a.prior_scale[c];
         iv = prior_inv_var(sc);
+        kind = a.prior_kind ? a.prior_kind[c] : 0;
       }
-      gout[c] = static_cast<float>(sm.cta_acc[c] + prior_grad_iv(pos[c], loc, iv));
-      if (want_lp) pl += prior_quad(pos[c], loc, sc);
+      gout[c] = static_cast<float>(sm.cta_acc[c] + prior_grad_kind(kind, pos[c], loc, sc, iv));
+      if (want_lp) pl += prior_logp_kind(kind, pos[c], loc, sc);
     }
     if (want_lp) {
       const double lik = sm.cta_acc[P];

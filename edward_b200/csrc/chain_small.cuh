@@ -10,8 +10,9 @@ __device__ __forceinline__ double finish_gradient(const KArgs& a, const float* p
   double pl = 0.0;
   for (int c = threadIdx.x; c < a.P; c += kChainThreads) {
     const float loc = a.prior_loc[c], sc = a.prior_scale[c];
-    gout[c] = static_cast<float>(a.sums[c] + prior_grad_iv(pos[c], loc, prior_inv_var(sc)));
-    pl += prior_quad(pos[c], loc, sc);
+    const int kind = a.prior_kind ? a.prior_kind[c] : 0;
+    gout[c] = static_cast<float>(a.sums[c] + prior_grad_kind(kind, pos[c], loc, sc, prior_inv_var(sc)));
+    pl += prior_logp_kind(kind, pos[c], loc, sc);
   }
   return (block_sum_f64(pl, red) - a.prior_const) + a.sums[a.P];
 }
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_sg_update(const KArgs a, c
     const float old = a.params[t_prev * a.ldp + c];
     const double pf = g.prior_factor ? static_cast<double>(g.prior_factor[c]) : 1.0;
     const float grad = static_cast<float>(static_cast<double>(g.lik_factor) * a.sums[c] +
-                                          pf * prior_grad(old, a.prior_loc[c], a.prior_scale[c]));
+                                          pf * prior_grad_kind(a.prior_kind ? a.prior_kind[c] : 0, old, a.prior_loc[c], a.prior_scale[c],
+                                                               prior_inv_var(a.prior_scale[c])));
     const float nz = g.noise ? g.noise[it * a.P + c] : philox_normal(a.seed, t, c);
     float out;
     if (g.kind == 0) {

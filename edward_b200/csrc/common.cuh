@@ -58,7 +58,8 @@ struct KArgs {
   float lik_scale;
   const float* prior_loc;
   const float* prior_scale;
-  double prior_const;  // sum_c (0.5*log(2*pi) + log(scale_c)), float64, computed once on the host
+  const int* prior_kind;  // [P] or nullptr (all Normal): 0 Normal(loc, scale), 1 Beta(a = loc, b = scale) through a sigmoid
+  double prior_const;  // sum of the priors' additive constants (Normal: 0.5*log(2*pi) + log(scale); Beta: lbeta), host float64
   // ---- streaming plan ----
   int Kact;          // active vector chunks per lane
   int J;             // row groups per tile
@@ -184,6 +185,35 @@ __device__ __forceinline__ float load_y(const void* y, int y_dtype, long long i)
 }
 __device__ __forceinline__ float y_from_bits(uint32_t bits, int y_dtype) {
   return y_dtype == 0 ? static_cast<float>(static_cast<int>(bits)) : __uint_as_float(bits);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Priors of the (unconstrained) latents, float64. kind 0: Normal(loc = p0, scale = p1) — the hot path. kind 1: a latent
+// with support (0, 1) and a Beta(a = p0, b = p1) prior, sampled in the unconstrained space u = logit(z) as the reference
+// does under auto_transform (inference.py:223-264, util/random_variables.py:856-917, hmc.py:132-159): the density
+// of u is Beta(sigmoid(u)) * |d sigmoid / du|, so  log p(u) = a log sigmoid(u) + b log sigmoid(-u) - lbeta(a, b)  (the
+// log-det-Jacobian log z + log(1-z) is folded in) and  d/du = a - (a + b) sigmoid(u).
+// The additive constants (0.5 log 2 pi + log scale; lbeta) are summed once on the host into KArgs::prior_const.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double log_sigmoid64(double u) {  // min(u, 0) - log1p(exp(-|u|))
+  return fmin(u, 0.0) - log1p(exp(-fabs(u)));
+}
+__device__ __forceinline__ double prior_logp_kind(int kind, float zc, float p0, float p1) {
+  if (kind == 1) {
+    const double u = static_cast<double>(zc);
+    return static_cast<double>(p0) * log_sigmoid64(u) + static_cast<double>(p1) * log_sigmoid64(-u);
+  }
+  const double t = (static_cast<double>(zc) - static_cast<double>(p0)) / static_cast<double>(p1);
+  return -0.5 * t * t;
+}
+// `aux` is the precomputed reciprocal variance for kind 0 (prior_inv_var) and unused otherwise.
+__device__ __forceinline__ double prior_grad_kind(int kind, float zc, float p0, float p1, double aux) {
+  if (kind == 1) {
+    const double u = static_cast<double>(zc);
+    const double sg = 1.0 / (1.0 + exp(-u));
+    return static_cast<double>(p0) - (static_cast<double>(p0) + static_cast<double>(p1)) * sg;
+  }
+  return -((static_cast<double>(zc) - static_cast<double>(p0)) * aux);
 }
 
 // Normal prior, float64: log density without the constant, and its gradient.

@@ -154,6 +154,8 @@ struct edhmc_handle {
   // device buffers
   float* d_prior_loc = nullptr;
   float* d_prior_scale = nullptr;
+  int* d_prior_kind = nullptr;  // nullptr: every latent has a Normal prior
+  std::vector<float> prior_loc_h, prior_scale_h;
   double prior_const = 0.0;
   ChainScalars* d_sc = nullptr;
   float* d_zcur = nullptr;
@@ -492,6 +494,7 @@ static void fill_args(edhmc_handle* h, KArgs& a) {
   a.lik_scale = c.lik_scale;
   a.prior_loc = h->d_prior_loc;
   a.prior_scale = h->d_prior_scale;
+  a.prior_kind = h->d_prior_kind;
   a.prior_const = h->prior_const;
   const Plan& p = h->plan;
   a.Kact = p.Kact;
@@ -579,6 +582,8 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   h->cfg.prior_scale_host = nullptr;
   h->P = P;
   h->prior_const = pc;
+  h->prior_loc_h.assign(cfg->prior_loc_host, cfg->prior_loc_host + P);
+  h->prior_scale_h.assign(cfg->prior_scale_host, cfg->prior_scale_host + P);
   if (const char* e = getenv("EDHMC_ZIGZAG")) h->zigzag = atoi(e);
   if (const char* e = getenv("EDHMC_L2_HINT")) h->l2_hint = atoi(e);
   if (const char* e = getenv("EDHMC_L2_FRAC")) h->l2_frac = static_cast<float>(atof(e));
@@ -750,6 +755,7 @@ int edhmc_destroy(edhmc_t* h) {
   h_free(h, h->d_abort);
   h_free(h, h->d_prior_loc);
   h_free(h, h->d_prior_scale);
+  if (h->d_prior_kind) cudaFree(h->d_prior_kind);
   h_free(h, h->d_sc);
   h_free(h, h->d_zcur);
   h_free(h, h->d_gcur);
@@ -948,6 +954,34 @@ int edhmc_set_trace(edhmc_t* h, double* trace_scalars, float* trace_pos) {
   if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
   h->trace_scalars = trace_scalars;
   h->trace_pos = trace_pos;
+  return 0;
+}
+
+int edhmc_set_prior_kinds(edhmc_t* h, const int32_t* kinds_host) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (!kinds_host) {
+    if (h->d_prior_kind) cudaFree(h->d_prior_kind);
+    h->d_prior_kind = nullptr;
+  } else {
+    if (h->C > 1) return fail(EDHMC_ERR_INVALID, "vectorised chains support Normal priors only");
+    double pc = 0.0;
+    for (int i = 0; i < h->P; ++i) {
+      const double p0 = h->prior_loc_h[i], p1 = h->prior_scale_h[i];
+      if (kinds_host[i] == 0) {
+        pc += 0.5 * log(2.0 * M_PI) + log(p1);
+      } else if (kinds_host[i] == 1) {
+        if (!(p0 > 0.0)) return fail(EDHMC_ERR_INVALID, "Beta prior of latent %d needs a > 0 (prior_loc), got %g", i, p0);
+        pc += lgamma(p0) + lgamma(p1) - lgamma(p0 + p1);  // lbeta(a, b)
+      } else {
+        return fail(EDHMC_ERR_INVALID, "unknown prior kind %d for latent %d", kinds_host[i], i);
+      }
+    }
+    if (!h->d_prior_kind) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_prior_kind), sizeof(int) * h->P));
+    CUDA_TRY(cudaMemcpy(h->d_prior_kind, kinds_host, sizeof(int) * h->P, cudaMemcpyHostToDevice));
+    h->prior_const = pc;
+  }
+  CUDA_TRY(cudaMemset(&h->d_sc->valid, 0, sizeof(int)));  // the cached log joint no longer applies
   return 0;
 }
 

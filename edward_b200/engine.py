@@ -301,6 +301,12 @@ class GLMSampler:
     with torch.cuda.device(self.dev):
       _C.check(self.lib.edhmc_reset(self._h, _stream_ptr(self.dev)))
 
+  def set_prior_kinds(self, kinds):
+    """Per-latent prior family (edhmc_set_prior_kinds): 0 Normal(loc, scale), 1 Beta(a = loc, b = scale) through a sigmoid."""
+    k = np.ascontiguousarray(kinds, np.int32).reshape(self.P)
+    with torch.cuda.device(self.dev):
+      _C.check(self.lib.edhmc_set_prior_kinds(self._h, k.ctypes.data_as(C.POINTER(C.c_int32))))
+
   def seed(self, seed: int):
     _C.check(self.lib.edhmc_seed(self._h, C.c_uint64(int(seed) & (2**64 - 1))))
 

@@ -21,7 +21,7 @@ import numpy as np
 from . import _C
 from . import graph as _g
 from .engine import GLMSpec
-from .models import Bernoulli, Empirical, Normal, Poisson
+from .models import Bernoulli, Beta, Empirical, Normal, Poisson, TransformedDistribution
 from .models.random_variable import RandomVariable
 
 
@@ -38,9 +38,10 @@ class LatentSlot:
 class GLMModel:
   spec: GLMSpec
   x_node: Optional[_g.Tensor]  # Placeholder / Variable / Constant holding X, or None for the ones-design
-  y_rv: RandomVariable
+  y_rv: Optional[RandomVariable]  # None: no observed variable (the latents are sampled from their priors)
   slots: List[LatentSlot]
   n_rows: int
+  prior_kinds: Optional[np.ndarray] = None  # per latent dimension (edhmc_set_prior_kinds), None = all Normal
 
 
 def _unsupported(msg):
@@ -93,18 +94,58 @@ def _decompose(eta, latents):
   _unsupported("cannot interpret the likelihood's parameter as a linear predictor")
 
 
+def _prior_of(z):
+  """(kind, p0, p1) of the prior of latent z IN THE UNCONSTRAINED SPACE the sampler works in (hmc.py:132-159):
+  Normal(loc, scale) -> itself; Beta(a, b), moved to the real line through the inverse sigmoid -> kind 1 with the
+  log-det-Jacobian folded in; TransformedDistribution(Normal(loc, scale), Softplus) with support 'nonnegative', moved back
+  through the inverse softplus -> the base Normal again (the two Jacobians cancel)."""
+  if isinstance(z, Normal):
+    return _C.PRIOR_NORMAL, z.loc, z.scale
+  if isinstance(z, Beta):
+    return _C.PRIOR_BETA_LOGIT, z.concentration1, z.concentration0
+  if isinstance(z, TransformedDistribution) and isinstance(z.distribution, Normal):
+    from . import bijectors as tfb
+    if isinstance(z.bijector, tfb.Softplus) and getattr(z, "support", None) == 'nonnegative':
+      return _C.PRIOR_NORMAL, z.distribution.loc, z.distribution.scale
+  _unsupported("latent %s must have a Normal prior, a Beta prior, or be a Softplus-transformed Normal" % z.name)
+
+
 def recognize(latent_vars: dict, data: dict) -> GLMModel:
+  """latent_vars maps each ORIGINAL latent to the Empirical store of its unconstrained samples."""
   latents = list(latent_vars.keys())
   observed = [k for k in data.keys() if isinstance(k, RandomVariable)]
+  for z in latents:
+    if z.dtype != _g.float32:
+      _unsupported("only float32 is supported on this path (got %r)" % z.dtype)
+    if not isinstance(latent_vars[z], Empirical):
+      raise TypeError("Posterior approximation must consist of only Empirical random variables.")
+  if len(observed) == 0:
+    # no data: one scalar latent sampled from its prior (tests/inferences/inference_auto_transform_test.py:114-161)
+    if len(latents) != 1 or int(np.prod(tuple(latents[0].shape) or (1,))) != 1:
+      _unsupported("without observed variables exactly one scalar latent is supported")
+    z = latents[0]
+    kind, p0, p1 = _prior_of(z)
+    spec = GLMSpec(1, False, _C.BERNOULLI_LOGIT,
+                   np.asarray(_const_value(p0, "prior parameter"), np.float32).reshape(1),
+                   np.asarray(_const_value(p1, "prior parameter"), np.float32).reshape(1), 1.0)
+    kinds = np.array([kind], np.int32)
+    return GLMModel(spec, None, None, [LatentSlot(z, latent_vars[z], 0, 1, len(z.shape) == 0)], 0,
+                    kinds if kind != _C.PRIOR_NORMAL else None)
   if len(observed) != 1:
-    _unsupported("exactly one observed random variable is required, got %d" % len(observed))
+    _unsupported("at most one observed random variable is supported, got %d" % len(observed))
   y_rv = observed[0]
 
   lik_scale = 1.0
   if isinstance(y_rv, Bernoulli):
-    if y_rv.logits is None:
-      _unsupported("Bernoulli must be parameterised by logits")
-    family, eta = _C.BERNOULLI_LOGIT, y_rv.logits
+    if y_rv.logits is not None:
+      family, eta = _C.BERNOULLI_LOGIT, y_rv.logits
+    else:
+      # Bernoulli(probs=z) with z a (0,1)-valued latent sampled through the sigmoid: the logits ARE the unconstrained
+      # latent (inference_auto_transform_test.py:163-188, Beta-Bernoulli)
+      z = _as_latent(y_rv._probs, latents)
+      if z is None or not isinstance(z, Beta):
+        _unsupported("Bernoulli must be parameterised by logits, or by probs = a Beta latent")
+      family, eta = _C.BERNOULLI_LOGIT, z
   elif isinstance(y_rv, Normal):
     family, eta = _C.NORMAL_IDENTITY, y_rv.loc
     sc = np.unique(_const_value(y_rv.scale, "the likelihood scale"))
@@ -123,12 +164,8 @@ def recognize(latent_vars: dict, data: dict) -> GLMModel:
   if len(used) != len(latents) or any(z not in used for z in latents):
     _unsupported("every latent variable must appear in the linear predictor (and nothing else may)")
   for z in used:
-    if not isinstance(z, Normal):
-      _unsupported("latent %s must have a Normal prior" % z.name)
-    if z.dtype != _g.float32:
-      _unsupported("only float32 is supported on this path (got %r)" % z.dtype)
-    if not isinstance(latent_vars[z], Empirical):
-      raise TypeError("Posterior approximation must consist of only Empirical random variables.")
+    if isinstance(z, Beta) and not (z is eta):
+      _unsupported("a Beta latent can only be the success probability of a Bernoulli likelihood")
 
   n_rows = int(y_rv.shape[0]) if len(y_rv.shape) >= 1 else 1
   if x_node is None:
@@ -148,14 +185,17 @@ def recognize(latent_vars: dict, data: dict) -> GLMModel:
   P = D + (1 if b is not None else 0)
   loc = np.zeros(P, np.float32)
   scale = np.ones(P, np.float32)
+  kinds = np.zeros(P, np.int32)
   slots = []
   off = 0
   for z, size in ((w, D), (b, 1)):
     if z is None:
       continue
-    loc[off:off + size] = np.broadcast_to(_const_value(z.loc, "prior loc"), tuple(z.shape) or ()).reshape(-1)
-    scale[off:off + size] = np.broadcast_to(_const_value(z.scale, "prior scale"), tuple(z.shape) or ()).reshape(-1)
+    kind, p0, p1 = _prior_of(z)
+    loc[off:off + size] = np.broadcast_to(_const_value(p0, "prior loc"), tuple(z.shape) or ()).reshape(-1)
+    scale[off:off + size] = np.broadcast_to(_const_value(p1, "prior scale"), tuple(z.shape) or ()).reshape(-1)
+    kinds[off:off + size] = kind
     slots.append(LatentSlot(z, latent_vars[z], off, size, len(z.shape) == 0))
     off += size
   spec = GLMSpec(D, b is not None, family, loc, scale, lik_scale)
-  return GLMModel(spec, x_node, y_rv, slots, n_rows)
+  return GLMModel(spec, x_node, y_rv, slots, n_rows, kinds if np.any(kinds != 0) else None)

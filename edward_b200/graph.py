@@ -151,6 +151,10 @@ class Tensor(object):
   def __neg__(self):
     return Mul(constant(-1.0, self.dtype), self)
 
+  def __getitem__(self, key):
+    probe = np.empty(tuple(d if d is not None else 1 for d in self.shape), np.bool_)[key]
+    return Lazy(lambda feed: self._eval(feed)[key], probe.shape, self.dtype, "StridedSlice", wants_feed=True)
+
   __array_priority__ = 100
 
 

@@ -53,11 +53,17 @@ class HMC(MonteCarlo):
                        "support then doing this is a no-op).")
     import torch
 
-    model = recognize(self.latent_vars, self.data)
+    # the sampler works in the unconstrained space (hmc.py:81-97,132-159): every original latent is paired with the
+    # Empirical store that holds its unconstrained samples
+    stores = {z: self.latent_vars_unconstrained[self.transformations.get(z, z)] for z in self.latent_vars}
+    model = recognize(stores, self.data)
     self._model = model
-    y_val = self.data[model.y_rv]
-    if isinstance(y_val, _g.Tensor):
-      y_val = _g.evaluate(y_val)
+    if model.y_rv is None:
+      y_val = np.zeros(0, np.int32)
+    else:
+      y_val = self.data[model.y_rv]
+      if isinstance(y_val, _g.Tensor):
+        y_val = _g.evaluate(y_val)
     self._y_value = y_val
     self._x_value = self._current_x({})
     self._x_key = self._x_identity(self._x_value)
@@ -110,6 +116,8 @@ class HMC(MonteCarlo):
                          n_rows_global=n_global)
     if sharded:
       sampler.init_comm(dist.get_world_size(), dist.get_rank())
+    if self._model.prior_kinds is not None:
+      sampler.set_prior_kinds(self._model.prior_kinds)
     if self._seed_value is None:
       bcast = None
       if sharded:
@@ -137,7 +145,7 @@ class HMC(MonteCarlo):
   def _current_x(self, feed_dict):
     model = self._model
     if model.x_node is None:
-      return np.ones((model.n_rows, 1), np.float32)
+      return np.ones((model.n_rows, 1), np.float32)  # a scalar latent used directly as the predictor; 0 rows = no data
     node = model.x_node
     if node in feed_dict:
       return feed_dict[node]

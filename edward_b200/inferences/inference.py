@@ -94,21 +94,31 @@ class Inference(abc.ABC):
       raise TypeError("scale must be a dict object.")
     self.scale = scale
 
-    # Latents with real support paired with Empirical ('points') posteriors need no transformation:
-    # transform(z) returns z itself (util/random_variables.py:909-910), so both maps are the identity.
+    # inference.py:223-264. map from original latent vars to unconstrained versions: a latent whose support differs
+    # from its posterior's is moved to the unconstrained space by ed.transform; an Empirical ('points') posterior is
+    # taken to already live there, and a constrained view of it (params pushed through the inverse map) is what
+    # `self.latent_vars[z]` returns afterwards.
     self.transformations = {}
     if auto_transform:
+      from ..models.empirical import Empirical
+      from ..util.random_variables import transform
       latent_vars = self.latent_vars.copy()
       self.latent_vars = {}
       self.latent_vars_unconstrained = {}
       for z, qz in latent_vars.items():
         if hasattr(z, 'support') and hasattr(qz, 'support') and z.support != qz.support and qz.support != 'point':
-          if z.support != 'real':
-            raise NotImplementedError("auto_transform of constrained latents (support=%r) is outside the "
-                                      "HMC/GLM path built here" % (z.support,))
-          self.transformations[z] = z
-          self.latent_vars_unconstrained[z] = qz
-          self.latent_vars[z] = qz
+          z_unconstrained = transform(z)
+          self.transformations[z] = z_unconstrained
+          if qz.support == "points":
+            qz_unconstrained = qz
+          else:
+            raise NotImplementedError("only Empirical posteriors are supported on this path")
+          self.latent_vars_unconstrained[z_unconstrained] = qz_unconstrained
+          if z_unconstrained is not z:
+            qz_constrained = Empirical(params=z_unconstrained.bijector.inverse(qz_unconstrained.params))
+          else:
+            qz_constrained = qz_unconstrained
+          self.latent_vars[z] = qz_constrained
         else:
           self.latent_vars[z] = qz
           self.latent_vars_unconstrained[z] = qz

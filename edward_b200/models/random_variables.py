@@ -123,3 +123,60 @@ class Poisson(RandomVariable):
       lam = self._rate_np()
       return y * np.log(lam) - lam - gammaln(y + 1.0)
     return _g.Lazy(fn, tuple(self.shape), self.dtype, "PoissonLogProb")
+
+
+class Beta(RandomVariable):
+  """Beta(concentration1, concentration0) — a latent with support (0, 1) (edward/models/random_variables.py:27-58 tags it
+  '01'); under auto_transform HMC samples it through a sigmoid (inference.py:223-264)."""
+  support = '01'
+
+  def __init__(self, concentration1=None, concentration0=None, validate_args=False, allow_nan_stats=True, name="Beta",
+               **kwargs):
+    self.concentration1 = _g.convert_to_tensor(concentration1)
+    self.concentration0 = _g.convert_to_tensor(concentration0, self.concentration1.dtype
+                                               if not isinstance(concentration0, _g.Tensor) else None)
+    self._args, self._kwargs = (concentration1, concentration0), dict(kwargs)
+    super(Beta, self).__init__(_bshape(self.concentration1, self.concentration0), (), self.concentration1.dtype, name=name,
+                               **kwargs)
+
+  def _ab(self, feed=None):
+    return _g.eval_in(self.concentration1, feed), _g.eval_in(self.concentration0, feed)
+
+  def _sample_np(self, sample_shape, feed=None):
+    a, b = self._ab(feed)
+    return np.random.beta(a, b, size=tuple(sample_shape) + tuple(self.batch_shape)).astype(self.dtype.np)
+
+  def log_prob(self, value):
+    from scipy.special import betaln
+    v = _g.convert_to_tensor(value, self.dtype)
+
+    def fn():
+      x = _g.evaluate(v)
+      a, b = self._ab()
+      return (a - 1.0) * np.log(x) + (b - 1.0) * np.log1p(-x) - betaln(a, b)
+    return _g.Lazy(fn, _bshape(v, self.concentration1), self.dtype, "BetaLogProb")
+
+  def mean(self):
+    return _g.Lazy(lambda: (lambda a, b: a / (a + b))(*self._ab()), tuple(self.batch_shape), self.dtype, "BetaMean")
+
+  def variance(self):
+    return _g.Lazy(lambda: (lambda a, b: a * b / ((a + b) ** 2 * (a + b + 1.0)))(*self._ab()), tuple(self.batch_shape),
+                   self.dtype, "BetaVariance")
+
+
+class TransformedDistribution(RandomVariable):
+  """TransformedDistribution(distribution, bijector): Y = bijector.forward(X), X ~ distribution
+  (tf.contrib.distributions.TransformedDistribution as Edward wraps it; the result of `ed.transform`,
+  util/random_variables.py:856-917). `support` is an instance attribute the caller may set."""
+
+  def __init__(self, distribution, bijector=None, validate_args=False, name="TransformedDistribution", **kwargs):
+    if bijector is None:
+      raise ValueError("TransformedDistribution needs a bijector")
+    self.distribution = distribution
+    self.bijector = bijector
+    self._args, self._kwargs = (distribution, bijector), dict(kwargs)
+    super(TransformedDistribution, self).__init__(tuple(distribution.batch_shape), tuple(distribution.event_shape),
+                                                  distribution.dtype, name=name, **kwargs)
+
+  def _sample_np(self, sample_shape, feed=None):
+    return np.asarray(self.bijector._forward_np(self.distribution._sample_np(sample_shape, feed)), self.dtype.np)

@@ -180,8 +180,23 @@ class _App(object):
 app = _App()
 
 
+def random_uniform(shape, minval=0.0, maxval=1.0, dtype=float32, seed=None):
+  dtype = _g.as_dtype(dtype)
+  shape = tuple(int(s) for s in shape)
+  return _g.Lazy(lambda: np.random.uniform(minval, maxval, size=shape), shape, dtype, "RandomUniform")
+
+
 class _Nn(object):
   sigmoid = staticmethod(sigmoid)
+
+  @staticmethod
+  def moments(x, axes, name=None):
+    """tf.nn.moments: (mean, population variance) over `axes`."""
+    x = convert_to_tensor(x)
+    ax = tuple(np.atleast_1d(axes).tolist())
+    shape = tuple(d for i, d in enumerate(x.shape) if i not in ax)
+    return (_g.Lazy(lambda: np.mean(_g.evaluate(x), axis=ax), shape, x.dtype, "Mean"),
+            _g.Lazy(lambda: np.var(_g.evaluate(x), axis=ax), shape, x.dtype, "Variance"))
 
   @staticmethod
   def softplus(x):
@@ -189,3 +204,18 @@ class _Nn(object):
 
 
 nn = _Nn()
+
+
+class _Namespace(object):
+  pass
+
+
+def _contrib():
+  from . import bijectors as _bij
+  c = _Namespace()
+  c.distributions = _Namespace()
+  c.distributions.bijectors = _bij
+  return c
+
+
+contrib = _contrib()  # tf.contrib.distributions.bijectors.{Softplus, Sigmoid, Invert}

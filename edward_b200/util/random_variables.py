@@ -1,6 +1,6 @@
 """check_data / check_latent_vars with the reference's error conventions
-(edward/util/random_variables.py:21-83). copy()/transform() are TF-graph rewrites and are not part of
-this path: HMC conditions the model through the GLM recogniser instead (edward_b200/glm.py)."""
+(edward/util/random_variables.py:21-83) and `transform` (:856-917). copy() is a TF-graph rewrite and is not part of this
+path: HMC conditions the model through the GLM recogniser instead (edward_b200/glm.py)."""
 from __future__ import annotations
 
 import numpy as np
@@ -72,3 +72,29 @@ def check_latent_vars(latent_vars):
       raise TypeError("Key-value pair in latent_vars does not have same shape: {}, {}".format(key.shape, value.shape))
     elif key.dtype != value.dtype:
       raise TypeError("Key-value pair in latent_vars does not have same dtype: {}, {}".format(key.dtype, value.dtype))
+
+
+def transform(x, *args, **kwargs):
+  """util/random_variables.py:856-917: the default map of a continuous random variable to the unconstrained space —
+  (0,1) through the inverse sigmoid, (0,inf) through the inverse softplus, the real line unchanged."""
+  from .. import bijectors as tfb
+  from ..models.random_variables import TransformedDistribution
+  if len(args) != 0 or kwargs.get('bijector', None) is not None:
+    return TransformedDistribution(x, *args, **kwargs)
+  try:
+    support = x.support
+  except AttributeError:
+    raise AttributeError("'{}' object has no 'support' so cannot be transformed.".format(type(x).__name__))
+  if support == '01':
+    bij, new_support = tfb.Invert(tfb.Sigmoid()), 'real'
+  elif support == 'nonnegative':
+    bij, new_support = tfb.Invert(tfb.Softplus()), 'real'
+  elif support in ('real', 'multivariate_real'):
+    return x
+  elif support == 'simplex':
+    raise NotImplementedError("simplex-valued latents are outside the HMC/GLM path built here")
+  else:
+    raise ValueError("'transform' does not handle supports of type '{}'".format(support))
+  new_x = TransformedDistribution(x, bij, *args, **kwargs)
+  new_x.support = new_support
+  return new_x

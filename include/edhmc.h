@@ -125,6 +125,14 @@ int edhmc_logp_grad(edhmc_t* h, const float* theta, double* logp, float* grad, v
 int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int64_t n_iter,
               float step_size, int32_t n_steps, const float* r0, const float* u, void* stream);
 
+/* Priors of constrained latents (reference: auto_transform, inference.py:223-264, hmc.py:132-159,
+ * util/random_variables.py:856-917). kinds_host[P]: 0 = Normal(loc, scale) (default), 1 = a latent with support (0,1)
+ * and a Beta(a = prior_loc, b = prior_scale) prior, sampled in the unconstrained space u = logit(z) with the
+ * log-det-Jacobian of the sigmoid folded into the log joint: log p(u) = a log sigmoid(u) + b log sigmoid(-u) - lbeta(a,b).
+ * The Empirical rows hold u, as the reference's do; the front-end maps them back with the bijector. A Bernoulli(probs=z)
+ * likelihood of such a latent is the Bernoulli-logit family with logits u. NULL restores all-Normal. Single chain only. */
+int edhmc_set_prior_kinds(edhmc_t* h, const int32_t* kinds_host);
+
 /* Optional per-transition trace for parity tests. Both may be NULL (default).
  *   trace_scalars [n_iter, 8] float64: {logp_old, logp_new, K_old, K_new, ratio, log_u, accept, reserved}
  *   trace_pos     [n_iter, P] float32: proposed position z_L of each transition. */

@@ -40,6 +40,7 @@ class GLMSpec:
   prior_loc: Optional[np.ndarray] = None    # [P]
   prior_scale: Optional[np.ndarray] = None  # [P]
   lik_scale: float = 1.0                    # Normal-identity only
+  prior_kind: Optional[np.ndarray] = None   # [P] 0 Normal(loc, scale); 1 Beta(a=loc, b=scale) latent sampled through a sigmoid
 
   def __post_init__(self):
     P = self.n_params
@@ -49,6 +50,8 @@ class GLMSpec:
       self.prior_scale = np.ones(P, np.float32)
     self.prior_loc = np.asarray(self.prior_loc, np.float32).reshape(P)
     self.prior_scale = np.asarray(self.prior_scale, np.float32).reshape(P)
+    if self.prior_kind is not None:
+      self.prior_kind = np.asarray(self.prior_kind, np.int32).reshape(P)
 
   @property
   def n_params(self) -> int:
@@ -92,6 +95,55 @@ def normal_log_prob_grad(x, loc, scale, dtype):
   scale = np.asarray(scale, dtype)
   z = (x - loc) / scale
   return (dtype(-0.5) * (dtype(2.0) * z)) / scale
+
+
+def beta_logit_log_prob(u, a, b, dtype):
+  """Density, in the unconstrained space u = logit(z), of a latent z ~ Beta(a, b) moved there by `ed.transform`
+  (util/random_variables.py:895-897: TransformedDistribution(z, Invert(Sigmoid()))), as HMC._log_joint_unconstrained
+  evaluates it (hmc.py:132-159): [TF 1.5] Beta._log_prob(z) = (a-1) log z + (b-1) log1p(-z) - lbeta(a, b) at z = sigmoid(u)
+  plus the bijector's inverse_log_det_jacobian = log sigmoid(u) + log sigmoid(-u). Collected:
+  a log sigmoid(u) + b log sigmoid(-u) - lbeta(a, b)."""
+  from scipy.special import betaln
+  u = np.asarray(u, dtype)
+  a = np.asarray(a, dtype)
+  b = np.asarray(b, dtype)
+  ls_pos = np.minimum(u, 0) - np.log1p(np.exp(-np.abs(u)))
+  ls_neg = np.minimum(-u, 0) - np.log1p(np.exp(-np.abs(u)))
+  return (a * ls_pos + b * ls_neg - betaln(a, b)).astype(dtype)
+
+
+def beta_logit_log_prob_grad(u, a, b, dtype):
+  u = np.asarray(u, dtype)
+  a = np.asarray(a, dtype)
+  b = np.asarray(b, dtype)
+  return (a - (a + b) / (1 + np.exp(-u))).astype(dtype)
+
+
+def prior_log_prob(theta, spec, dtype):
+  """Sum over the latents of the prior log density in the unconstrained space (hmc.py:183-185 + :132-159)."""
+  theta = np.asarray(theta, dtype)
+  if spec.prior_kind is None:
+    return normal_log_prob(theta, spec.prior_loc, spec.prior_scale, dtype)
+  out = np.empty(spec.n_params, dtype)
+  for i in range(spec.n_params):
+    if spec.prior_kind[i] == 1:
+      out[i] = beta_logit_log_prob(theta[i], spec.prior_loc[i], spec.prior_scale[i], dtype)
+    else:
+      out[i] = normal_log_prob(theta[i], spec.prior_loc[i], spec.prior_scale[i], dtype)
+  return out
+
+
+def prior_log_prob_grad(theta, spec, dtype):
+  theta = np.asarray(theta, dtype)
+  if spec.prior_kind is None:
+    return normal_log_prob_grad(theta, spec.prior_loc, spec.prior_scale, dtype)
+  out = np.empty(spec.n_params, dtype)
+  for i in range(spec.n_params):
+    if spec.prior_kind[i] == 1:
+      out[i] = beta_logit_log_prob_grad(theta[i], spec.prior_loc[i], spec.prior_scale[i], dtype)
+    else:
+      out[i] = normal_log_prob_grad(theta[i], spec.prior_loc[i], spec.prior_scale[i], dtype)
+  return out
 
 
 def bernoulli_logit_log_prob(logits, y, dtype):
@@ -183,9 +235,10 @@ def log_joint(X, y, theta, spec: GLMSpec, dtype=np.float64):
   w, b = _split(theta, spec)
   D = spec.n_features
   lj = dtype(0.0)
-  lj = lj + np.sum(normal_log_prob(w, spec.prior_loc[:D], spec.prior_scale[:D], dtype), dtype=dtype)
+  pr = prior_log_prob(theta, spec, dtype)
+  lj = lj + np.sum(pr[:D], dtype=dtype)
   if spec.has_bias:
-    lj = lj + np.sum(normal_log_prob(b, spec.prior_loc[D], spec.prior_scale[D], dtype), dtype=dtype)
+    lj = lj + np.sum(pr[D:], dtype=dtype)
   eta = linear_predictor(X, theta, spec, dtype)
   lj = lj + np.sum(log_lik_terms(eta, y, spec, dtype), dtype=dtype)
   return dtype(lj)
@@ -203,7 +256,7 @@ def grad_log_joint(X, y, theta, spec: GLMSpec, dtype=np.float64):
   g[:D] = np.matmul(Xd.T, r[:, None]).reshape(-1)
   if spec.has_bias:
     g[D] = np.sum(r, dtype=dtype)
-  g = g + normal_log_prob_grad(theta, spec.prior_loc, spec.prior_scale, dtype)
+  g = g + prior_log_prob_grad(theta, spec, dtype)
   return g.astype(dtype)
 
 

@@ -200,3 +200,40 @@ def test_synthetic_data_is_shard_invariant():
   X, y, w = o.synth_data(N, D)
   X2, y2, _ = o.synth_data(N - 65536, D, row_start=65536)
   assert np.array_equal(X[65536:], X2) and np.array_equal(y[65536:], y2)
+
+
+def test_beta_logit_prior_matches_autodiff_of_the_literal_tf_expression():
+  """A Beta(a, b) latent moved to the real line by ed.transform (util/random_variables.py:895-897): the oracle's closed
+  form a log sigmoid(u) + b log sigmoid(-u) - lbeta against the literal composition [TF 1.5] Beta._log_prob(sigmoid(u)) +
+  Sigmoid.forward_log_det_jacobian(u) = -softplus(-u) - softplus(u), and its gradient against torch.autograd."""
+  import torch
+  from scipy.special import betaln
+  for a, b in ((1.0, 1.0), (4.0, 8.0), (0.5, 2.5)):
+    u = torch.linspace(-6, 6, 25, dtype=torch.float64, requires_grad=True)
+    z = torch.sigmoid(u)
+    lp = (a - 1.0) * torch.log(z) + (b - 1.0) * torch.log1p(-z) - float(betaln(a, b))
+    lp = lp + (-torch.nn.functional.softplus(-u) - torch.nn.functional.softplus(u))
+    (g,) = torch.autograd.grad(lp.sum(), u)
+    un = u.detach().numpy()
+    np.testing.assert_allclose(o.beta_logit_log_prob(un, a, b, np.float64), lp.detach().numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(o.beta_logit_log_prob_grad(un, a, b, np.float64), g.numpy(), rtol=1e-12, atol=1e-12)
+    # it is a density on the real line: integrates to one
+    grid = np.linspace(-40, 40, 400001)
+    assert abs(np.trapezoid(np.exp(o.beta_logit_log_prob(grid, a, b, np.float64)), grid) - 1.0) < 1e-6
+
+
+def test_oracle_beta_bernoulli_posterior_through_the_sigmoid():
+  """tests/inferences/inference_auto_transform_test.py:163-188 on the oracle: z ~ Beta(1,1), 10 Bernoulli(probs=z)
+  observations, HMC in logit space; the mapped-back samples have the moments of the exact Beta(4, 8) posterior."""
+  x_obs = np.asarray([0, 0, 1, 1, 0, 0, 0, 0, 0, 1], np.int32)
+  spec = o.GLMSpec(1, False, o.BERNOULLI_LOGIT, np.ones(1, np.float32), np.ones(1, np.float32), 1.0, prior_kind=np.array([1]))
+  X = np.ones((10, 1), np.float32)
+  T = 3000
+  r0, u = o.synth_draws(T, 1, seed=5)
+  params = np.zeros((T, 1))
+  infos, nacc = o.run(X, x_obs, params, r0, u, 1.0, 5, spec)
+  z = 1 / (1 + np.exp(-params[500:, 0]))
+  a, b = 1.0 + x_obs.sum(), 1.0 + (1 - x_obs).sum()
+  assert abs(z.mean() - a / (a + b)) < 0.02
+  assert abs(z.var() - a * b / ((a + b) ** 2 * (a + b + 1))) < 0.004
+  assert nacc > 0.5 * T
