@@ -16,7 +16,8 @@ EDHMC_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NONFINITE, ERR_RANGE, ERR_STATE, ERR_COMM, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 BERNOULLI_LOGIT, NORMAL_IDENTITY, POISSON_LOG = 0, 1, 2
 PRIOR_NORMAL, PRIOR_BETA_LOGIT = 0, 1
-Y_I32, Y_F32, Y_U8 = 0, 1, 2
+Y_I32, Y_F32, Y_U8, Y_F64 = 0, 1, 2, 3
+F32, F64 = 0, 1
 PLAN_AUTO, PLAN_PERSISTENT, PLAN_STEPWISE = 0, 1, 2
 
 EXPORTS = [
@@ -24,6 +25,7 @@ EXPORTS = [
     "edhmc_logp_grad", "edhmc_run", "edhmc_set_trace", "edhmc_read_state", "edhmc_reset", "edhmc_seed",
     "edhmc_comm_unique_id", "edhmc_comm_init", "edhmc_peer_export", "edhmc_peer_attach", "edhmc_peer_detach", "edhmc_plan_info",
     "edhmc_sgmcmc_run", "edhmc_run_chains", "edhmc_logp_grad_chains", "edhmc_read_chain_state", "edhmc_set_chain_trace", "edhmc_set_chain_debug", "edhmc_chains_plan_probe", "edhmc_set_timeline", "edhmc_probe_read", "edhmc_comm_cached", "edhmc_comm_release", "edhmc_set_prior_kinds",
+    "edhmc_bind_data_f64", "edhmc_logp_grad_f64", "edhmc_run_f64", "edhmc_set_trace_f64",
 ]
 
 
@@ -57,7 +59,8 @@ class Cfg(C.Structure):
       ("plan", C.c_int32),
       ("debug", C.c_int32),
       ("n_chains", C.c_int32),
-      ("reserved", C.c_int32 * 4),
+      ("dtype", C.c_int32),
+      ("reserved", C.c_int32 * 3),
   ]
 
 
@@ -104,6 +107,10 @@ def lib():
   L.edhmc_comm_cached.argtypes = [i32, i32, i32]
   L.edhmc_comm_release.argtypes = [i32]
   L.edhmc_set_prior_kinds.argtypes = [vp, C.POINTER(i32)]
+  L.edhmc_bind_data_f64.argtypes = [vp, vp, vp, C.c_int, vp]
+  L.edhmc_logp_grad_f64.argtypes = [vp, vp, vp, vp, vp]
+  L.edhmc_run_f64.argtypes = [vp, vp, i64, i64, i64, i64, C.c_double, i32, vp, vp, vp]
+  L.edhmc_set_trace_f64.argtypes = [vp, vp, vp]
   for name in EXPORTS:
     if name not in ("edhmc_last_error",):
       getattr(L, name).restype = C.c_int

@@ -14,6 +14,7 @@
 #include "chain_small.cuh"
 #include "chains.cuh"
 #include "chains_wide.cuh"
+#include "f64.cuh"
 
 using namespace edhmc;
 
@@ -207,6 +208,11 @@ struct edhmc_handle {
   // stats
   long long passes_last = 0, launches_last = 0;
   int plan_in_use = 0;
+  // float64 models (f64.cuh)
+  bool f64 = false;
+  const double* X64 = nullptr;
+  double *d64_zcur = nullptr, *d64_gcur = nullptr, *d64_z = nullptr, *d64_r = nullptr, *d64_g = nullptr, *d64_partials = nullptr;
+  double *trace_scalars64 = nullptr, *trace_pos64 = nullptr;
   bool no_cta_ring = false;  // y is not 16-byte aligned: the CTA-wide ring (bulk copies of y) cannot be used
   long long* timeline = nullptr;
   int tl_cap = 0;
@@ -214,6 +220,13 @@ struct edhmc_handle {
 
 // Shared-memory bank-conflict degree of the row loads for G lanes per row, vectors of V floats, row stride
 // ldx floats: lanes of one LDS phase (32/V lanes) hit bank groups of V words; returns the worst multiplicity.
+// warps per CTA of the float64 pass: as many (<= 8) as fit their [P+1] double slices in shared memory
+static int pass64_warps(int P) {
+  const size_t per_warp = static_cast<size_t>(P + 1) * sizeof(double);
+  size_t nw = (200u << 10) / per_warp;
+  return nw >= 8 ? 8 : static_cast<int>(nw);
+}
+
 static cudaError_t h_alloc(edhmc_handle* h, void** p, size_t bytes) {
   const size_t need = (bytes + 255) / 256 * 256;
   if (h->arena && h->arena_used + need <= h->arena_cap) {
@@ -552,11 +565,20 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   if (cfg->ldx < cfg->n_features) return fail(EDHMC_ERR_INVALID, "ldx (%lld) < n_features (%d)", (long long)cfg->ldx, cfg->n_features);
   if (cfg->ldx > (1 << 20)) return fail(EDHMC_ERR_INVALID, "ldx too large");
   if (cfg->family < 0 || cfg->family > 2) return fail(EDHMC_ERR_INVALID, "unknown family %d", cfg->family);
-  if (cfg->y_dtype < 0 || cfg->y_dtype > 2) return fail(EDHMC_ERR_INVALID, "unknown y_dtype %d", cfg->y_dtype);
+  if (cfg->dtype != EDHMC_F32 && cfg->dtype != EDHMC_F64) return fail(EDHMC_ERR_INVALID, "unknown dtype %d", cfg->dtype);
+  if (cfg->y_dtype < 0 || cfg->y_dtype > 3) return fail(EDHMC_ERR_INVALID, "unknown y_dtype %d", cfg->y_dtype);
+  if (cfg->dtype == EDHMC_F64) {
+    if (cfg->y_dtype != EDHMC_Y_I32 && cfg->y_dtype != EDHMC_Y_F64) return fail(EDHMC_ERR_INVALID, "float64 models take int32 or float64 y");
+    if (cfg->n_chains > 1) return fail(EDHMC_ERR_INVALID, "vectorised chains are float32 only");
+    if (pass64_warps(cfg->n_features + (cfg->has_bias ? 1 : 0)) < 1)
+      return fail(EDHMC_ERR_INVALID, "float64 models support up to 25,000 latent dimensions");
+  } else if (cfg->y_dtype == EDHMC_Y_F64) {
+    return fail(EDHMC_ERR_INVALID, "float64 y needs a float64 model");
+  }
   if (cfg->family == EDHMC_NORMAL_IDENTITY && !(cfg->lik_scale > 0.0f))
     return fail(EDHMC_ERR_INVALID, "lik_scale must be > 0 for the Normal family");
   if (!cfg->prior_loc_host || !cfg->prior_scale_host) return fail(EDHMC_ERR_INVALID, "prior arrays are required");
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 3; ++i)
     if (cfg->reserved[i] != 0) return fail(EDHMC_ERR_INVALID, "reserved fields must be zero");
   if (cfg->n_chains > 1) {
     if (cfg->n_chains % kMcChainsPerCta != 0)
@@ -594,7 +616,8 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
     delete h;
     return fail(EDHMC_ERR_CUDA, "cudaDeviceGetAttribute failed");
   }
-  int rc = make_plan(h);
+  h->f64 = cfg->dtype == EDHMC_F64;
+  int rc = h->f64 ? 0 : make_plan(h);
   if (rc) {
     delete h;
     return rc;
@@ -609,7 +632,7 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   } while (0)
   const size_t pb = static_cast<size_t>(P) * sizeof(float);
   {
-    const size_t cap = static_cast<size_t>(2) * h->num_sms * (P + 1) * sizeof(double) + 24 * (static_cast<size_t>(P) + 64) * sizeof(double) + 65536;
+    const size_t cap = static_cast<size_t>(2) * h->num_sms * (P + 1) * sizeof(double) + 40 * (static_cast<size_t>(P) + 64) * sizeof(double) + 65536;
     if (cudaMalloc(reinterpret_cast<void**>(&h->arena), cap) == cudaSuccess) {
       h->arena_cap = cap;
     } else {
@@ -631,6 +654,21 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   ALLOC(h->d_ticket, sizeof(unsigned int));
   ALLOC(h->d_sums, static_cast<size_t>(P + 1) * sizeof(double));
   ALLOC(h->d_bad, sizeof(unsigned long long));
+  if (h->f64) {
+    const size_t pd = static_cast<size_t>(P) * sizeof(double);
+    ALLOC(h->d64_zcur, pd);
+    ALLOC(h->d64_gcur, pd);
+    ALLOC(h->d64_z, pd);
+    ALLOC(h->d64_r, pd);
+    ALLOC(h->d64_g, pd);
+    ALLOC(h->d64_partials, static_cast<size_t>(h->num_sms) * 4 * (P + 1) * sizeof(double));
+    if (cudaFuncSetAttribute(k64_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10) != cudaSuccess) {
+      edhmc_destroy(h);
+      return fail(EDHMC_ERR_CUDA, "cudaFuncSetAttribute(k64_pass) failed");
+    }
+    cudaMemset(h->d64_zcur, 0, pd);
+    cudaMemset(h->d64_gcur, 0, pd);
+  }
   if (cfg->n_chains > 1) {
     h->C = cfg->n_chains;
     h->mc_Dp = (cfg->n_features + 7) / 8 * 8;
@@ -767,6 +805,12 @@ int edhmc_destroy(edhmc_t* h) {
   h_free(h, h->d_ticket);
   h_free(h, h->d_sums);
   h_free(h, h->d_bad);
+  h_free(h, h->d64_zcur);
+  h_free(h, h->d64_gcur);
+  h_free(h, h->d64_z);
+  h_free(h, h->d64_r);
+  h_free(h, h->d64_g);
+  h_free(h, h->d64_partials);
   h_free(h, h->y_owned);
   h_free(h, h->mc_z);
   h_free(h, h->mc_r);
@@ -800,6 +844,7 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   if (h->cfg.n_rows > 0 && (!X || !y)) return fail(EDHMC_ERR_INVALID, "X and y are required");
+  if (h->f64) return fail(EDHMC_ERR_INVALID, "float64 model: use edhmc_bind_data_f64");
   if (reinterpret_cast<uintptr_t>(X) % 16 != 0) return fail(EDHMC_ERR_INVALID, "X must be 16-byte aligned");
   if (h->cfg.y_dtype != EDHMC_Y_U8 && reinterpret_cast<uintptr_t>(y) % 4 != 0)
     return fail(EDHMC_ERR_INVALID, "y must be 4-byte aligned");
@@ -861,11 +906,150 @@ static int allreduce_sums(edhmc_handle* h, cudaStream_t stream) {
   return 0;
 }
 
+// ---- float64 models (f64.cuh): the stepwise schedule in double ----
+static void fill_args64(edhmc_handle* h, K64Args& a) {
+  memset(&a, 0, sizeof(a));
+  const edhmc_cfg& c = h->cfg;
+  a.X = h->X64;
+  a.y = h->y;
+  a.n_rows = c.n_rows;
+  a.ldx = c.ldx;
+  a.D = c.n_features;
+  a.P = h->P;
+  a.has_bias = c.has_bias;
+  a.family = c.family;
+  a.y_is_f64 = c.y_dtype == EDHMC_Y_F64 ? 1 : 0;
+  a.lik_scale = c.lik_scale;
+  a.prior_loc = h->d_prior_loc;
+  a.prior_scale = h->d_prior_scale;
+  a.prior_kind = h->d_prior_kind;
+  a.prior_const = h->prior_const;
+  a.sums = h->d_sums;
+  a.sc = h->d_sc;
+  a.zcur = h->d64_zcur;
+  a.gcur = h->d64_gcur;
+  a.z = h->d64_z;
+  a.r = h->d64_r;
+  a.g = h->d64_g;
+  a.seed = h->seed;
+  a.trace_scalars = h->trace_scalars64;
+  a.trace_pos = h->trace_pos64;
+}
+
+static int pass64(edhmc_handle* h, const K64Args& a, const double* theta, int gate, cudaStream_t stream) {
+  const int nw = pass64_warps(a.P);
+  long long want = (a.n_rows + 8 * nw - 1) / (8 * nw);
+  if (want < 1) want = 1;
+  const int grid = static_cast<int>(want < h->num_sms * 4 ? want : h->num_sms * 4);
+  const size_t smem = static_cast<size_t>(nw) * (a.P + 1) * sizeof(double);
+  k64_pass<<<grid, nw * 32, smem, stream>>>(a, theta, h->d64_partials, gate);
+  k64_reduce<<<(a.P + 1 + 255) / 256, 256, 0, stream>>>(h->d64_partials, grid, a.P + 1, a.sums, a.sc, gate);
+  CUDA_TRY(cudaGetLastError());
+  h->launches_last += 2;
+  return allreduce_sums(h, stream);
+}
+
+static int run64(edhmc_handle* h, double* params, int64_t ldp, int64_t t0, int64_t n_iter, double eps, int32_t n_steps,
+                 const double* r0, const double* u, cudaStream_t stream) {
+  K64Args a;
+  fill_args64(h, a);
+  a.params = params;
+  a.ldp = ldp;
+  a.t0 = t0;
+  a.n_iter = n_iter;
+  a.eps = eps;
+  a.L = n_steps;
+  a.r0 = r0;
+  a.u = u;
+  h->launches_last = 0;
+  h->passes_last = n_iter * n_steps;
+  h->plan_in_use = EDHMC_PLAN_STEPWISE;
+  k64_check<<<1, kChainThreads, 0, stream>>>(a);
+  if (int rc = pass64(h, a, h->d64_zcur, 1, stream)) return rc;
+  k64_init_finish<<<1, kChainThreads, 0, stream>>>(a);
+  for (int64_t it = 0; it < n_iter; ++it) {
+    k64_begin<<<1, kChainThreads, 0, stream>>>(a, it);
+    for (int s = 0; s < n_steps; ++s) {
+      if (int rc = pass64(h, a, h->d64_z, 0, stream)) return rc;
+      k64_leap<<<1, kChainThreads, 0, stream>>>(a, it, s);
+    }
+    h->launches_last += 1 + n_steps;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int edhmc_bind_data_f64(edhmc_t* h, const double* X, const void* y, int check_finite, void* stream_) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  if (!h->f64) return fail(EDHMC_ERR_INVALID, "float32 model: use edhmc_bind_data");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (h->cfg.n_rows > 0 && (!X || !y)) return fail(EDHMC_ERR_INVALID, "X and y are required");
+  if (reinterpret_cast<uintptr_t>(X) % 8 != 0) return fail(EDHMC_ERR_INVALID, "X must be 8-byte aligned");
+  h->X64 = X;
+  h->y = y;
+  h->bound = true;
+  CUDA_TRY(cudaMemsetAsync(&h->d_sc->valid, 0, sizeof(int), stream));
+  if (check_finite && h->cfg.n_rows > 0) {
+    CUDA_TRY(cudaMemsetAsync(h->d_bad, 0, sizeof(unsigned long long), stream));
+    k64_check_finite<<<h->num_sms * 4, 256, 0, stream>>>(h->X64, h->cfg.n_rows, h->cfg.ldx, h->cfg.n_features, y,
+                                                        h->cfg.y_dtype == EDHMC_Y_F64 ? 1 : 0, h->d_bad);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, h->d_bad, sizeof(bad), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (bad) {
+      h->bound = false;
+      return fail(EDHMC_ERR_NONFINITE, "Tensor had NaN or Inf values (%llu non-finite entries in X/y)", bad);
+    }
+  }
+  return 0;
+}
+
+int edhmc_logp_grad_f64(edhmc_t* h, const double* theta, double* logp, double* grad, void* stream_) {
+  if (!h || !theta || !logp || !grad) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (!h->f64) return fail(EDHMC_ERR_INVALID, "float32 model: use edhmc_logp_grad");
+  if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data_f64 has not been called");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  K64Args a64;
+  fill_args64(h, a64);
+  h->launches_last = 0;
+  h->passes_last = 1;
+  if (int rc = pass64(h, a64, theta, 0, stream)) return rc;
+  k64_logp_grad_finish<<<1, kChainThreads, 0, stream>>>(a64, theta, logp, grad);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int edhmc_run_f64(edhmc_t* h, double* params, int64_t ldp, int64_t T, int64_t t0, int64_t n_iter, double step_size,
+                  int32_t n_steps, const double* r0, const double* u, void* stream_) {
+  if (!h || !params) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (!h->f64) return fail(EDHMC_ERR_INVALID, "float32 model: use edhmc_run");
+  if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data_f64 has not been called");
+  if (ldp < h->P) return fail(EDHMC_ERR_INVALID, "ldp (%lld) < number of latent dimensions (%d)", (long long)ldp, h->P);
+  if (n_steps < 0 || n_iter < 0 || t0 < 0) return fail(EDHMC_ERR_INVALID, "negative n_steps / n_iter / t0");
+  if (t0 + n_iter > T)
+    return fail(EDHMC_ERR_RANGE, "indices[0] = %lld is not in [0, %lld)", (long long)(t0 + n_iter - 1), (long long)T);
+  if (n_iter == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (int rc = run64(h, params, ldp, t0, n_iter, step_size, n_steps, r0, u, stream)) return rc;
+  if (h->cfg.debug) {
+    ChainScalars sc;
+    CUDA_TRY(cudaMemcpyAsync(&sc, h->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (sc.nonfinite) return fail(EDHMC_ERR_NONFINITE, "log joint density had NaN or Inf values");
+  }
+  return 0;
+}
+
 int edhmc_logp_grad(edhmc_t* h, const float* theta, double* logp, float* grad, void* stream_) {
   if (!h || !theta || !logp || !grad) return fail(EDHMC_ERR_INVALID, "null argument");
   if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data has not been called");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (h->f64) return fail(EDHMC_ERR_INVALID, "float64 model: use edhmc_logp_grad_f64");
   h->launches_last = 0;
   h->passes_last = 1;
   KArgs a;
@@ -883,6 +1067,7 @@ int edhmc_logp_grad(edhmc_t* h, const float* theta, double* logp, float* grad, v
 int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int64_t n_iter, float step_size,
               int32_t n_steps, const float* r0, const float* u, void* stream_) {
   if (!h || !params) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (h->f64) return fail(EDHMC_ERR_INVALID, "float64 model: use edhmc_run_f64");
   if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data has not been called");
   if (ldp < h->P) return fail(EDHMC_ERR_INVALID, "ldp (%lld) < number of latent dimensions (%d)", (long long)ldp, h->P);
   if (n_steps < 0 || n_iter < 0 || t0 < 0) return fail(EDHMC_ERR_INVALID, "negative n_steps / n_iter / t0");
@@ -954,6 +1139,13 @@ int edhmc_set_trace(edhmc_t* h, double* trace_scalars, float* trace_pos) {
   if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
   h->trace_scalars = trace_scalars;
   h->trace_pos = trace_pos;
+  return 0;
+}
+
+int edhmc_set_trace_f64(edhmc_t* h, double* trace_scalars, double* trace_pos) {
+  if (!h) return fail(EDHMC_ERR_INVALID, "null handle");
+  h->trace_scalars64 = trace_scalars;
+  h->trace_pos64 = trace_pos;
   return 0;
 }
 
@@ -1159,6 +1351,7 @@ int edhmc_sgmcmc_run(edhmc_t* h, int32_t kind, float* params, int64_t ldp, int64
   if (!h || !params) return fail(EDHMC_ERR_INVALID, "null argument");
   if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data has not been called");
   if (kind != 0 && kind != 1) return fail(EDHMC_ERR_INVALID, "kind must be 0 (SGLD) or 1 (SGHMC)");
+  if (h->f64) return fail(EDHMC_ERR_INVALID, "SGLD / SGHMC are float32 only");
   if (kind == 1 && !velocity) return fail(EDHMC_ERR_INVALID, "SGHMC needs a velocity buffer");
   if (ldp < h->P) return fail(EDHMC_ERR_INVALID, "ldp (%lld) < number of latent dimensions (%d)", (long long)ldp, h->P);
   if (n_iter < 0 || t0 < 0) return fail(EDHMC_ERR_INVALID, "negative n_iter / t0");

@@ -48,28 +48,36 @@ def _stream_ptr(dev) -> int:
 
 
 _Y_DTYPES = {torch.int32: _C.Y_I32, torch.float32: _C.Y_F32, torch.uint8: _C.Y_U8}
+_Y_DTYPES_F64 = {torch.int32: _C.Y_I32, torch.float64: _C.Y_F64}
 
 
 class GLMSampler:
   """One chain of HMC over a GLM. Row-sharded when `comm` (a torch.distributed group spec) is given."""
 
   def __init__(self, spec: GLMSpec, X, y, device=None, plan: int = _C.PLAN_AUTO, debug: bool = False,
-               check_finite: bool = True, n_rows_global: Optional[int] = None, n_chains: int = 1):
+               check_finite: bool = True, n_rows_global: Optional[int] = None, n_chains: int = 1, dtype=torch.float32):
+    """`dtype` torch.float64 selects the compact float64 path (edhmc_dtype, hmc_test.py:93-97): X, params, draws and
+    gradients are then double; one chain, HMC only."""
     self.lib = _C.lib()
     self.dev = _require_cuda(device)
     self.spec = spec
+    if dtype not in (torch.float32, torch.float64):
+      raise TypeError("dtype must be torch.float32 or torch.float64, got %r" % (dtype,))
+    self.dtype = dtype
+    f64 = dtype == torch.float64
     P = spec.n_params
     loc = np.zeros(P, np.float32) if spec.prior_loc is None else np.ascontiguousarray(spec.prior_loc, np.float32).reshape(P)
     scale = np.ones(P, np.float32) if spec.prior_scale is None else np.ascontiguousarray(spec.prior_scale, np.float32).reshape(P)
-    self.X = self._to_device(X, torch.float32)
+    self.X = self._to_device(X, dtype)
     if self.X.dim() != 2 or self.X.shape[1] != spec.n_features:
       raise TypeError("X must have shape [N, %d], got %s" % (spec.n_features, tuple(self.X.shape)))
     if self.X.stride(1) != 1 or self.X.data_ptr() % 16 != 0:
       self.X = self.X.contiguous()
     yt = y if isinstance(y, torch.Tensor) else torch.as_tensor(np.asarray(y))
-    if yt.dtype not in _Y_DTYPES:
+    ymap = _Y_DTYPES_F64 if f64 else _Y_DTYPES
+    if yt.dtype not in ymap:
       # the reference casts observed data to the random variable's dtype (inference.py:88-95)
-      yt = yt.to(torch.int32 if spec.family != _C.NORMAL_IDENTITY else torch.float32)
+      yt = yt.to(torch.int32 if spec.family != _C.NORMAL_IDENTITY else dtype)
     self.y = yt.to(self.dev).contiguous()
     if self.y.dim() != 1 or self.y.shape[0] != self.X.shape[0]:
       raise TypeError("y must have shape [%d], got %s" % (self.X.shape[0], tuple(self.y.shape)))
@@ -83,7 +91,8 @@ class GLMSampler:
     cfg.ldx = int(self.X.stride(0)) if self.n_rows > 1 else max(int(self.X.stride(0)), spec.n_features)
     cfg.has_bias = 1 if spec.has_bias else 0
     cfg.family = int(spec.family)
-    cfg.y_dtype = _Y_DTYPES[self.y.dtype]
+    cfg.y_dtype = ymap[self.y.dtype]
+    cfg.dtype = _C.F64 if f64 else _C.F32
     cfg.lik_scale = float(spec.lik_scale)
     cfg.prior_loc_host = loc.ctypes.data_as(C.POINTER(C.c_float))
     cfg.prior_scale_host = scale.ctypes.data_as(C.POINTER(C.c_float))
@@ -95,7 +104,8 @@ class GLMSampler:
     self._h = C.c_void_p()
     _C.check(self.lib.edhmc_create(C.byref(self._h), C.byref(cfg)))
     with torch.cuda.device(self.dev):
-      _C.check(self.lib.edhmc_bind_data(self._h, self.X.data_ptr(), self.y.data_ptr(), 1 if check_finite else 0,
+      bind = self.lib.edhmc_bind_data_f64 if f64 else self.lib.edhmc_bind_data
+      _C.check(bind(self._h, self.X.data_ptr(), self.y.data_ptr(), 1 if check_finite else 0,
                                         _stream_ptr(self.dev)))
     self._trace = None
     self.nranks = 1
@@ -163,37 +173,39 @@ class GLMSampler:
 
   # ---- evaluation ------------------------------------------------------------------------------
   def logp_grad(self, theta):
-    """log p(y, theta) (float64 scalar tensor) and its gradient (float32 [P]) — hmc.py:161-192,199."""
-    th = self._to_device(theta, torch.float32).contiguous().reshape(self.P)
+    """log p(y, theta) (float64 scalar tensor) and its gradient ([P], the model's dtype) — hmc.py:161-192,199."""
+    th = self._to_device(theta, self.dtype).contiguous().reshape(self.P)
     logp = torch.empty(1, dtype=torch.float64, device=self.dev)
-    grad = torch.empty(self.P, dtype=torch.float32, device=self.dev)
+    grad = torch.empty(self.P, dtype=self.dtype, device=self.dev)
     with torch.cuda.device(self.dev):
-      _C.check(self.lib.edhmc_logp_grad(self._h, th.data_ptr(), logp.data_ptr(), grad.data_ptr(), _stream_ptr(self.dev)))
+      fn = self.lib.edhmc_logp_grad_f64 if self.dtype == torch.float64 else self.lib.edhmc_logp_grad
+      _C.check(fn(self._h, th.data_ptr(), logp.data_ptr(), grad.data_ptr(), _stream_ptr(self.dev)))
     return logp, grad
 
   def run(self, params: torch.Tensor, t0: int, n_iter: int, step_size: float, n_steps: int,
           r0: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None):
-    """n_iter transitions in place on `params` [T, >=P] (device, float32, row-major)."""
-    if params.device != self.dev or params.dtype != torch.float32:
-      raise TypeError("params must be a float32 tensor on %s" % self.dev)
+    """n_iter transitions in place on `params` [T, >=P] (device, the model's dtype, row-major)."""
+    if params.device != self.dev or params.dtype != self.dtype:
+      raise TypeError("params must be a %s tensor on %s" % (str(self.dtype).replace("torch.", ""), self.dev))
     if params.dim() == 1:
       params = params.view(-1, 1)
     if params.stride(1) != 1:
       raise TypeError("params rows must be contiguous")
     r0p = up = None
     if r0 is not None:
-      r0 = self._to_device(r0, torch.float32).contiguous()
+      r0 = self._to_device(r0, self.dtype).contiguous()
       if r0.numel() < n_iter * self.P:
         raise ValueError("r0 must hold n_iter*P momentum draws")
       r0p = r0.data_ptr()
     if u is not None:
-      u = self._to_device(u, torch.float32).contiguous()
+      u = self._to_device(u, self.dtype).contiguous()
       if u.numel() < n_iter:
         raise ValueError("u must hold n_iter uniforms")
       up = u.data_ptr()
     with torch.cuda.device(self.dev):
-      _C.check(self.lib.edhmc_run(self._h, params.data_ptr(), int(params.stride(0)), int(params.shape[0]), int(t0),
-                                  int(n_iter), float(step_size), int(n_steps), r0p, up, _stream_ptr(self.dev)))
+      fn = self.lib.edhmc_run_f64 if self.dtype == torch.float64 else self.lib.edhmc_run
+      _C.check(fn(self._h, params.data_ptr(), int(params.stride(0)), int(params.shape[0]), int(t0),
+                  int(n_iter), float(step_size), int(n_steps), r0p, up, _stream_ptr(self.dev)))
 
   # ---- SGLD / SGHMC on the same gradient kernel (sgld.py:52-87, sghmc.py:58-96) -----------------
   def sgmcmc_run(self, kind: str, params: torch.Tensor, t0: int, n_iter: int, step_size: float, friction: float = 0.1,
@@ -269,9 +281,10 @@ class GLMSampler:
 
   def set_trace(self, n_iter: int):
     sc = torch.zeros(n_iter, 8, dtype=torch.float64, device=self.dev)
-    pos = torch.zeros(n_iter, self.P, dtype=torch.float32, device=self.dev)
+    pos = torch.zeros(n_iter, self.P, dtype=self.dtype, device=self.dev)
     self._trace = (sc, pos)
-    _C.check(self.lib.edhmc_set_trace(self._h, sc.data_ptr(), pos.data_ptr()))
+    fn = self.lib.edhmc_set_trace_f64 if self.dtype == torch.float64 else self.lib.edhmc_set_trace
+    _C.check(fn(self._h, sc.data_ptr(), pos.data_ptr()))
     return sc, pos
 
   def set_timeline(self, n_passes: int):
@@ -288,7 +301,8 @@ class GLMSampler:
 
   def clear_trace(self):
     self._trace = None
-    _C.check(self.lib.edhmc_set_trace(self._h, None, None))
+    fn = self.lib.edhmc_set_trace_f64 if self.dtype == torch.float64 else self.lib.edhmc_set_trace
+    _C.check(fn(self._h, None, None))
 
   def read_state(self):
     n = C.c_int64(0)
@@ -311,6 +325,8 @@ class GLMSampler:
     _C.check(self.lib.edhmc_seed(self._h, C.c_uint64(int(seed) & (2**64 - 1))))
 
   def plan_info(self) -> dict:
+    if self.dtype == torch.float64:
+      return {"plan_in_use": _C.PLAN_STEPWISE, "dtype": "f64"}
     out = (C.c_int64 * 11)()
     n = _C.check(self.lib.edhmc_plan_info(self._h, out, 11))
     keys = ["grid_ctas", "warps_per_cta", "ring_stages", "tile_rows", "lanes_per_row", "vec_width", "smem_bytes",

@@ -42,6 +42,7 @@ class GLMModel:
   slots: List[LatentSlot]
   n_rows: int
   prior_kinds: Optional[np.ndarray] = None  # per latent dimension (edhmc_set_prior_kinds), None = all Normal
+  dtype: str = "float32"  # "float32" (the hot path) or "float64" (hmc_test.py:93-97, the compact device path)
 
 
 def _unsupported(msg):
@@ -114,9 +115,11 @@ def recognize(latent_vars: dict, data: dict) -> GLMModel:
   """latent_vars maps each ORIGINAL latent to the Empirical store of its unconstrained samples."""
   latents = list(latent_vars.keys())
   observed = [k for k in data.keys() if isinstance(k, RandomVariable)]
+  dtypes = {z.dtype.name for z in latents}
+  if len(dtypes) != 1 or not dtypes <= {"float32", "float64"}:
+    _unsupported("the latent variables must share one dtype, float32 or float64 (got %s)" % sorted(dtypes))
+  dtype = dtypes.pop()
   for z in latents:
-    if z.dtype != _g.float32:
-      _unsupported("only float32 is supported on this path (got %r)" % z.dtype)
     if not isinstance(latent_vars[z], Empirical):
       raise TypeError("Posterior approximation must consist of only Empirical random variables.")
   if len(observed) == 0:
@@ -130,7 +133,7 @@ def recognize(latent_vars: dict, data: dict) -> GLMModel:
                    np.asarray(_const_value(p1, "prior parameter"), np.float32).reshape(1), 1.0)
     kinds = np.array([kind], np.int32)
     return GLMModel(spec, None, None, [LatentSlot(z, latent_vars[z], 0, 1, len(z.shape) == 0)], 0,
-                    kinds if kind != _C.PRIOR_NORMAL else None)
+                    kinds if kind != _C.PRIOR_NORMAL else None, dtype)
   if len(observed) != 1:
     _unsupported("at most one observed random variable is supported, got %d" % len(observed))
   y_rv = observed[0]
@@ -198,4 +201,4 @@ def recognize(latent_vars: dict, data: dict) -> GLMModel:
     slots.append(LatentSlot(z, latent_vars[z], off, size, len(z.shape) == 0))
     off += size
   spec = GLMSpec(D, b is not None, family, loc, scale, lik_scale)
-  return GLMModel(spec, x_node, y_rv, slots, n_rows, kinds if np.any(kinds != 0) else None)
+  return GLMModel(spec, x_node, y_rv, slots, n_rows, kinds if np.any(kinds != 0) else None, dtype)

@@ -84,7 +84,7 @@ class HMC(MonteCarlo):
         raise TypeError("Empirical random variables must be directly parameterized by a tf.Variable "
                         "for HMC to update them (hmc.py:66-70).")
       rows_max = max(rows_max, int(variables[0].shape[0]))
-    self._packed = torch.zeros(rows_max, P, dtype=torch.float32, device=self._sampler.dev)
+    self._packed = torch.zeros(rows_max, P, dtype=self._sampler.dtype, device=self._sampler.dev)
     for slot in model.slots:
       var = slot.qz.get_variables()[0]
       rows = int(var.shape[0])
@@ -113,7 +113,7 @@ class HMC(MonteCarlo):
       dist.all_reduce(cnt)
       n_global = int(cnt.item())
     sampler = GLMSampler(self._model.spec, x, self._y_value, device=dev, plan=self._plan, debug=self.debug,
-                         n_rows_global=n_global)
+                         n_rows_global=n_global, dtype=getattr(torch, self._model.dtype))
     if sharded:
       sampler.init_comm(dist.get_world_size(), dist.get_rank())
     if self._model.prior_kinds is not None:
@@ -145,7 +145,7 @@ class HMC(MonteCarlo):
   def _current_x(self, feed_dict):
     model = self._model
     if model.x_node is None:
-      return np.ones((model.n_rows, 1), np.float32)  # a scalar latent used directly as the predictor; 0 rows = no data
+      return np.ones((model.n_rows, 1), model.dtype)  # a scalar latent used directly as the predictor; 0 rows = no data
     node = model.x_node
     if node in feed_dict:
       return feed_dict[node]
@@ -222,7 +222,7 @@ class HMC(MonteCarlo):
 
   def load_state_dict(self, state):
     import torch
-    params = np.asarray(state["params"], np.float32)
+    params = np.asarray(state["params"], self._model.dtype)
     if tuple(params.shape) != tuple(self._packed.shape):
       raise ValueError("checkpoint params have shape %s, expected %s" % (params.shape, tuple(self._packed.shape)))
     self._packed.copy_(torch.as_tensor(params).to(self._packed.device))

@@ -41,6 +41,8 @@ class _SGMCMC(HMC):
   def build_update(self):
     train = super(_SGMCMC, self).build_update()
     model = self._model
+    if model.dtype != "float32":
+      raise NotImplementedError("SGLD / SGHMC run in float32 on this path (got %s latents)" % model.dtype)
     self._lik_factor = _scalar(self.scale.get(model.y_rv, 1.0), "the observed variable")
     pf = np.ones(model.spec.n_params, np.float32)
     for slot in model.slots:

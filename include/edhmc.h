@@ -58,8 +58,19 @@ typedef enum edhmc_family {
 typedef enum edhmc_ydtype {
   EDHMC_Y_I32 = 0, /* reference dtype of Bernoulli data (inference.py:88-95 casts to key.dtype=int32) */
   EDHMC_Y_F32 = 1,
-  EDHMC_Y_U8 = 2
+  EDHMC_Y_U8 = 2,
+  EDHMC_Y_F64 = 3  /* float64 models only */
 } edhmc_ydtype;
+
+/* Floating-point type of the model: X, theta, params, gradients, momentum / uniform draws. The hot path and every
+ * BASELINE configuration are float32. EDHMC_F64 serves the reference's float64 models (tests/inferences/hmc_test.py:93-97)
+ * through a compact device path (csrc/f64.cuh) with its own typed entry points: edhmc_bind_data_f64, edhmc_logp_grad_f64,
+ * edhmc_run_f64, edhmc_set_trace_f64 (y: EDHMC_Y_I32 or EDHMC_Y_F64). One chain, HMC only; the float32 entry points
+ * refuse a float64 handle and vice versa. */
+typedef enum edhmc_dtype {
+  EDHMC_F32 = 0,
+  EDHMC_F64 = 1
+} edhmc_dtype;
 
 /* Execution plan selector (all are CUDA paths; there is no CPU path). */
 typedef enum edhmc_plan {
@@ -84,7 +95,8 @@ typedef struct edhmc_cfg {
   int32_t debug;           /* 1: check log-joint/gradient for NaN/Inf after every run (inference.py:279-281) */
   int32_t n_chains;        /* 0 or 1: one chain (the reference). C > 1: C vectorised chains (extension; C % 128 == 0,
                               n_features <= 64, no bias) served by edhmc_run_chains / edhmc_logp_grad_chains */
-  int32_t reserved[4];     /* must be zero */
+  int32_t dtype;           /* edhmc_dtype */
+  int32_t reserved[3];     /* must be zero */
 } edhmc_cfg;
 
 typedef struct edhmc_handle edhmc_t;
@@ -137,6 +149,15 @@ int edhmc_set_prior_kinds(edhmc_t* h, const int32_t* kinds_host);
  *   trace_scalars [n_iter, 8] float64: {logp_old, logp_new, K_old, K_new, ratio, log_u, accept, reserved}
  *   trace_pos     [n_iter, P] float32: proposed position z_L of each transition. */
 int edhmc_set_trace(edhmc_t* h, double* trace_scalars, float* trace_pos);
+
+/* float64 models (cfg.dtype == EDHMC_F64; the reference runs its HMC tests in both dtypes, tests/inferences/hmc_test.py:93-97,
+ * with every tensor of hmc.py:61-130 a float64). Same semantics as the entry points above with X, theta, grad, params, the
+ * injected draws, the step size and trace_pos in double. X: 8-byte aligned. */
+int edhmc_bind_data_f64(edhmc_t* h, const double* X, const void* y, int check_finite, void* stream);
+int edhmc_logp_grad_f64(edhmc_t* h, const double* theta, double* logp, double* grad, void* stream);
+int edhmc_run_f64(edhmc_t* h, double* params, int64_t ldp, int64_t T, int64_t t0, int64_t n_iter, double step_size,
+                  int32_t n_steps, const double* r0, const double* u, void* stream);
+int edhmc_set_trace_f64(edhmc_t* h, double* trace_scalars, double* trace_pos);
 
 /* Counters owned by the handle: number of accepted proposals since the last reset
  * (MonteCarlo.n_accept, monte_carlo.py:100) and the cached log-joint of the current state.

@@ -123,9 +123,16 @@ def test_recogniser_rejects_everything_else():
     recognize({w: qw}, data)  # no observed variable
   w64 = Normal(loc=tf.zeros(2, dtype=tf.float64), scale=tf.ones(2, dtype=tf.float64))
   X64 = tf.placeholder(tf.float64, [10, 2])
-  with pytest.raises(NotImplementedError, match="float32"):
-    recognize({w64: Empirical(params=tf.Variable(tf.zeros([5, 2], dtype=tf.float64)))},
-              {X64: np.zeros((10, 2)), Bernoulli(logits=ed.dot(X64, w64)): np.zeros(10)})
+  # float64 models are recognised (hmc_test.py:93-97) ...
+  m64 = recognize({w64: Empirical(params=tf.Variable(tf.zeros([5, 2], dtype=tf.float64)))},
+                  {X64: np.zeros((10, 2)), Bernoulli(logits=ed.dot(X64, w64)): np.zeros(10)})
+  assert m64.dtype == "float64" and m64.spec.n_features == 2
+  # ... but latents of mixed dtypes are not
+  b32 = Normal(loc=tf.zeros(1), scale=tf.ones(1))
+  with pytest.raises(NotImplementedError, match="share one dtype"):
+    recognize({w64: Empirical(params=tf.Variable(tf.zeros([5, 2], dtype=tf.float64))),
+               b32: Empirical(params=tf.Variable(tf.zeros([5, 1])))},
+              {X64: np.zeros((10, 2)), Bernoulli(logits=ed.dot(X64, w64) + b32): np.zeros(10)})
   extra = Normal(loc=tf.zeros(2), scale=tf.ones(2))
   with pytest.raises(NotImplementedError):
     recognize({w: qw, extra: Empirical(params=tf.Variable(tf.zeros([5, 2])))},
