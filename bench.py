@@ -300,20 +300,42 @@ def timeline_of(torch, s, run_once, n_passes=48):
   if t.shape[0] < 4 or not np.any(t[:, :, 1]):
     return None
   wait = t[:, :, 8:16]
-  d = {
-      "unit": "SM cycles (clock64), median over CTAs and passes 8..%d of one launch" % (n_passes - 1),
-      "pass_tiles_and_cta_reduce": float(np.median(t[:, :, 1] - t[:, :, 0])),
-      "publish_partials": float(np.median(t[:, :, 2] - t[:, :, 1])),
-      "grid_barrier_wait_median": float(np.median(t[:, :, 3] - t[:, :, 2])),
-      "grid_barrier_wait_fastest_cta": float(np.median((t[:, :, 3] - t[:, :, 2]).min(axis=1))),
-      "grid_barrier_wait_slowest_cta": float(np.median((t[:, :, 3] - t[:, :, 2]).max(axis=1))),
-      "totals_ready_after_barrier": float(np.median(t[:, :, 4] - t[:, :, 3])),
-      "integrator": float(np.median(t[:, :, 5] - t[:, :, 4])),
-      "serial_section": float(np.median(t[:, :, 5] - t[:, :, 1])),
-      "step": float(np.median(t[1:, :, 0] - t[:-1, :, 0])),
-      "step_ns_globaltimer": float(np.median(t[1:, 0, 6] - t[:-1, 0, 6])),
-      "tile_wait_per_warp": float(np.median(wait[wait > 0])) if np.any(wait > 0) else 0.0,
-  }
+  step = float(np.median(t[1:, :, 0] - t[:-1, :, 0]))
+  if t.shape[1] > 1 and not np.any(t[:, 1:, 3]):
+    # leader protocol (chain.cuh): CTA 0 gathers the partials, integrates and sends the next position; the other CTAs
+    # publish their sums and poll for it. Slots 3..5 are stamped by the leader only.
+    lead, work = t[:, 0, :], t[:, 1:, :]
+    d = {
+        "unit": "SM cycles (clock64), median over passes 8..%d of one launch (workers: also over CTAs)" % (n_passes - 1),
+        "protocol": "leader (flag-in-data partials -> CTA 0 -> flag-in-data position)",
+        "pass_tiles_and_cta_reduce": float(np.median(work[:, :, 1] - work[:, :, 0])),
+        "publish_partials": float(np.median(work[:, :, 2] - work[:, :, 1])),
+        "worker_wait_for_next_position_median": float(np.median(work[1:, :, 0] - work[:-1, :, 2])),
+        "worker_wait_fastest_cta": float(np.median((work[1:, :, 0] - work[:-1, :, 2]).min(axis=1))),
+        "worker_wait_slowest_cta": float(np.median((work[1:, :, 0] - work[:-1, :, 2]).max(axis=1))),
+        "leader_gather_partials": float(np.median(lead[:, 4] - lead[:, 2])),
+        "leader_integrator_and_send": float(np.median(lead[:, 5] - lead[:, 4])),
+        "serial_section": float(np.median(work[1:, :, 0] - work[:-1, :, 1])),
+        "step": step,
+        "step_ns_globaltimer": float(np.median(t[1:, 0, 6] - t[:-1, 0, 6])),
+        "tile_wait_per_warp": float(np.median(wait[wait > 0])) if np.any(wait > 0) else 0.0,
+    }
+  else:
+    d = {
+        "unit": "SM cycles (clock64), median over CTAs and passes 8..%d of one launch" % (n_passes - 1),
+        "protocol": "grid barrier, every CTA reads every CTA's partials",
+        "pass_tiles_and_cta_reduce": float(np.median(t[:, :, 1] - t[:, :, 0])),
+        "publish_partials": float(np.median(t[:, :, 2] - t[:, :, 1])),
+        "grid_barrier_wait_median": float(np.median(t[:, :, 3] - t[:, :, 2])),
+        "grid_barrier_wait_fastest_cta": float(np.median((t[:, :, 3] - t[:, :, 2]).min(axis=1))),
+        "grid_barrier_wait_slowest_cta": float(np.median((t[:, :, 3] - t[:, :, 2]).max(axis=1))),
+        "totals_ready_after_barrier": float(np.median(t[:, :, 4] - t[:, :, 3])),
+        "integrator": float(np.median(t[:, :, 5] - t[:, :, 4])),
+        "serial_section": float(np.median(t[:, :, 5] - t[:, :, 1])),
+        "step": step,
+        "step_ns_globaltimer": float(np.median(t[1:, 0, 6] - t[:-1, 0, 6])),
+        "tile_wait_per_warp": float(np.median(wait[wait > 0])) if np.any(wait > 0) else 0.0,
+    }
   d["serial_fraction_of_step"] = d["serial_section"] / d["step"] if d["step"] > 0 else None
   return d
 

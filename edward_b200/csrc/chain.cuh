@@ -212,6 +212,83 @@ static __device__ __noinline__ bool wide_allreduce(const WideArgs a, unsigned lo
   return true;
 }
 
+// Leader protocol (one GPU, P+1 <= kWideCols): the serial section between two data passes runs on CTA 0 alone.
+//   worker CTA, end of pass p:   stores its float64 sums as flag-in-data entries {lo32, seq, hi32, seq} (no fence, no
+//                                counter) and goes straight to polling the position of pass p+1;
+//   group leader (every kLlGroup-th CTA): polls the entries of its group (its own included) until every one carries
+//                                seq(p), adds them in ascending order and publishes the group sum the same way (one CTA
+//                                gathering all 148 x (P+1) entries alone is bound by its 64 B/clk L2 port: 2,000+ cycles);
+//   leader (CTA 0):              polls the group sums, adds them in the order of reduce_partials, runs the integrator /
+//                                accept step and stores the next position as {float, seq(p+1)} words, which the workers'
+//                                lanes are polling.
+// Against "grid barrier + every CTA reads every CTA's partials + redundant integrator" this removes the release fence
+// and the counter round trip of the barrier, 147 of the 148 reads of the partials (which contend for the same L2
+// lines) and one L2 round trip between "totals known" and "next pass starts". Both buffers are double-buffered on the
+// parity of the pass; reuse is safe because entry p+2 of a CTA is only written after it has seen position p+2, which
+// the leader computes after it has consumed every entry of pass p+1 (and so of pass p).
+// The summation order is reduce_partials' (tree16 over the CTAs of a group, tree16 over the groups), so the persistent
+// and the stepwise plan stay bit-identical.
+// Level 1 (group leaders, CTA index % kLlGroup == 0): thread c tree-sums column c of its group's members (tree16, the
+// order of reduce_partials) and publishes the group sum as a flag-in-data entry.
+static __device__ __forceinline__ void ll_group_sum(const uint4* part, uint4* grp_out, int ncta, int ncol, unsigned int seq) {
+  const int g0 = blockIdx.x;  // first member
+  const int nm = min(kLlGroup, ncta - g0);
+  for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+    uint4 e[kLlGroup];
+#pragma unroll
+    for (int m = 0; m < kLlGroup; ++m)
+      e[m] = m < nm ? ld_relaxed_v4(part + static_cast<size_t>(g0 + m) * ncol + c) : make_uint4(0u, seq, 0u, seq);
+    bool again;
+    do {
+      again = false;
+#pragma unroll
+      for (int m = 0; m < kLlGroup; ++m) {
+        if (e[m].y != seq || e[m].w != seq) {
+          e[m] = ld_relaxed_v4(part + static_cast<size_t>(g0 + m) * ncol + c);
+          again = true;
+        }
+      }
+    } while (again);
+    double v[16];
+#pragma unroll
+    for (int m = 0; m < kLlGroup; ++m) v[m] = __hiloint2double(static_cast<int>(e[m].z), static_cast<int>(e[m].x));
+    const double s = tree16(v);
+    st_relaxed_v4(grp_out + c, make_uint4(static_cast<unsigned int>(__double2loint(s)), seq,
+                                          static_cast<unsigned int>(__double2hiint(s)), seq));
+  }
+}
+
+// Level 2 (CTA 0): thread c polls the group sums of column c (all loads in flight together), tree-sums them and owns
+// cta_acc[c] — the thread that goes on to compute latent c's gradient, so only the log-likelihood column needs a barrier.
+static __device__ __forceinline__ void ll_reduce_groups(const uint4* grp, int ngroups, int P, unsigned int seq, double* cta_acc,
+                                                     long long* dbg) {
+  const int ncol = P + 1;
+  for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+    if (dbg && threadIdx.x == 0) dbg[20] = clock64();
+    uint4 e[kLlMaxGroups];
+#pragma unroll
+    for (int g = 0; g < kLlMaxGroups; ++g)
+      e[g] = g < ngroups ? ld_relaxed_v4(grp + static_cast<size_t>(g) * ncol + c) : make_uint4(0u, seq, 0u, seq);
+    bool again;
+    do {
+      again = false;
+#pragma unroll
+      for (int g = 0; g < kLlMaxGroups; ++g) {
+        if (e[g].y != seq || e[g].w != seq) {
+          e[g] = ld_relaxed_v4(grp + static_cast<size_t>(g) * ncol + c);
+          again = true;
+        }
+      }
+    } while (again);
+    if (dbg && threadIdx.x == 0) dbg[21] = clock64();
+    double v[16];
+#pragma unroll
+    for (int g = 0; g < kLlMaxGroups; ++g) v[g] = __hiloint2double(static_cast<int>(e[g].z), static_cast<int>(e[g].x));
+    cta_acc[c] = tree16(v);
+  }
+  __syncthreads();
+}
+
 // Development timeline (edhmc_set_timeline): thread 0 of every CTA stamps clock64 / globaltimer at fixed points of
 // the first tl_cap passes of a persistent launch. Record = kTlRec int64: {pass start, tiles done + CTA reduced, partials
 // published, grid barrier passed, totals ready (incl. peer exchange), integrator done, globaltimer at pass start,
@@ -234,6 +311,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   if (single && a.gate && !a.sc->need_init) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_last;
+  __shared__ int s_init0;  // leader protocol: 1 if this launch starts with the initial evaluation pass
   // The chain scalars live in shared memory BETWEEN the serial sections: every thread reloads them after a data pass
   // and thread 0 stores them back before the next one, so none of them occupies a register across the tile loop (with
   // them live the allocator rematerialised address arithmetic inside the loop: 262 instructions per 32 rows, ncu r02).
@@ -421,12 +499,37 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   const bool guarded = a.nranks > 1 || wide;  // waits that can time out: poll the abort flag
   const unsigned long long seq0 = (!single && guarded) ? *a.comm_seq : 0ull;
   bool aborted = false;
+  // leader protocol (see ll_reduce_partials): the host selects it for one GPU and P+1 <= kWideCols
+  // (a.leader is set only for the persistent plan on one GPU with a narrow model and more than one CTA). Nothing of it
+  // is kept in registers across the data pass: the flag comes from the constant bank, in_init0 from shared memory.
+#define EDHMC_LEAD (a.leader != 0)
+#define EDHMC_WORKER (a.leader != 0 && blockIdx.x != 0)
+  if (tid == 0) s_init0 = in_init ? 1 : 0;
+  __syncthreads();
   for (long long pass = 0; pass < n_passes; ++pass) {
-    const bool in_init_p = s_cs2[pass & 1].in_init != 0;
+    if (EDHMC_WORKER && pass > 0) {
+      const unsigned int ll_seq = a.ll_seq0 + static_cast<unsigned int>(pass) + 1u;
+      // the position of this pass, from the leader: every lane polls its own {float, seq} word
+      const uint2* src = a.ll_theta + (static_cast<size_t>(pass & 1) * kLlCopies + (blockIdx.x % kLlCopies)) * P;
+      for (int c = tid; c < P; c += kThreads) {
+        uint2 v;
+        do {
+          v = ld_relaxed_v2(src + c);
+        } while (v.y != ll_seq);
+        const float zn = __uint_as_float(v.x);
+        z[c] = zn;
+        if (c < D) sm.theta_s[c] = zn;
+      }
+      EDHMC_TL(25, clock64());
+      __syncthreads();
+    }
+    // which pass of a trajectory this is follows from its index alone (every transition has exactly L passes)
+    const bool in_init_p = EDHMC_LEAD ? (s_init0 != 0 && pass == 0) : (s_cs2[pass & 1].in_init != 0);
+    const int s_p = EDHMC_LEAD ? (static_cast<int>(pass) - s_init0) % (a.L > 0 ? a.L : 1) : s_cs2[pass & 1].s;
     const float* pos = single ? a.theta_in : (in_init_p ? zc : z);
     const float bias = a.has_bias ? pos[D] : 0.0f;
     // the log likelihood is only consumed at the ends of a trajectory (initial evaluation, last leapfrog step)
-    const bool want_lp = single ? (a.single_lp != 0) : (in_init_p || s_cs2[pass & 1].s + 1 >= a.L);
+    const bool want_lp = single ? (a.single_lp != 0) : (in_init_p || s_p + 1 >= a.L);
     EDHMC_TL(0, clock64());
     EDHMC_TL(6, global_timer_ns());
     if constexpr (RM == 1)
@@ -451,14 +554,34 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
         if (kMayWide && P + 1 > kWideCols)
           reduce_partials_wide(a.partials, ncta, P + 1, sm.cta_acc);
         else
-          reduce_partials<(NW >= 12 ? 20 : 40)>(a.partials, ncta, P, sm.cta_acc, sm.comb);
+          reduce_partials<2>(a.partials, ncta, P, sm.cta_acc, reinterpret_cast<double*>(sm.xw));
         for (int c = tid; c <= P; c += kThreads) a.sums[c] = sm.cta_acc[c];
         if (tid == 0) *a.ticket = 0u;
       }
       return;
     }
 
-    if (ncta > 1 || wide) {
+    if (EDHMC_LEAD) {
+      const unsigned int ll_seq = a.ll_seq0 + static_cast<unsigned int>(pass) + 1u;
+      uint4* mine = a.ll_part + (static_cast<size_t>(pass & 1) * ncta + blockIdx.x) * (P + 1);
+      for (int c = tid; c <= P; c += kThreads) {
+        const double v = sm.cta_acc[c];
+        st_relaxed_v4(mine + c, make_uint4(static_cast<unsigned int>(__double2loint(v)), ll_seq,
+                                           static_cast<unsigned int>(__double2hiint(v)), ll_seq));
+      }
+      EDHMC_TL(2, clock64());
+      const int ngroups = (ncta + kLlGroup - 1) / kLlGroup;
+      uint4* grp = a.ll_group + static_cast<size_t>(pass & 1) * ngroups * (P + 1);
+      if (blockIdx.x % kLlGroup == 0)
+        ll_group_sum(a.ll_part + static_cast<size_t>(pass & 1) * ncta * (P + 1), grp + static_cast<size_t>(blockIdx.x / kLlGroup) * (P + 1),
+                     ncta, P + 1, ll_seq);
+      if (EDHMC_WORKER) continue;  // next: poll the position of pass + 1 (top of the loop)
+      ll_reduce_groups(grp, ngroups, P, ll_seq, sm.cta_acc,
+                       (tl_on && pass < a.tl_cap) ? a.timeline + (static_cast<size_t>(pass) * gridDim.x + blockIdx.x) * kTlRec
+                                                   : nullptr);
+      EDHMC_TL(3, clock64());
+      EDHMC_TL(7, global_timer_ns());
+    } else if (ncta > 1 || wide) {
       double* mine = a.partials + (static_cast<size_t>(bufsel) * ncta + blockIdx.x) * (P + 1);
       for (int c = tid; c <= P; c += kThreads) mine[c] = sm.cta_acc[c];
       __syncthreads();
@@ -489,7 +612,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
       }
       EDHMC_TL(3, clock64());
       EDHMC_TL(7, global_timer_ns());
-      if (!wide) reduce_partials<(NW >= 12 ? 20 : 40)>(a.partials + static_cast<size_t>(bufsel) * ncta * (P + 1), ncta, P, sm.cta_acc, sm.comb);
+      if (!wide) reduce_partials<2>(a.partials + static_cast<size_t>(bufsel) * ncta * (P + 1), ncta, P, sm.cta_acc, reinterpret_cast<double*>(sm.xw));
       bufsel ^= 1;
       ++epoch;
     }
@@ -543,6 +666,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
       const double lik = sm.cta_acc[P];
       logp_new = (block_sum_f64(pl, sm.red) - a.prior_const) + lik;
     }
+    EDHMC_TL(22, clock64());
 
     if (in_init) {
       logp_cur = logp_new;
@@ -566,6 +690,18 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
         }
       }
     }
+    EDHMC_TL(23, clock64());
+    if (EDHMC_LEAD && pass + 1 < n_passes) {
+      // the position of pass + 1 to the workers; each thread sends the latents it has just written itself
+      const unsigned int seq_next = a.ll_seq0 + static_cast<unsigned int>(pass) + 2u;
+      uint2* dst = a.ll_theta + static_cast<size_t>((pass + 1) & 1) * kLlCopies * P;
+      for (int c = tid; c < P && tid < CT; c += CT) {
+        const uint2 w = make_uint2(__float_as_uint(z[c]), seq_next);
+#pragma unroll
+        for (int k = 0; k < kLlCopies; ++k) st_relaxed_v2(dst + static_cast<size_t>(k) * P + c, w);
+      }
+    }
+    EDHMC_TL(24, clock64());
     store_chain(pass + 1);
     __syncthreads();
     EDHMC_TL(5, clock64());

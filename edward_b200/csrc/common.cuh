@@ -13,7 +13,7 @@ constexpr int kMaxStages = 8;
 constexpr int kXwFloats = 2048;  // per-CTA scratch for the one-shot cross-warp reduction (8 KB)
 constexpr int kMaxFeatures = 2048;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kTlRec = 16;  // int64 slots per (pass, CTA) record of the development timeline
+constexpr int kTlRec = 32;  // int64 slots per (pass, CTA) record of the development timeline
 
 // Inbox of the in-kernel all-reduce (row shards over the GPUs of one NVLink domain; also the second level of
 // the wide single-GPU reduction). One cudaMalloc per rank, exported with cudaIpc: flags[2][kMaxRanks] (u64) at
@@ -23,6 +23,9 @@ constexpr int kMaxRanks = 8;
 constexpr int kInboxStride = kMaxFeatures + 8;
 constexpr int kInboxCountOff = 128;
 constexpr int kInboxDataOff = 256;
+constexpr int kLlGroup = 16;     // CTAs per first-level group of the narrow-model reduction (leader protocol and reduce_partials)
+constexpr int kLlMaxGroups = 16;  // so grids of up to 256 CTAs
+constexpr int kLlCopies = 8;      // replicas of the broadcast position: CTA i polls copy i % 8 (spreads the polling over L2 slices)
 constexpr int kWideCols = 256;    // more totals than this: two-level reduction (column slices) instead of all-read-all
 constexpr int kWideSlices = 128;  // column slices of the two-level reduction (independent of the grid size)
 constexpr size_t kInboxBytes = kInboxDataOff + sizeof(double) * 2 * kMaxRanks * kInboxStride;
@@ -95,6 +98,12 @@ struct KArgs {
   unsigned long long* bar;     // grid barrier counter (persistent plan)
   unsigned int* ticket;        // last-arriver ticket (stepwise plan)
   double* sums;                // [P+1] shard sums → all-reduced in place (stepwise plan)
+  // ---- leader protocol of the persistent plan (one GPU, P+1 <= kWideCols; chain.cuh) ----
+  int leader;                  // 1: CTA 0 owns the chain; the other CTAs only run data passes
+  unsigned int ll_seq0;        // sequence number of this launch's pass 0, minus 1 (never repeats within 2^32 passes)
+  uint4* ll_part;              // [2][grid][P+1] {lo32, seq, hi32, seq}: per-CTA float64 sums with the flag in the data
+  uint4* ll_group;             // [2][ceil(grid / kLlGroup)][P+1]: sums of groups of kLlGroup CTAs, same entry format
+  uint2* ll_theta;             // [2][kLlCopies][P] {float bits, seq}: the position of the next pass
   // ---- chain state ----
   ChainScalars* sc;
   float* zcur;  // [P]

@@ -165,6 +165,11 @@ struct edhmc_handle {
   float* d_r = nullptr;
   float* d_g = nullptr;
   double* d_partials = nullptr;
+  uint4* d_ll_part = nullptr;   // leader protocol (chain.cuh): flag-in-data partials [2][num_sms][P+1]
+  uint4* d_ll_group = nullptr;  // leader protocol: sums of groups of kLlGroup CTAs [2][ceil(num_sms / kLlGroup)][P+1]
+  uint2* d_ll_theta = nullptr;  // leader protocol: flag-in-data position [2][P]
+  unsigned int ll_seq = 1;      // sequence numbers handed out so far
+  int leader = 1;               // EDHMC_LEADER=0 keeps the grid-barrier protocol on one GPU (same-box A/B)
   size_t partials_cap = 0;
   unsigned long long* d_bar = nullptr;
   unsigned int* d_ticket = nullptr;
@@ -651,6 +656,17 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   h->partials_cap = static_cast<size_t>(2) * h->num_sms * (P + 1);
   ALLOC(h->d_partials, h->partials_cap * sizeof(double));
   ALLOC(h->d_bar, sizeof(unsigned long long));
+  if (P + 1 <= kWideCols) {
+    const size_t pbytes = static_cast<size_t>(2) * h->num_sms * (P + 1) * sizeof(uint4);
+    ALLOC(h->d_ll_part, pbytes);
+    const size_t gbytes = static_cast<size_t>(2) * ((h->num_sms + kLlGroup - 1) / kLlGroup) * (P + 1) * sizeof(uint4);
+    ALLOC(h->d_ll_group, gbytes);
+    ALLOC(h->d_ll_theta, static_cast<size_t>(2) * kLlCopies * P * sizeof(uint2));
+    cudaMemset(h->d_ll_group, 0, gbytes);
+    cudaMemset(h->d_ll_part, 0, pbytes);
+    cudaMemset(h->d_ll_theta, 0, static_cast<size_t>(2) * kLlCopies * P * sizeof(uint2));
+  }
+  if (const char* e = getenv("EDHMC_LEADER")) h->leader = atoi(e);
   ALLOC(h->d_ticket, sizeof(unsigned int));
   ALLOC(h->d_sums, static_cast<size_t>(P + 1) * sizeof(double));
   ALLOC(h->d_bad, sizeof(unsigned long long));
@@ -802,6 +818,9 @@ int edhmc_destroy(edhmc_t* h) {
   h_free(h, h->d_g);
   h_free(h, h->d_partials);
   h_free(h, h->d_bar);
+  h_free(h, h->d_ll_part);
+  h_free(h, h->d_ll_theta);
+  h_free(h, h->d_ll_group);
   h_free(h, h->d_ticket);
   h_free(h, h->d_sums);
   h_free(h, h->d_bad);
@@ -1101,6 +1120,15 @@ int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int
     CUDA_TRY(cudaMemsetAsync(h->d_bar, 0, sizeof(unsigned long long), stream));
     void* kp[] = {&a};
     a.mode = 0;
+    if (h->leader && h->d_ll_part && a.nranks == 1 && h->plan.grid > 1 && h->plan.grid <= h->num_sms &&
+        h->plan.grid <= kLlGroup * kLlMaxGroups && n_iter * n_steps < (1ll << 30)) {
+      a.leader = 1;
+      a.ll_part = h->d_ll_part;
+      a.ll_theta = h->d_ll_theta;
+      a.ll_group = h->d_ll_group;
+      a.ll_seq0 = h->ll_seq;
+      h->ll_seq += static_cast<unsigned int>(n_iter * n_steps + 2);  // one number per pass of this launch, never reused
+    }
     CUDA_TRY(cudaLaunchCooperativeKernel(h->plan.fn, dim3(h->plan.grid), dim3(h->plan.NW * 32), kp, h->plan.smem, stream));
     ++h->launches_last;
   } else {

@@ -176,6 +176,25 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsign
 __device__ __forceinline__ void red_release_sys_add_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// ---- flag-in-data words (the leader protocol of the persistent plan): relaxed gpu-scope vector accesses. An 8-byte
+// aligned 64-bit access is single-copy atomic; a 16-byte entry carries its sequence number in BOTH 8-byte halves, so a
+// torn 16-byte access is detected by the reader.
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(uint4* p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 ld_relaxed_v2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_v2(uint2* p, uint2 v) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ int ld_volatile_s32(const int* p) {
   int v;
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

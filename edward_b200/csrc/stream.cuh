@@ -303,12 +303,24 @@ struct LaneMap {
   static __device__ __forceinline__ constexpr int lg_xor(int b) { return SPLIT ? b * RPS : b; }
 };
 
+// Balanced binary tree over 16 float64 slots ((v0+v1)+(v2+v3))+..., the fixed summation order of every cross-CTA and
+// cross-warp reduction of the narrow-model path: float64 adds have a long latency on this part (a chain of 8 costs ~600
+// cycles, measured with the per-pass timeline), a tree of 16 is four levels deep. Absent slots hold 0.0 (x + 0.0 == x).
+__device__ __forceinline__ double tree16(double (&v)[16]) {
+#pragma unroll
+  for (int w = 1; w < 16; w <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 2 * w) v[i] += v[i + w];
+  }
+  return v[0];
+}
+
 // End of a pass: sums the per-lane gradient accumulators g[], the bias gradient gb and the log-likelihood lp over the
 // warp (halving butterfly) and then over the warps of the CTA (fixed order, float64) into sm.cta_acc[0..P].
 template <int G, int V, int K, int NW, bool SPLIT, typename WT, typename RING>
 __device__ __forceinline__ void pass_reduce(const KArgs& a, const PlanRegs& pr, const WT& wt, RING& ring, const SmemLayout& sm,
                                             const typename Acc<V>::type* g, float gb, double lp, bool park, bool deferred,
-                                            uint32_t park_s, uint64_t policy) {
+                                            uint32_t park_s, uint64_t policy, long long* tlx = nullptr) {
   constexpr int RPS = 32 / G;
   constexpr int KV = K * V;
   constexpr int NA = (V == 1) ? KV : KV / 2;
@@ -356,20 +368,24 @@ __device__ __forceinline__ void pass_reduce(const KArgs& a, const PlanRegs& pr, 
       xwd[warp] = static_cast<double>(gb);
       xwd[kMaxWarps + warp] = lp;
     }
+    if (tlx != nullptr && threadIdx.x == 0) tlx[10] = clock64();  // slot 18: warp 0 reduced and published its sums
     __syncthreads();
+    if (tlx != nullptr && threadIdx.x == 0) tlx[11] = clock64();  // slot 19: all warps did
     for (int c = threadIdx.x; c <= P; c += NW * 32) {
-      double s = 0.0;
+      double v[16];
+#pragma unroll
+      for (int wq = 0; wq < 16; ++wq) v[wq] = 0.0;
       if (c < D) {
 #pragma unroll
-        for (int wq = 0; wq < NW; ++wq) s += static_cast<double>(sm.xw[wq * D + c]);
+        for (int wq = 0; wq < NW; ++wq) v[wq] = static_cast<double>(sm.xw[wq * D + c]);
       } else if (c == P) {
 #pragma unroll
-        for (int wq = 0; wq < NW; ++wq) s += xwd[kMaxWarps + wq];
+        for (int wq = 0; wq < NW; ++wq) v[wq] = xwd[kMaxWarps + wq];
       } else {
 #pragma unroll
-        for (int wq = 0; wq < NW; ++wq) s += xwd[wq];
+        for (int wq = 0; wq < NW; ++wq) v[wq] = xwd[wq];
       }
-      cta_acc[c] = s;
+      cta_acc[c] = tree16(v);
     }
     __syncthreads();
   } else {
@@ -389,18 +405,20 @@ __device__ __forceinline__ void pass_reduce(const KArgs& a, const PlanRegs& pr, 
     }
     __syncthreads();
     for (int c = threadIdx.x; c <= P; c += NW * 32) {
-      double s = 0.0;
+      double v[16];
+#pragma unroll
+      for (int wq = 0; wq < 16; ++wq) v[wq] = 0.0;
       if (c < D) {
 #pragma unroll
-        for (int wq = 0; wq < NW; ++wq) s += static_cast<double>(lds_f32<0>(park_tab[wq] + c * 4));
+        for (int wq = 0; wq < NW; ++wq) v[wq] = static_cast<double>(lds_f32<0>(park_tab[wq] + c * 4));
       } else if (c == P) {
 #pragma unroll
-        for (int wq = 0; wq < NW; ++wq) s += xwd[kMaxWarps + wq];
+        for (int wq = 0; wq < NW; ++wq) v[wq] = xwd[kMaxWarps + wq];
       } else {
 #pragma unroll
-        for (int wq = 0; wq < NW; ++wq) s += xwd[wq];
+        for (int wq = 0; wq < NW; ++wq) v[wq] = xwd[wq];
       }
-      cta_acc[c] = s;
+      cta_acc[c] = tree16(v);
     }
     fence_proxy_async_smem();  // the parked stages go back to the TMA (async proxy) after the barrier
     __syncthreads();
@@ -605,53 +623,71 @@ __device__ __forceinline__ void stream_pass(const KArgs& a, const PlanRegs& pr, 
 }
 
 // Sums the per-CTA partials [ncta][P+1] (global, float64) in a fixed order into cta_acc[0..P].
-// Every CTA that calls this gets bit-identical totals. `comb` holds blockDim.x doubles. The loads of a
-// thread are issued in independent batches of 40: with 148 CTAs and >= 4 thread slices per column ONE L2 round trip
-// covers them all (the timeline of round 2 showed four dependent rounds of 12 costing 2.8 us per leapfrog step).
-template <int B = 40>
-__device__ __forceinline__ void reduce_partials(const double* part, int ncta, int P, double* cta_acc, double* comb) {
+// Every CTA that calls this gets bit-identical totals.
+// Canonical order (shared with the leader protocol of chain.cuh, which computes the first level on group-leader CTAs):
+//   level 1: G_g[c] = tree16 over the CTAs g*16 .. g*16+15 of column c;   level 2: total[c] = tree16 over G_0 .. G_15.
+// `scratch` holds kXwFloats/2 doubles (the cross-warp scratch of pass_reduce, free by now). When 16 group sums of every
+// (padded) column fit in it, thread (c, q) computes the groups q, q+nsl, ... (two groups = 32 independent loads in flight
+// at a time) and thread c combines them; otherwise thread c walks all groups itself.
+template <int B = 2>
+__device__ __forceinline__ void reduce_partials(const double* part, int ncta, int P, double* cta_acc, double* scratch) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int ncol = P + 1;
+  const int ngroups = (ncta + kLlGroup - 1) / kLlGroup;
   int cpad = 32;
   while (cpad < ncol && cpad < nthr) cpad <<= 1;
-  if (cpad >= ncol && cpad <= nthr) {
+  if (cpad >= ncol && cpad * kLlMaxGroups <= kXwFloats / 2) {
     const int nsl = nthr / cpad;
     const int c = tid % cpad, q = tid / cpad;
-    double s = 0.0;
-    if (c < ncol && q < nsl) {
-      for (int cta = q; cta < ncta; cta += B * nsl) {
-        double v[B];
+    if (c < ncol) {
+      for (int g0 = q; g0 < kLlMaxGroups; g0 += B * nsl) {
+        double v[B][16];
 #pragma unroll
         for (int i = 0; i < B; ++i) {
-          const int cc = cta + i * nsl;
-          v[i] = cc < ncta ? __ldcg(part + static_cast<size_t>(cc) * ncol + c) : 0.0;
+#pragma unroll
+          for (int m = 0; m < 16; ++m) {
+            const int cc = (g0 + i * nsl) * kLlGroup + m;
+            v[i][m] = (g0 + i * nsl < ngroups && cc < ncta) ? __ldcg(part + static_cast<size_t>(cc) * ncol + c) : 0.0;
+          }
         }
 #pragma unroll
-        for (int i = 0; i < B; ++i) s += v[i];
+        for (int i = 0; i < B; ++i)
+          if (g0 + i * nsl < kLlMaxGroups) scratch[(g0 + i * nsl) * cpad + c] = tree16(v[i]);
       }
     }
-    if (q < nsl) comb[q * cpad + c] = s;
     __syncthreads();
     if (tid < ncol) {
-      double t = 0.0;
-      for (int qq = 0; qq < nsl; ++qq) t += comb[qq * cpad + tid];
-      cta_acc[tid] = t;
+      double G[16];
+#pragma unroll
+      for (int g = 0; g < kLlMaxGroups; ++g) G[g] = scratch[g * cpad + tid];
+      cta_acc[tid] = tree16(G);
     }
     __syncthreads();
-  } else {
-    for (int c = tid; c < ncol; c += nthr) {
-      double s = 0.0;
-      for (int cta = 0; cta < ncta; cta += B) {
-        double v[B];
-#pragma unroll
-        for (int i = 0; i < B; ++i) v[i] = (cta + i) < ncta ? __ldcg(part + static_cast<size_t>(cta + i) * ncol + c) : 0.0;
-#pragma unroll
-        for (int i = 0; i < B; ++i) s += v[i];
-      }
-      cta_acc[c] = s;
-    }
-    __syncthreads();
+    return;
   }
+  for (int c = tid; c < ncol; c += nthr) {
+    double G[kLlMaxGroups];
+#pragma unroll
+    for (int g = 0; g < kLlMaxGroups; ++g) G[g] = 0.0;
+#pragma unroll
+    for (int g0 = 0; g0 < kLlMaxGroups; g0 += B) {
+      if (g0 < ngroups) {
+        double v[B][16];
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+#pragma unroll
+          for (int m = 0; m < 16; ++m) {
+            const int cc = (g0 + i) * kLlGroup + m;
+            v[i][m] = cc < ncta ? __ldcg(part + static_cast<size_t>(cc) * ncol + c) : 0.0;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < B; ++i) G[g0 + i] = tree16(v[i]);
+      }
+    }
+    cta_acc[c] = tree16(G);
+  }
+  __syncthreads();
 }
 
 }  // namespace edhmc

@@ -194,6 +194,7 @@ __device__ EDHMC_PASS_INLINE void stream_pass_cta_tiles(CtaPassCtx* __restrict__
   const uint32_t lane_off = (wrow0 + grp) * row_bytes + lg * V * 4;
   const bool acct = cx->tl_wait != nullptr && lane == 0 && warp < 8;
   long long wait_cyc = 0;
+  if (cx->tl_wait != nullptr && threadIdx.x == 0) cx->tl_wait[8] = clock64();  // slot 16: tile loop starts
   for (int kt = 0; kt < nt; ++kt) {
     const int kk = backward ? (nt - 1 - kt) : kt;
     const uint32_t sb = ring_s + stage * stage_bytes;
@@ -231,6 +232,7 @@ __device__ EDHMC_PASS_INLINE void stream_pass_cta_tiles(CtaPassCtx* __restrict__
     }
   }
   if (acct) cx->tl_wait[warp] = wait_cyc;
+  if (cx->tl_wait != nullptr && threadIdx.x == 0) cx->tl_wait[9] = clock64();  // slot 17: tile loop done (warp 0)
   // cursor back to the caller (every thread holds the same values; its own copy of the context is per thread)
   cx->stage = stage;
   cx->parity = parity;
@@ -316,7 +318,7 @@ __device__ __forceinline__ void stream_pass_cta(const KArgs& a, const PlanRegs& 
   ring.npass = cx.npass;
   ring.nk = cx.nk;
   ++ring.cpass;
-  pass_reduce<G, V, K, NW, true>(a, pr, ct, ring, sm, g, gb, lp, false, false, 0u, policy);
+  pass_reduce<G, V, K, NW, true>(a, pr, ct, ring, sm, g, gb, lp, false, false, 0u, policy, cx.tl_wait);
 }
 
 }  // namespace edhmc

@@ -289,13 +289,13 @@ class GLMSampler:
 
   def set_timeline(self, n_passes: int):
     """Development aid: per-CTA clock64 stamps of the first n_passes passes of the next persistent run()
-    ([n_passes, grid, 16] int64; see edhmc_set_timeline). n_passes = 0 switches it off."""
+    ([n_passes, grid, 32] int64; see edhmc_set_timeline). n_passes = 0 switches it off."""
     if not n_passes:
       self._timeline = None
       _C.check(self.lib.edhmc_set_timeline(self._h, None, 0))
       return None
     grid = self.plan_info()["grid_ctas"]
-    self._timeline = torch.zeros(n_passes, grid, 16, dtype=torch.int64, device=self.dev)
+    self._timeline = torch.zeros(n_passes, grid, 32, dtype=torch.int64, device=self.dev)
     _C.check(self.lib.edhmc_set_timeline(self._h, self._timeline.data_ptr(), int(n_passes)))
     return self._timeline
 

@@ -227,10 +227,11 @@ int edhmc_set_chain_trace(edhmc_t* h, double* trace);
 int edhmc_set_chain_debug(edhmc_t* h, long long* buf);
 
 /* Development aid for the persistent plan of edhmc_run: thread 0 of every CTA stamps its first `n_passes` data passes
- * into buf [n_passes][grid_ctas][16] int64 (device): clock64 at {pass start, CTA sums ready, partials published, grid
+ * into buf [n_passes][grid_ctas][32] int64 (device): clock64 at {pass start, CTA sums ready, partials published, grid
  * barrier passed, totals ready (after the peer exchange when sharded), integrator done}, then %globaltimer (ns) at
  * {pass start, grid barrier passed}, then the cycles warps 0..7 spent waiting for their tiles to land (one-ring-per-CTA
- * plans). NULL switches it off (default). bench.py reports the medians as `timeline`.
+ * plans), then (slots 16..) stamps of the leader CTA under the leader protocol (slots 3..5 are then stamped by CTA 0
+ * only). NULL switches it off (default). bench.py reports the medians as `timeline`.
  * Replaces: nothing in the reference (introspection). */
 int edhmc_set_timeline(edhmc_t* h, long long* buf, int32_t n_passes);
 
