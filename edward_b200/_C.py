@@ -25,7 +25,7 @@ EXPORTS = [
     "edhmc_logp_grad", "edhmc_run", "edhmc_set_trace", "edhmc_read_state", "edhmc_reset", "edhmc_seed",
     "edhmc_comm_unique_id", "edhmc_comm_init", "edhmc_peer_export", "edhmc_peer_attach", "edhmc_peer_detach", "edhmc_plan_info",
     "edhmc_sgmcmc_run", "edhmc_run_chains", "edhmc_logp_grad_chains", "edhmc_read_chain_state", "edhmc_set_chain_trace", "edhmc_set_chain_debug", "edhmc_chains_plan_probe", "edhmc_set_timeline", "edhmc_probe_read", "edhmc_comm_cached", "edhmc_comm_release", "edhmc_set_prior_kinds",
-    "edhmc_bind_data_f64", "edhmc_logp_grad_f64", "edhmc_run_f64", "edhmc_set_trace_f64",
+    "edhmc_bind_data_f64", "edhmc_logp_grad_f64", "edhmc_run_f64", "edhmc_set_trace_f64", "edhmc_predictive",
 ]
 
 
@@ -111,6 +111,7 @@ def lib():
   L.edhmc_logp_grad_f64.argtypes = [vp, vp, vp, vp, vp]
   L.edhmc_run_f64.argtypes = [vp, vp, i64, i64, i64, i64, C.c_double, i32, vp, vp, vp]
   L.edhmc_set_trace_f64.argtypes = [vp, vp, vp]
+  L.edhmc_predictive.argtypes = [vp, i64, i64, i32, vp, i32, i32, f32, vp, i64, vp, vp, i32, i32, vp, vp, i32, vp]
   for name in EXPORTS:
     if name not in ("edhmc_last_error",):
       getattr(L, name).restype = C.c_int

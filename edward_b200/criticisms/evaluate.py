@@ -4,7 +4,8 @@ on the device over the Empirical sample stores that ed.HMC / ed.SGLD left there 
 The reference evaluates the output variable n_samples times, each run drawing a fresh posterior sample of every
 latent (independently per latent, empirical.py:98-110), and averages: probabilities for Bernoulli outputs
 (evaluate.py:132-143), draws for continuous outputs (:158-162), mean log-density for 'log_lik' (:222-227).
-Here the n_samples draws are gathered from the device stores and pushed through one [N, D]·[D, S] product.
+Here the n_samples draws are gathered from the device stores and pushed through ONE fused kernel (edhmc_predictive,
+csrc/criticism.cuh): the [N, D]·[D, S] contraction with the family's link and the reductions over the draws in its epilogue.
 """
 from __future__ import annotations
 
@@ -41,15 +42,54 @@ def _latent_draws(z, n_samples, dev):
   raise NotImplementedError("latent %s in the posterior predictive" % type(z).__name__)
 
 
-def _predictive_eta(output_key, data, n_samples, dev):
-  """eta [N, S] of the output variable's linear predictor under n_samples posterior draws."""
+def predictive(X, y, W, B, family, lik_scale=1.0, want_loglik=True):
+  """One fused device pass (edhmc_predictive, csrc/criticism.cuh) over rows X [N, D] and S posterior draws W [S, D],
+  B [S] or None: returns (mean_s E[y_n | eta_ns] as float32 [N], sum_s log p(y_n | eta_ns) as float64 [N] or None).
+  eta [N, S] is never materialised."""
+  import ctypes as C
   import torch
+  from .. import _C
+  from ..engine import _stream_ptr, _Y_DTYPES
+  dev = X.device
+  X = X.to(torch.float32)
+  if X.stride(1) != 1:
+    X = X.contiguous()
+  S, D = int(W.shape[0]), int(W.shape[1])
+  cols = [W.to(dev, torch.float32)]
+  if B is not None:
+    cols.append(B.to(dev, torch.float32).reshape(S, 1))
+  packed = torch.cat(cols, dim=1).contiguous()  # [S, D (+1)]: the draws, gathered from the sample stores
+  idx = torch.arange(S, dtype=torch.int32, device=dev)
+  yt = None
+  if y is not None:
+    yt = y.to(dev)
+    if yt.dtype not in _Y_DTYPES:
+      yt = yt.to(torch.float32)
+    yt = yt.contiguous()
+  N = int(X.shape[0])
+  mean = torch.empty(N, dtype=torch.float32, device=dev)
+  ll = torch.empty(N, dtype=torch.float64, device=dev) if (want_loglik and yt is not None) else None
+  with torch.cuda.device(dev):
+    _C.check(_C.lib().edhmc_predictive(
+        X.data_ptr(), N, int(X.stride(0)) if N > 1 else max(int(X.stride(0)), D), D,
+        yt.data_ptr() if yt is not None else None, _Y_DTYPES[yt.dtype] if yt is not None else 0, int(family), float(lik_scale),
+        packed.data_ptr(), int(packed.stride(0)), idx.data_ptr(), idx.data_ptr() if B is not None else None, D, S,
+        mean.data_ptr(), ll.data_ptr() if ll is not None else None, dev.index, _stream_ptr(dev)))
+  return mean, ll
+
+
+def _predictive_inputs(output_key, data, n_samples, dev):
+  """(X [N, D] on the device, W [S, D], B [S] | None, family, lik_scale) of the output variable under n_samples draws."""
+  import torch
+  from .. import _C
+  lik_scale = 1.0
   if isinstance(output_key, Bernoulli):
-    eta_node = output_key.logits
+    eta_node, family = output_key.logits, _C.BERNOULLI_LOGIT
   elif isinstance(output_key, Normal):
-    eta_node = output_key.loc
+    eta_node, family = output_key.loc, _C.NORMAL_IDENTITY
+    lik_scale = float(np.unique(_g.evaluate(output_key.scale))[0])
   elif isinstance(output_key, Poisson):
-    eta_node = output_key.log_rate
+    eta_node, family = output_key.log_rate, _C.POISSON_LOG
   else:
     raise NotImplementedError("ed.evaluate: output %s" % type(output_key).__name__)
   if eta_node is None:
@@ -74,10 +114,8 @@ def _predictive_eta(output_key, data, n_samples, dev):
     xv = data[x_node] if x_node in data else _g.evaluate(x_node)
     X = xv.to(dev, torch.float32) if isinstance(xv, torch.Tensor) else torch.as_tensor(np.asarray(xv, np.float32), device=dev)
   W = _latent_draws(w, n_samples, dev)          # [S, D]
-  eta = X @ W.t()                                # [N, S]
-  if b is not None:
-    eta = eta + _latent_draws(b, n_samples, dev).reshape(1, n_samples)
-  return eta
+  B = _latent_draws(b, n_samples, dev).reshape(n_samples) if b is not None else None
+  return X, W, B, family, lik_scale
 
 
 def evaluate(metrics, data, n_samples=500, output_key=None, seed=None):
@@ -104,19 +142,22 @@ def evaluate(metrics, data, n_samples=500, output_key=None, seed=None):
   dev = _device()
   yv = data[output_key]
   y_true = yv.to(dev, torch.float32) if isinstance(yv, torch.Tensor) else torch.as_tensor(np.asarray(yv, np.float32), device=dev)
-  eta = _predictive_eta(output_key, data, n_samples, dev)
-  y_col = y_true.reshape(-1, 1)
+  X, W, B, family, lik_scale = _predictive_inputs(output_key, data, n_samples, dev)
+  want_ll = any((m[0] if isinstance(m, tuple) else m) in ('log_lik', 'log_likelihood') for m in metrics)
+  mean, ll = predictive(X, y_true, W, B, family, lik_scale, want_loglik=want_ll)
 
   probs = y_pred = None
   if isinstance(output_key, Bernoulli):
-    probs = torch.sigmoid(eta).mean(dim=1)
+    probs = mean  # evaluate.py:132-143: the mean of the Bernoulli probabilities over the draws
     rnd = torch.rand_like(probs)
     y_pred = torch.round(torch.where(probs == 0.5, rnd, probs))
   elif isinstance(output_key, Normal):
-    scale = float(np.unique(_g.evaluate(output_key.scale))[0])
-    y_pred = (eta + scale * torch.randn_like(eta)).mean(dim=1)
+    # evaluate.py:158-162 averages n_samples draws y ~ Normal(eta_s, scale): their mean is mean_s(eta_s) plus
+    # Normal(0, scale^2 / n_samples) noise
+    y_pred = mean + (lik_scale / np.sqrt(n_samples)) * torch.randn_like(mean)
   elif isinstance(output_key, Poisson):
-    y_pred = torch.poisson(torch.exp(eta)).mean(dim=1)
+    # the sum of independent Poisson(rate_s) draws is Poisson(sum_s rate_s)
+    y_pred = torch.poisson(mean * n_samples) / n_samples
 
   out = []
   for metric in metrics:
@@ -135,14 +176,7 @@ def evaluate(metrics, data, n_samples=500, output_key=None, seed=None):
     elif metric in ('mae', 'MAE', 'mean_absolute_error'):
       out.append(float((y_pred - y_true).abs().mean()))
     elif metric in ('log_lik', 'log_likelihood'):
-      if isinstance(output_key, Bernoulli):
-        lp = -(torch.clamp(eta, min=0) - eta * y_col + torch.log1p(torch.exp(-eta.abs())))
-      elif isinstance(output_key, Normal):
-        scale = float(np.unique(_g.evaluate(output_key.scale))[0])
-        lp = -0.5 * ((y_col - eta) / scale) ** 2 - (0.5 * np.log(2 * np.pi) + np.log(scale))
-      else:
-        lp = y_col * eta - torch.exp(eta) - torch.lgamma(y_col + 1.0)
-      out.append(float(lp.mean(dim=0).mean()))
+      out.append(float(ll.sum() / (ll.numel() * n_samples)))  # evaluate.py:222-227: mean over rows and draws
     elif callable(metric):
       out.append(metric(y_true.cpu().numpy(), y_pred.cpu().numpy()))
     else:

@@ -15,6 +15,7 @@
 #include "chains.cuh"
 #include "chains_wide.cuh"
 #include "f64.cuh"
+#include "criticism.cuh"
 
 using namespace edhmc;
 
@@ -1680,6 +1681,29 @@ int edhmc_plan_info(edhmc_t* h, int64_t* out, int32_t cap) {
   int n = cap < 11 ? cap : 11;
   for (int i = 0; i < n; ++i) out[i] = v[i];
   return n;
+}
+
+int edhmc_predictive(const float* X, int64_t n_rows, int64_t ldx, int32_t n_features, const void* y, int32_t y_dtype,
+                     int32_t family, float lik_scale, const float* params, int64_t ldp, const int32_t* idx_w,
+                     const int32_t* idx_b, int32_t bias_col, int32_t n_draws, float* mean_out, double* loglik_out,
+                     int32_t device, void* stream) {
+  if (!X || !params || !idx_w || !mean_out) return fail(EDHMC_ERR_INVALID, "null argument");
+  if (n_rows < 0 || n_features < 1 || ldx < n_features || n_draws < 1 || ldp < n_features)
+    return fail(EDHMC_ERR_INVALID, "bad shape (n_rows %lld, n_features %d, ldx %lld, n_draws %d, ldp %lld)", (long long)n_rows,
+                n_features, (long long)ldx, n_draws, (long long)ldp);
+  if (family < 0 || family > 2) return fail(EDHMC_ERR_INVALID, "unknown family %d", family);
+  if (y_dtype < 0 || y_dtype > 2) return fail(EDHMC_ERR_INVALID, "unknown y_dtype %d", y_dtype);
+  if (loglik_out && !y) return fail(EDHMC_ERR_INVALID, "the log-likelihood needs y");
+  if (idx_b && (bias_col < 0 || bias_col >= ldp)) return fail(EDHMC_ERR_INVALID, "bias_col out of range");
+  if (family == EDHMC_NORMAL_IDENTITY && !(lik_scale > 0.0f)) return fail(EDHMC_ERR_INVALID, "lik_scale must be > 0");
+  if (n_rows == 0) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  const long long blocks = (n_rows + kPredRows - 1) / kPredRows;
+  k_predictive<<<static_cast<unsigned int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      X, n_rows, ldx, n_features, y, y_dtype, family, lik_scale, params, ldp, idx_w, idx_b, bias_col, n_draws, mean_out,
+      loglik_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

@@ -235,6 +235,19 @@ int edhmc_set_chain_debug(edhmc_t* h, long long* buf);
  * Replaces: nothing in the reference (introspection). */
 int edhmc_set_timeline(edhmc_t* h, long long* buf, int32_t n_passes);
 
+/* Posterior-predictive evaluation over the device-resident sample store: what ed.evaluate
+ * (criticisms/evaluate.py:20-235) and ed.ppc compute for the GLMs of this path. For every row n of X and S draws
+ * s = 0..S-1 of the latents — w_s = params[idx_w[s], 0..D), b_s = params[idx_b[s], bias_col] (independent index lists:
+ * the reference draws every latent independently, empirical.py:98-110; idx_b NULL = no bias) — eta = x_n . w_s + b_s and
+ *   mean_out[n]   = mean_s E[y | eta]: sigmoid(eta) (Bernoulli, evaluate.py:132-143), eta (Normal), exp(eta) (Poisson);
+ *   loglik_out[n] = sum_s log p(y_n | eta) (float64; evaluate.py:222-227 averages it), or NULL.
+ * One fused pass: X is read once, eta [N, S] is never materialised; sums are accumulated in a fixed order.
+ * All pointers are device pointers. Stateless (no handle). */
+int edhmc_predictive(const float* X, int64_t n_rows, int64_t ldx, int32_t n_features, const void* y, int32_t y_dtype,
+                     int32_t family, float lik_scale, const float* params, int64_t ldp, const int32_t* idx_w,
+                     const int32_t* idx_b, int32_t bias_col, int32_t n_draws, float* mean_out, double* loglik_out,
+                     int32_t device, void* stream);
+
 /* Read-bandwidth probe for the roofline denominators (bench.py): queues `iters` read sweeps over buf[0..bytes) on
  * `stream`; the caller times them with CUDA events. mode 0: LDG.128 grid-stride loads; mode 1: 1-D TMA bulk copies into
  * a shared-memory ring (the access path of the sampler's data pass). A buffer that fits the L2 gives the L2 read

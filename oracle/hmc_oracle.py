@@ -480,3 +480,30 @@ def sghmc_run(X, y, params, noise, step_size, friction, spec: GLMSpec, dtype=np.
     params[t] = old + v
     v = (dtype(1.0) - dtype(0.5) * dtype(friction)) * v + lr * g + sd * np.asarray(noise[i], dtype)
   return v
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Posterior-predictive criticism: what edward/criticisms/evaluate.py computes for a GLM output under
+# S posterior draws. evaluate.py:132-143 averages the Bernoulli probabilities over the draws; :158-162 averages draws of
+# a continuous output (here: their conditional means); :222-227 ('log_lik') averages log p(y | draw) over rows and draws.
+# ---------------------------------------------------------------------------------------------------------------------
+def predictive(X, y, W, B, family, lik_scale=1.0):
+  """X [N, D], W [S, D], B [S] or None -> (mean_s E[y_n | eta_ns] [N], sum_s log p(y_n | eta_ns) [N]), float64."""
+  X = np.asarray(X, np.float64)
+  W = np.asarray(W, np.float64)
+  y = np.asarray(y, np.float64)
+  eta = X @ W.T
+  if B is not None:
+    eta = eta + np.asarray(B, np.float64)[None, :]
+  yc = y[:, None]
+  if family == BERNOULLI_LOGIT:
+    mean = (1.0 / (1.0 + np.exp(-eta))).mean(axis=1)
+    ll = -(np.maximum(eta, 0.0) - eta * yc + np.log1p(np.exp(-np.abs(eta))))  # tf sigmoid_cross_entropy_with_logits
+  elif family == NORMAL_IDENTITY:
+    mean = eta.mean(axis=1)
+    ll = -0.5 * ((yc - eta) / lik_scale) ** 2 - (0.5 * np.log(2.0 * np.pi) + np.log(lik_scale))
+  else:
+    from scipy.special import gammaln
+    mean = np.exp(eta).mean(axis=1)
+    ll = yc * eta - np.exp(eta) - gammaln(yc + 1.0)
+  return mean, ll.sum(axis=1)

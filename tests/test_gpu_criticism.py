@@ -116,3 +116,44 @@ def test_checkpoint_resume_is_bit_identical():
     inf2.update()
   assert np.array_equal(qw2.params.eval(), full)
   assert int(inf2.n_accept.eval()) == n_full
+
+
+PRED = [
+    # N, D, S, bias, family
+    (1, 1, 1, False, o.BERNOULLI_LOGIT),
+    (63, 3, 5, True, o.BERNOULLI_LOGIT),
+    (1000, 54, 300, True, o.BERNOULLI_LOGIT),   # cfg 2 feature count, evaluate's default order of draws
+    (777, 200, 65, False, o.BERNOULLI_LOGIT),   # several column chunks, a ragged draw chunk
+    (500, 17, 64, True, o.NORMAL_IDENTITY),
+    (300, 12, 130, True, o.POISSON_LOG),
+]
+
+
+@pytest.mark.parametrize("N,D,S,bias,fam", PRED)
+def test_predictive_kernel_matches_oracle(N, D, S, bias, fam):
+  """edhmc_predictive (the fused contraction + link + reduction over draws) against the float64 restatement of
+  evaluate.py:132-143,158-162,222-227 on the same draws: 1e-5 relative."""
+  import torch
+  from edward_b200.criticisms.evaluate import predictive
+  rng = np.random.default_rng(N + D + S)
+  X = rng.standard_normal((N, D)).astype(np.float32)
+  W = (rng.standard_normal((S, D)) / np.sqrt(D)).astype(np.float32)
+  B = (0.3 * rng.standard_normal(S)).astype(np.float32) if bias else None
+  if fam == o.BERNOULLI_LOGIT:
+    y = (rng.random(N) < 0.5).astype(np.int32)
+  elif fam == o.NORMAL_IDENTITY:
+    y = rng.standard_normal(N).astype(np.float32)
+  else:
+    y = rng.poisson(1.0, N).astype(np.int32)
+  dev = torch.device("cuda")
+  mean, ll = predictive(torch.tensor(X, device=dev), torch.tensor(y, device=dev), torch.tensor(W, device=dev),
+                        torch.tensor(B, device=dev) if bias else None, fam, 0.7)
+  mean_o, ll_o = o.predictive(X, y, W, B, fam, 0.7)
+  assert np.max(np.abs(mean.cpu().numpy() - mean_o)) <= 1e-5 * max(1.0, np.max(np.abs(mean_o)))
+  assert np.max(np.abs(ll.cpu().numpy() - ll_o)) <= 1e-5 * np.max(np.abs(ll_o)) + 1e-6
+  # a strided design matrix (a column slice of a wider array) gives the same numbers
+  Xw = torch.zeros(N, D + 3, device=dev)
+  Xw[:, :D] = torch.tensor(X, device=dev)
+  mean2, ll2 = predictive(Xw[:, :D], torch.tensor(y, device=dev), torch.tensor(W, device=dev),
+                          torch.tensor(B, device=dev) if bias else None, fam, 0.7)
+  assert torch.equal(mean, mean2) and torch.equal(ll, ll2)

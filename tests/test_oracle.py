@@ -237,3 +237,28 @@ def test_oracle_beta_bernoulli_posterior_through_the_sigmoid():
   assert abs(z.mean() - a / (a + b)) < 0.02
   assert abs(z.var() - a * b / ((a + b) ** 2 * (a + b + 1))) < 0.004
   assert nacc > 0.5 * T
+
+
+def test_predictive_oracle_against_scipy():
+  """oracle.predictive (the restatement of evaluate.py:132-143,158-162,222-227) against scipy.stats densities."""
+  import scipy.stats as st
+  rng = np.random.default_rng(11)
+  N, D, S = 40, 5, 7
+  X = rng.standard_normal((N, D))
+  W = rng.standard_normal((S, D)) / 2
+  B = rng.standard_normal(S) / 3
+  eta = X @ W.T + B[None, :]
+  yb = (rng.random(N) < 0.5).astype(np.int32)
+  m, l = o.predictive(X, yb, W, B, o.BERNOULLI_LOGIT)
+  p = 1 / (1 + np.exp(-eta))
+  assert np.allclose(m, p.mean(axis=1), rtol=1e-12)
+  assert np.allclose(l, st.bernoulli.logpmf(yb[:, None], p).sum(axis=1), rtol=1e-10)
+  yn = rng.standard_normal(N)
+  m, l = o.predictive(X, yn, W, B, o.NORMAL_IDENTITY, 0.7)
+  assert np.allclose(m, eta.mean(axis=1), rtol=1e-12)
+  assert np.allclose(l, st.norm.logpdf(yn[:, None], eta, 0.7).sum(axis=1), rtol=1e-10)
+  yp = rng.poisson(1.0, N)
+  m, l = o.predictive(X, yp, W, None, o.POISSON_LOG)
+  eta0 = X @ W.T
+  assert np.allclose(m, np.exp(eta0).mean(axis=1), rtol=1e-12)
+  assert np.allclose(l, st.poisson.logpmf(yp[:, None], np.exp(eta0)).sum(axis=1), rtol=1e-10)
