@@ -257,9 +257,9 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
 
   if (warp == 0) {
     // ================= TMA producer =================
+    int s = 0, ph = 0;  // stage of tile i, parity of the phase its x_empty wait refers to ((i / NS) - 1) & 1
     for (int i = 0; i < nt; ++i) {
-      const int s = i % NS;
-      if (i >= NS) mbar_wait_s(XEMPTY(s), ((i / NS) - 1) & 1);
+      if (i >= NS) mbar_wait_s(XEMPTY(s), ph ^ 1);
       if (elect_one()) {
         fence_proxy_async_smem();
         mbar_arrive_expect_tx_s(XFULL(s), tile_bytes + kT2Rows * 4);
@@ -267,16 +267,21 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
         bulk_g2s_s(smem_u32(ysm + s * kT2Rows), a.yt + (tile0 + i) * kT2Rows, kT2Rows * 4, XFULL(s));
       }
       __syncwarp();
+      if (++s == NS) {
+        s = 0;
+        ph ^= 1;
+      }
     }
   } else if (warp == 1) {
     // ================= MMA1 issuer: Sᵀ[b] = Wᵀ·X(i)ᵀ =================
     const uint64_t da_h = smem_desc(smem_u32(A1), 2048, 128), da_l = smem_desc(smem_u32(A1) + a1_half, 2048, 128);
     const uint32_t id1 = idesc_tf32(128, kT2Rows);
     const int nks = Dp / 8;
+    int s = 0, ph = 0, sm1 = 0, phm1 = 0, sm2 = 0, phm2 = 0;  // (stage, phase parity) of tiles i, i-1, i-2
     for (int i = 0; i < nt; ++i) {
-      const int s = i % NS, b = i & 1;
-      mbar_wait_s(XFULL(s), (i / NS) & 1);
-      if (i >= 2) mbar_wait_s(XEMPTY((i - 2) % NS), ((i - 2) / NS) & 1);  // MMA2(i-2) has read R[b]
+      const int b = i & 1;
+      mbar_wait_s(XFULL(s), ph);
+      if (i >= 2) mbar_wait_s(XEMPTY(sm2), phm2);  // MMA2(i-2) has read R[b]
       tc_fence_after();
       const uint32_t xs = smem_u32(ring + s * stage_bytes);
       const uint64_t db_h = smem_desc(xs, kT3Pitch, 128), db_l = smem_desc(xs + plane_bytes, kT3Pitch, 128);
@@ -294,14 +299,23 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
         tc_commit(SREADY(b));
       }
       __syncwarp();
+      sm2 = sm1;
+      phm2 = phm1;
+      sm1 = s;
+      phm1 = ph;
+      if (++s == NS) {
+        s = 0;
+        ph ^= 1;
+      }
     }
   } else if (warp == 2) {
     // ================= MMA2 issuer: G' += R(i)·X(i), A = R from TMEM, B = B2T[b] =================
     const uint32_t id2 = idesc_tf32(128, kTcN2);
+    int s = 0, ph = 0, sg = 0, in_seg = 0;  // stage / phase of tile i; its segment and position inside it
     for (int i = 0; i < nt; ++i) {
-      const int s = i % NS, b = i & 1;
-      const int sg = i / seg_tiles, gb = sg & 1;
-      const bool seg_first = (i % seg_tiles) == 0, seg_last = (i % seg_tiles) == seg_tiles - 1 || i == nt - 1;
+      const int b = i & 1;
+      const int gb = sg & 1;
+      const bool seg_first = in_seg == 0, seg_last = in_seg == seg_tiles - 1 || i == nt - 1;
       mbar_wait_s(RREADY(b), (i >> 1) & 1);
       if (seg_first && sg >= 2) mbar_wait_s(GEMPTY(gb), ((sg >> 1) - 1) & 1);  // the epilogue has flushed segment sg-2
       tc_fence_after();
@@ -322,10 +336,21 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
         if (seg_last) tc_commit(GFULL(gb));
       }
       __syncwarp();
+      if (++in_seg == seg_tiles) {
+        in_seg = 0;
+        ++sg;
+      }
+      if (i + 1 < nt && ++s == NS) {
+        s = 0;
+        ph ^= 1;
+      }
     }
-    if (nt > 0) mbar_wait_s(XEMPTY((nt - 1) % NS), ((nt - 1) / NS) & 1);  // the last commit covers every MMA
+    if (nt > 0) mbar_wait_s(XEMPTY(s), ph);  // the last commit covers every MMA
   } else if (warp >= 4) {
     // ================= epilogue (16 warps): transpose the landed tile, then Sᵀ → R =================
+    // (Two groups of 8 warps converting alternate tiles concurrently were measured and are slower, 318 vs 288 us per step:
+    // R overwrites S in place and there are two S/R buffers, so MMA1(i+2) waits for MMA2(i), which waits for the epilogue
+    // of tile i — the epilogue LATENCY of one tile is on the critical path, and 8 warps take twice as long as 16.)
     const int q = warp & 3, cg = (warp - 4) >> 2;  // TMEM lane quadrant, column group (16 columns)
     const uint32_t lane_base = static_cast<uint32_t>(32 * q) << 16;
     const int col = cg * 16;
@@ -335,6 +360,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
     const int pk = et % npk, mbt = et / npk;  // valid when mbt < 16
     const int tp = pk / kc1, tkc = pk - tp * kc1;
     const bool has_item = mbt < 16;
+    const int it_src = tp * plane_bytes + tkc * kT3Pitch + mbt * 64;
+    const int it_dst = tp * kT3B2Plane + mbt * kT3B2Lbo + ((tkc * 4) >> 3) * kT3B2Sbo + ((tkc * 4) & 7) * 16;
     // float64 running sums of this thread's (chain, 16 features) in global memory (L2-resident), laid out
     // [row group][feature][chain] so that the 32 chains of a warp are 256 contiguous bytes per feature: segment 0
     // stores, later segments add with fire-and-forget reductions (no load round trip in the epilogue warps)
@@ -361,21 +388,24 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
       tc_fence_before();
       mbar_arrive(&bars[12 + gb]);
     };
+    // cursors kept incrementally (integer divisions by run-time values cost ~20 instructions each in every warp)
+    int s = 0, xph = 0, sm1 = 0, phm1 = 0, sm2 = 0, phm2 = 0;  // (stage, x_full parity) of tiles i, i-1, i-2
+    int sg = 0, in_seg = 0;
+    const bool plain = !(a.want_logp || a.family != 0);  // gradient-only Bernoulli pass: the short residual
     for (int i = 0; i < nt; ++i) {
-      const int s = i % NS, b = i & 1;
-      if (i > 0 && (i % seg_tiles) == 0) flush_segment(i / seg_tiles - 1);
+      const int b = i & 1;
+      if (i > 0 && in_seg == 0) flush_segment(sg - 1);
       const long long r0 = row_begin + static_cast<long long>(i) * kT2Rows;
       const int rows = row_end - r0 >= kT2Rows ? kT2Rows : static_cast<int>(row_end - r0);
-      mbar_wait_s(XFULL(s), (i / NS) & 1);
-      if (i >= 2) mbar_wait_s(XEMPTY((i - 2) % NS), ((i - 2) / NS) & 1);  // MMA2(i-2) has read B2T[b]
+      mbar_wait_s(XFULL(s), xph);
+      if (i >= 2) mbar_wait_s(XEMPTY(sm2), phm2);  // MMA2(i-2) has read B2T[b]
       if (has_item) {
-        const unsigned char* src = ring + s * stage_bytes + tp * plane_bytes + tkc * kT3Pitch + mbt * 64;
+        const unsigned char* src = ring + s * stage_bytes + it_src;
         float4 v0 = *reinterpret_cast<const float4*>(src);
         float4 v1 = *reinterpret_cast<const float4*>(src + 16);
         float4 v2 = *reinterpret_cast<const float4*>(src + 32);
         float4 v3 = *reinterpret_cast<const float4*>(src + 48);
-        const int d0 = tkc * 4;
-        unsigned char* dst = B2T + b * 2 * kT3B2Plane + tp * kT3B2Plane + mbt * kT3B2Lbo + (d0 >> 3) * kT3B2Sbo + (d0 & 7) * 16;
+        unsigned char* dst = B2T + b * 2 * kT3B2Plane + it_dst;
         *reinterpret_cast<float4*>(dst) = make_float4(v0.x, v1.x, v2.x, v3.x);
         *reinterpret_cast<float4*>(dst + 16) = make_float4(v0.y, v1.y, v2.y, v3.y);
         *reinterpret_cast<float4*>(dst + 32) = make_float4(v0.z, v1.z, v2.z, v3.z);
@@ -384,16 +414,25 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
       fence_proxy_async_smem();
       mbar_wait_s(SREADY(b), (i >> 1) & 1);
       tc_fence_after();
-      const float* ys = ysm + s * kT2Rows;
+      const float4* ys4 = reinterpret_cast<const float4*>(ysm + s * kT2Rows + col);
+      float yv[16];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 t = ys4[j4];
+        yv[4 * j4] = t.x;
+        yv[4 * j4 + 1] = t.y;
+        yv[4 * j4 + 2] = t.z;
+        yv[4 * j4 + 3] = t.w;
+      }
       uint32_t v[16], vh[16], vl[16];
       tmem_ld16(tm + 64 * b + lane_base + col, v);
       tmem_wait_ld();
-      if (a.want_logp || a.family != 0) {
+      if (!plain) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int m = col + j;
           float lpv, rv;
-          row_terms(a.family, __uint_as_float(v[j]), ys[m], a.lik_scale, lpv, rv);
+          row_terms(a.family, __uint_as_float(v[j]), yv[j], a.lik_scale, lpv, rv);
           if (m >= rows) {
             lpv = 0.0f;
             rv = 0.0f;
@@ -404,11 +443,22 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
           vh[j] = __float_as_uint(h);
           vl[j] = __float_as_uint(l);
         }
+      } else if (rows == kT2Rows) {
+        // full tile, gradient only: y - 1 / (1 + 2^(-eta log2 e)), five instructions and two special-function ops per
+        // element (absolute error <= 1.2e-7 per residual, random in sign: far inside the 1e-5 of the gradient)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float rv = bernoulli_resid_direct(__uint_as_float(v[j]), yv[j]);
+          float h, l;
+          split_tf32(rv, h, l);
+          vh[j] = __float_as_uint(h);
+          vl[j] = __float_as_uint(l);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int m = col + j;
-          float rv = bernoulli_resid_fast(__uint_as_float(v[j]), ys[m]);  // ex2.approx + rcp.approx, error <= 4e-7
+          float rv = bernoulli_resid_direct(__uint_as_float(v[j]), yv[j]);
           if (m >= rows) rv = 0.0f;
           float h, l;
           split_tf32(rv, h, l);
@@ -421,6 +471,18 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bars[8 + b]);  // R[b] and B2T[b] are ready
+      sm2 = sm1;
+      phm2 = phm1;
+      sm1 = s;
+      phm1 = xph;
+      if (++s == NS) {
+        s = 0;
+        xph ^= 1;
+      }
+      if (++in_seg == seg_tiles) {
+        in_seg = 0;
+        ++sg;
+      }
     }
     if (nt > 0) flush_segment((nt - 1) / seg_tiles);
   }
