@@ -130,8 +130,7 @@ __host__ __device__ inline int tc3_smem_layout(int Dp, int* off /*8*/) {
   o += tc3_stages(Dp) * stage_bytes;
   off[1] = o;  // ys[stages][64]
   o += kT3MaxStages * kT2Rows * 4;
-  off[2] = o;  // A1 hi, lo
-  o += 2 * (Dp / 4) * 2048;
+  off[2] = o;  // (formerly Wᵀ hi / lo as a shared-memory operand; Wᵀ now lives in TMEM)
   off[3] = o;  // B2T[2] {hi, lo}
   o += 2 * 2 * kT3B2Plane;
   off[4] = o;  // mbarriers: x_full[3], x_empty[3], s_ready[2], r_ready[2] + tmem slot
@@ -176,6 +175,13 @@ __global__ void k_mc_pretile(const McArgs a, float* xt, float* yt) {
   }
 }
 
+// development timeline (edhmc_set_chain_debug): clock64 of CTA (0,0) per tile and role, [64 tiles][16 slots]:
+// 0 TMA issued | 1 MMA1 inputs ready, 2 MMA1 issued | 3 MMA2 inputs ready, 4 MMA2 issued |
+// 5 epilogue: tile landed, 6 transposed, 7 S ready, 8 S loaded, 9 R stored and signalled
+#define T3_DBG(slot)                                                                       \
+  do {                                                                                     \
+    if (dbg_on && i < 64) a.dbg[i * 16 + (slot)] = clock64();                              \
+  } while (0)
 __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, const float* theta, int gate) {
   if (gate && !*a.need_init) return;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -186,18 +192,17 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
   const int NS = tc3_stages(Dp);
   unsigned char* ring = smem + off[0];
   float* ysm = reinterpret_cast<float*>(smem + off[1]);
-  unsigned char* A1 = smem + off[2];
   unsigned char* B2T = smem + off[3];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off[4]);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off[4] + 112);
   double* lpc = reinterpret_cast<double*>(smem + off[5]);
   const int kc1 = Dp / 4;
-  const int a1_half = kc1 * 2048;
   const int plane_bytes = kc1 * kT3Pitch;
   const int tile_bytes = 2 * plane_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cb = blockIdx.y * kMcChainsPerCta;
+  const bool dbg_on = a.dbg != nullptr && (a.dbg_lp != 0) == (a.want_logp != 0) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp < 3 || warp == 4);
   // barrier indices: 0-2 x_full, 3-5 x_empty, 6-7 s_ready, 8-9 r_ready
   const uint32_t bar0 = smem_u32(bars);
   auto XFULL = [&](int s) { return bar0 + static_cast<uint32_t>(s * 8); };
@@ -222,20 +227,6 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
   }
   __syncthreads();
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
-  for (int i = tid; i < kMcChainsPerCta * kc1; i += kT3Threads) {
-    const int c = i % kMcChainsPerCta, kc = i / kMcChainsPerCta;
-    float4 h, l;
-    float* hp = &h.x;
-    float* lq = &l.x;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int d = kc * 4 + e;
-      const float v = d < D ? theta[static_cast<size_t>(cb + c) * D + d] : 0.0f;
-      split_tf32(v, hp[e], lq[e]);
-    }
-    *reinterpret_cast<float4*>(A1 + kc * 2048 + c * 16) = h;
-    *reinterpret_cast<float4*>(A1 + a1_half + kc * 2048 + c * 16) = l;
-  }
   // B2T: features Dp..63 and the padding are never written by the transpose: zero once
   for (int i = tid; i < 4 * kT3B2Plane / 16; i += kT3Threads) reinterpret_cast<float4*>(B2T)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_proxy_async_smem();
@@ -244,6 +235,31 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
   const uint32_t tm_g = tm + 256;  // G'[0] at +256, G'[1] at +320
+  // Wᵀ (this CTA's 128 chains x Dp features, split hi / lo) goes to TMEM columns 384..447 / 448..511 and is the A operand
+  // of MMA1 from there: read from shared memory instead, every MMA1 instruction fetched 4 KB of Wᵀ next to 2 KB of X and
+  // ran at 53 cycles (the per-role timeline, profiles/r02_cfg3_*) against 36 for MMA2, whose A operand is in TMEM.
+  const uint32_t tm_w = tm + 384;
+  if (warp >= 4) {
+    const int q = warp & 3, cg = (warp - 4) >> 2;
+    const int c = cb + 32 * q + lane;
+    uint32_t wh[16], wl[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int d = cg * 16 + j;
+      const float v = d < D ? theta[static_cast<size_t>(c) * D + d] : 0.0f;
+      float h, l;
+      split_tf32(v, h, l);
+      wh[j] = __float_as_uint(h);
+      wl[j] = __float_as_uint(l);
+    }
+    const uint32_t lb = static_cast<uint32_t>(32 * q) << 16;
+    tmem_st16(tm_w + lb + cg * 16, wh);
+    tmem_st16(tm_w + 64 + lb + cg * 16, wl);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   long long u0, u1;
   tile_range(a.n_rows, a.n_rowgroups, blockIdx.x, u0, u1);
@@ -267,50 +283,52 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
         bulk_g2s_s(smem_u32(ysm + s * kT2Rows), a.yt + (tile0 + i) * kT2Rows, kT2Rows * 4, XFULL(s));
       }
       __syncwarp();
+      T3_DBG(0);
       if (++s == NS) {
         s = 0;
         ph ^= 1;
       }
     }
   } else if (warp == 1) {
-    // ================= MMA1 issuer: Sᵀ[b] = Wᵀ·X(i)ᵀ =================
-    const uint64_t da_h = smem_desc(smem_u32(A1), 2048, 128), da_l = smem_desc(smem_u32(A1) + a1_half, 2048, 128);
+    // ================= MMA issuer (both contractions) =================
+    // One thread issues MMA1 and MMA2: tcgen05.mma instructions of one thread execute in issue order, so MMA1(i+2), which
+    // overwrites S/R[b], can be issued right behind MMA2(i), which reads R[b], without waiting for it to COMPLETE. With
+    // two issuer warps that hazard needed a completion wait (x_empty), and R(i) → MMA2(i) done → MMA1(i+2) issued → done
+    // → epilogue(i+2) was the critical path of the pass: 4,400 cycles per two tiles (per-role timeline, profiles/r02_cfg3_*).
+    //   MMA1  Sᵀ[b] = Wᵀ·X(j)ᵀ   A = Wᵀ from TMEM, B = the landed tile
+    //   MMA2  G'   += R(i)·X(i)  A = R from TMEM,  B = B2T[b]
     const uint32_t id1 = idesc_tf32(128, kT2Rows);
+    const uint32_t id2 = idesc_tf32(128, kTcN2);
     const int nks = Dp / 8;
-    int s = 0, ph = 0, sm1 = 0, phm1 = 0, sm2 = 0, phm2 = 0;  // (stage, phase parity) of tiles i, i-1, i-2
-    for (int i = 0; i < nt; ++i) {
+    int s1 = 0, ph1 = 0;  // (stage, x_full parity) of the next tile MMA1 is issued for
+    auto issue_mma1 = [&](int i) {
       const int b = i & 1;
-      mbar_wait_s(XFULL(s), ph);
-      if (i >= 2) mbar_wait_s(XEMPTY(sm2), phm2);  // MMA2(i-2) has read R[b]
+      mbar_wait_s(XFULL(s1), ph1);
       tc_fence_after();
-      const uint32_t xs = smem_u32(ring + s * stage_bytes);
+      T3_DBG(1);
+      const uint32_t xs = smem_u32(ring + s1 * stage_bytes);
       const uint64_t db_h = smem_desc(xs, kT3Pitch, 128), db_l = smem_desc(xs + plane_bytes, kT3Pitch, 128);
       const uint32_t ts = tm + 64 * b;
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           if (ks < nks) {
-            const uint64_t oa = static_cast<uint64_t>(ks * (4096 >> 4)), ob = static_cast<uint64_t>(ks * ((2 * kT3Pitch) >> 4));
-            tc_mma_ss(ts, da_h + oa, db_h + ob, id1, ks > 0);
-            tc_mma_ss(ts, da_h + oa, db_l + ob, id1, 1);
-            tc_mma_ss(ts, da_l + oa, db_h + ob, id1, 1);
+            const uint64_t ob = static_cast<uint64_t>(ks * ((2 * kT3Pitch) >> 4));
+            tc_mma_ts(ts, tm_w + ks * 8, db_h + ob, id1, ks > 0);
+            tc_mma_ts(ts, tm_w + ks * 8, db_l + ob, id1, 1);
+            tc_mma_ts(ts, tm_w + 64 + ks * 8, db_h + ob, id1, 1);
           }
         }
         tc_commit(SREADY(b));
       }
       __syncwarp();
-      sm2 = sm1;
-      phm2 = phm1;
-      sm1 = s;
-      phm1 = ph;
-      if (++s == NS) {
-        s = 0;
-        ph ^= 1;
+      T3_DBG(2);
+      if (++s1 == NS) {
+        s1 = 0;
+        ph1 ^= 1;
       }
-    }
-  } else if (warp == 2) {
-    // ================= MMA2 issuer: G' += R(i)·X(i), A = R from TMEM, B = B2T[b] =================
-    const uint32_t id2 = idesc_tf32(128, kTcN2);
+    };
+    for (int i = 0; i < 2 && i < nt; ++i) issue_mma1(i);
     int s = 0, ph = 0, sg = 0, in_seg = 0;  // stage / phase of tile i; its segment and position inside it
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
@@ -319,6 +337,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
       mbar_wait_s(RREADY(b), (i >> 1) & 1);
       if (seg_first && sg >= 2) mbar_wait_s(GEMPTY(gb), ((sg >> 1) - 1) & 1);  // the epilogue has flushed segment sg-2
       tc_fence_after();
+      T3_DBG(3);
       const uint32_t bs = smem_u32(B2T + b * 2 * kT3B2Plane);
       const uint64_t d2_h = smem_desc(bs, kT3B2Lbo, kT3B2Sbo), d2_l = smem_desc(bs + kT3B2Plane, kT3B2Lbo, kT3B2Sbo);
       const uint32_t r_h = tm + 64 * b, r_l = tm + 128 + 64 * b;
@@ -336,6 +355,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
         if (seg_last) tc_commit(GFULL(gb));
       }
       __syncwarp();
+      T3_DBG(4);
+      if (i + 2 < nt) issue_mma1(i + 2);  // into S/R[b], behind MMA2(i) in the same in-order pipe
       if (++in_seg == seg_tiles) {
         in_seg = 0;
         ++sg;
@@ -392,13 +413,18 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
     int s = 0, xph = 0, sm1 = 0, phm1 = 0, sm2 = 0, phm2 = 0;  // (stage, x_full parity) of tiles i, i-1, i-2
     int sg = 0, in_seg = 0;
     const bool plain = !(a.want_logp || a.family != 0);  // gradient-only Bernoulli pass: the short residual
+    const int flush_at = seg_tiles > 1 ? 1 : 0;
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
-      if (i > 0 && in_seg == 0) flush_segment(sg - 1);
+      // The float64 flush of segment sg-1 waits for ITS last MMA2, which the tensor pipe may still be executing when
+      // the first tile of segment sg arrives here; flushing one tile later (G' is double-buffered, the buffer is needed
+      // again only a whole segment later) keeps the epilogue from idling behind the tensor pipe.
+      if (sg > 0 && in_seg == flush_at) flush_segment(sg - 1);
       const long long r0 = row_begin + static_cast<long long>(i) * kT2Rows;
       const int rows = row_end - r0 >= kT2Rows ? kT2Rows : static_cast<int>(row_end - r0);
       mbar_wait_s(XFULL(s), xph);
       if (i >= 2) mbar_wait_s(XEMPTY(sm2), phm2);  // MMA2(i-2) has read B2T[b]
+      T3_DBG(5);
       if (has_item) {
         const unsigned char* src = ring + s * stage_bytes + it_src;
         float4 v0 = *reinterpret_cast<const float4*>(src);
@@ -412,8 +438,10 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
         *reinterpret_cast<float4*>(dst + 48) = make_float4(v0.w, v1.w, v2.w, v3.w);
       }
       fence_proxy_async_smem();
+      T3_DBG(6);
       mbar_wait_s(SREADY(b), (i >> 1) & 1);
       tc_fence_after();
+      T3_DBG(7);
       const float4* ys4 = reinterpret_cast<const float4*>(ysm + s * kT2Rows + col);
       float yv[16];
 #pragma unroll
@@ -427,7 +455,29 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
       uint32_t v[16], vh[16], vl[16];
       tmem_ld16(tm + 64 * b + lane_base + col, v);
       tmem_wait_ld();
-      if (!plain) {
+      T3_DBG(8);
+      if (a.family == 0 && !plain) {
+        // last leapfrog step of a trajectory, Bernoulli: residual AND log-likelihood from three special-function ops per
+        // element (common.cuh bernoulli_terms_fast); the 16 terms of a tile are summed in float32, one float64 add per tile
+        // (the general path below paced this pass at 8,300 cycles per tile against 2,150 for a gradient-only one)
+        float lpt = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int m = col + j;
+          float lpv, rv;
+          bernoulli_terms_fast(__uint_as_float(v[j]), yv[j], lpv, rv);
+          if (m >= rows) {
+            lpv = 0.0f;
+            rv = 0.0f;
+          }
+          lpt += lpv;
+          float h, l;
+          split_tf32(rv, h, l);
+          vh[j] = __float_as_uint(h);
+          vl[j] = __float_as_uint(l);
+        }
+        lp += static_cast<double>(lpt);
+      } else if (!plain) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int m = col + j;
@@ -471,6 +521,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bars[8 + b]);  // R[b] and B2T[b] are ready
+      T3_DBG(9);
       sm2 = sm1;
       phm2 = phm1;
       sm1 = s;
@@ -484,7 +535,13 @@ __global__ void __launch_bounds__(kT3Threads, 1) k_mc_pass_tc3(const McArgs a, c
         ++sg;
       }
     }
-    if (nt > 0) flush_segment((nt - 1) / seg_tiles);
+    if (nt > 0) {
+      // segments whose deferred flush did not come up inside the loop: the one before the last if the last segment has
+      // a single tile, then the last one
+      const int last_seg = (nt - 1) / seg_tiles;
+      if (last_seg > 0 && flush_at == 1 && (nt - 1) - last_seg * seg_tiles < 1) flush_segment(last_seg - 1);
+      flush_segment(last_seg);
+    }
   }
 
   // ---- write this row group's partial sums ----

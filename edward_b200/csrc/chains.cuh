@@ -63,6 +63,7 @@ struct McArgs {
   const float* xt;
   const float* yt;  // [ntiles64][64] float
   long long* dbg;  // optional per-role clock64 timeline of CTA (0,0): [tile][16]
+  int dbg_lp;      // which passes stamp it: 1 = the log-likelihood passes, 0 = the gradient-only ones
 };
 
 // host launchers (chains.cu)

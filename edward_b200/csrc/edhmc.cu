@@ -1466,6 +1466,7 @@ static void fill_mc_args(edhmc_handle* h, McArgs& a) {
   a.seed = h->seed;
   a.trace = h->mc_trace;
   a.dbg = h->mc_dbg;
+  a.dbg_lp = getenv("EDHMC_MC_DBG_LP") ? atoi(getenv("EDHMC_MC_DBG_LP")) : 0;
   a.xt = h->mc_xt;
   a.yt = h->mc_yt;
 }
