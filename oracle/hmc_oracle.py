@@ -3,14 +3,18 @@
 TEST INFRASTRUCTURE ONLY. Nothing under edward_b200/ may import this module; only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, as the checker.
 
-PARITY UNPINNED. The reference (/root/reference, blei-lab/edward 1.3.5) delegates every arithmetic
-op on this path to TensorFlow 1.x (`tensorflow>=1.2.0rc0`, setup.py:18; CI pins tensorflow==1.5.0,
-.travis.yml:40), which is neither vendored nor installable here, and the reference's own tests hold
-no golden vector / known-answer value for this path (tests/inferences/hmc_test.py:33-35,79-80 assert
-posterior moments only). This file therefore restates
+PARITY PIN. The reference (/root/reference, blei-lab/edward 1.3.5) delegates every arithmetic op on this path to
+TensorFlow 1.x (`tensorflow>=1.2.0rc0`, setup.py:18; CI pins tensorflow==1.5.0, .travis.yml:40), which is neither
+vendored nor installable here, and the reference's own tests hold no golden vector / known-answer value for this path
+(tests/inferences/hmc_test.py:33-35,79-80 assert posterior moments only). TensorFlow output is therefore NOT available;
+the pin is the next best thing: tests/golden/make_reference_golden.py + ref_exec.py EXECUTE the reference's own
+`leapfrog` and `HMC.build_update` source (edward/inferences/hmc.py, read from /root/reference at generation time) with
+torch standing in for the few tf.* calls they make and torch.autograd for tf.gradients on the literal TF density
+expressions, and the resulting fixtures tests/golden/ref_*.npz (committed with the generator) are what this file is
+held to (tests/test_reference_exec.py), float32 and float64. This file restates
   * the algorithm from the reference's own sources (cited per function), and
   * the TF 1.5 densities from their published definitions (cited as [TF 1.5]),
-and is pinned by: scipy.stats densities, finite differences, the in-tree closed forms
+and is additionally pinned by: scipy.stats densities, finite differences, the in-tree closed forms
 edward/inferences/conjugacy/conjugate_log_probs.py:21-24,134-141, and the reference's statistical
 HMC tests (see tests/test_oracle.py).
 
