@@ -284,10 +284,19 @@ __global__ void __launch_bounds__(kMwThreads, 1) k_mcw_gemm(const McwArgs a, int
             const float eta = __uint_as_float(v[j]);
             const float yv = __ldg(a.yt + row0 + j);
             float lpv = 0.0f, r;
-            if (a.want_logp)
+            // Bernoulli: the special-function forms of common.cuh (three / two MUFU ops per element) — with the general
+            // row_terms (expf, logf, a division) the epilogue of a log-likelihood step outlasted the MMAs of the next tile
+            // (tensor pipe 56 % active on those steps against 91 % on gradient-only ones, profiles r01f)
+            if (a.family == 0) {
+              if (a.want_logp)
+                bernoulli_terms_fast(eta, yv, lpv, r);
+              else
+                r = bernoulli_resid_direct(eta, yv);
+            } else if (a.want_logp) {
               row_terms(a.family, eta, yv, a.lik_scale, lpv, r);
-            else
+            } else {
               r = row_resid(a.family, eta, yv, a.lik_scale);
+            }
             if (row0 + j >= a.n_rows) {
               lpv = 0.0f;
               r = 0.0f;
