@@ -15,6 +15,7 @@
 // and log joint of the transition's start state — are cached here from the previous transition.
 #pragma once
 #include "stream_cta.cuh"
+#include "stream_ldg.cuh"
 
 namespace edhmc {
 
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   // Two copies, selected by the parity of the pass: thread 0 may already store the state for pass p+1 while a slow
   // warp still reads the state of pass p (a mid-trajectory serial section has no barrier between the two).
   __shared__ ChainRegs s_cs2[2];
-  const int ngroups = RM == 1 ? NW / a.wpg : NW;  // ring mode 1: warp groups, each with a row range and a ring
+  const int ngroups = RM == 2 ? 1 : (RM == 1 ? NW / a.wpg : NW);  // ring mode 1: warp groups, each with a row range and a ring
   const SmemLayout sm = carve_smem(smem_raw, a, ngroups);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = a.P, D = a.D;
@@ -330,18 +331,24 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   float* zc = g + ppad;
   float* gc = zc + ppad;
 
-  if constexpr (RM == 1)
+  if constexpr (RM == 2) {
+    for (int i = tid; i < a.wpad; i += kThreads) sm.theta_s[i] = 0.0f;  // no ring, no barriers: theta only
+    __syncthreads();
+  } else if constexpr (RM == 1) {
     smem_setup_cta(sm, a, ngroups);
-  else
+  } else {
     smem_setup(sm, a, NW);
+  }
   const PlanRegs pr = plan_regs(a);
   const uint64_t policy = a.l2_hint == 2 ? l2_policy_pin_fraction(a.l2_frac) : (a.l2_hint ? l2_policy_evict_last() : 0ull);
   // ring mode 0: every warp owns a row range and a private ring; ring mode 1: the CTA owns a row range and one ring
   const int group = RM == 1 ? warp / a.wpg : warp;
-  const WarpTiles wt = warp_tiles(a, blockIdx.x * ngroups + group, ncta * ngroups);
-  using RingT = typename std::conditional<RM == 1, CtaRing, Ring>::type;
+  const WarpTiles wt = RM == 2 ? WarpTiles{} : warp_tiles(a, blockIdx.x * ngroups + group, ncta * ngroups);
+  using RingT = typename std::conditional<RM >= 1, CtaRing, Ring>::type;
   RingT ring;
-  if constexpr (RM == 1)
+  if constexpr (RM == 2)
+    ring.cpass = 0;  // ring mode 2 has no ring: only the pass parity (zig-zag direction) lives here
+  else if constexpr (RM == 1)
     cta_ring_init(ring, sm, a, group);
   else
     ring_init(ring, sm.ring + warp * a.S * a.stage_floats, sm.bars + warp * kMaxStages);
@@ -448,12 +455,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
     ring.cpass = par0;
     if constexpr (RM == 1)
       ring.par0 = par0;
-    else
+    else if constexpr (RM == 0)
       ring.ipass = par0;
   }
   if constexpr (RM == 1)
     cta_ring_prologue(pr, wt, ring, n_passes, policy, tid == group * a.wpg * 32);
-  else
+  else if constexpr (RM == 0)
     ring_prologue(pr, wt, ring, n_passes, lane, policy);
   if (!single) {
     if (in_init) {
@@ -532,10 +539,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
     const bool want_lp = single ? (a.single_lp != 0) : (in_init_p || s_p + 1 >= a.L);
     EDHMC_TL(0, clock64());
     EDHMC_TL(6, global_timer_ns());
-    if constexpr (RM == 1)
+    if constexpr (RM == 2) {
+      stream_pass_ldg<K, NW>(a, sm, bias, want_lp, a.zigzag && (ring.cpass & 1));
+      ++ring.cpass;
+    } else if constexpr (RM == 1) {
       stream_pass_cta<G, V, K, NW>(a, pr, wt, ring, sm, bias, policy, want_lp);
-    else
+    } else {
       stream_pass<G, V, K, NW>(a, pr, wt, ring, sm, bias, policy, want_lp);
+    }
     EDHMC_TL(1, clock64());
 
     if (single) {

@@ -79,6 +79,10 @@ struct KArgs {
   int tm;            // tl & 3: per-tile drift of the 16-byte alignment (non-zero only if ldx % 4 != 0)
   int wpg;           // ring mode 1: warps per group (each group owns a row range and a ring of S stages)
   int interleave;    // 1: tile t belongs to warp t % (grid*NW) (moving window); 0: contiguous row range per warp
+  // ---- ring mode 2 (stream_ldg.cuh): X re-laid at bind time into column-pair-major 32-row tiles, read with LDG ----
+  const float2* Xt;  // [n_tiles][Kact][32] float2
+  const float* Yt;   // [n_tiles][32]
+  long long n_tiles;
   // ---- launch mode ----
   int mode;               // 0: run n_iter transitions (cooperative launch); 1: one data pass at theta_in
   int gate;               // mode 1: return immediately unless sc->need_init

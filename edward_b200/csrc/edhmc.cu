@@ -148,7 +148,11 @@ struct edhmc_handle {
   const void* y = nullptr;
   int y_dtype = 0;
   int* y_owned = nullptr;  // int32 copy when the caller's y is uint8
-  Plan plan;
+  Plan plan;        // the plan of full-data passes (HMC, logp_grad, full-batch SGLD / SGHMC)
+  Plan plan_rows;   // a plan that reads the caller's row-major X (ring mode 0 / 1): row-window passes (mini-batches)
+  float2* d_xt = nullptr;  // ring mode 2: X re-laid into column-pair-major 32-row tiles (stream_ldg.cuh), owned
+  float* d_yt = nullptr;
+  long long n_tiles = 0;
   int zigzag = 1;
   int l2_hint = 0;
   float l2_frac = 1.0f;
@@ -369,11 +373,11 @@ static bool make_plan_cta(edhmc_handle* h, Plan& out) {
 // large tiles amortise the per-tile bookkeeping best), else the fewest lanes whose slice is <= 32 floats;
 // K = smallest compiled tier >= chunks per lane; warps per CTA from the register footprint (warps_for);
 // tiles sized so that >= 3 ring stages per warp fit in shared memory.
-static int make_plan(edhmc_handle* h) {
+static int make_plan_rows(edhmc_handle* h) {
   const edhmc_cfg& c = h->cfg;
   {
     int ring = 1;  // EDHMC_RING=0 keeps the per-warp rings for every shape (A/B runs)
-    if (const char* e = getenv("EDHMC_RING")) ring = atoi(e);
+    if (const char* e = getenv("EDHMC_RING")) ring = atoi(e) == 0 ? 0 : 1;
     Plan pc;
     if (ring == 1 && !h->no_cta_ring && !h->interleave && make_plan_cta(h, pc)) {
       h->plan = pc;
@@ -498,7 +502,73 @@ static int make_plan(edhmc_handle* h) {
   return 0;
 }
 
-static void fill_args(edhmc_handle* h, KArgs& a) {
+// Ring mode 2 (stream_ldg.cuh): narrow rows (D <= 64) read from a bind-time re-lay of X with coalesced LDG.64, one lane per
+// row, theta in shared memory, 12 warps per CTA, no shared-memory staging.
+static bool make_plan_ldg(edhmc_handle* h, Plan& out) {
+  const edhmc_cfg& c = h->cfg;
+  const int D = c.n_features;
+  if (D > 64) return false;
+  static const int tiers2[] = {1, 2, 4, 6, 8, 10, 12, 14, 16, 24, 27, 32};
+  const int chunks = (D + 1) / 2;
+  int K = 0;
+  for (int t : tiers2)
+    if (t >= chunks) {
+      K = t;
+      break;
+    }
+  if (!K) return false;
+  Plan p;
+  p.RM = 2;
+  p.G = 1;
+  p.V = 2;
+  p.K = K;
+  p.Kact = chunks;
+  p.NW = 12;
+  p.WPG = 12;
+  p.J = 1;
+  p.RT = 32;
+  p.S = 0;
+  p.stage_floats = 0;
+  p.wpad = 2 * K;
+  p.fn = lookup_kernel(1, 2, K, p.NW, 2);
+  if (!p.fn) return false;
+  size_t offs[8];
+  p.smem = smem_layout_bytes(1, 0, 0, h->P, p.wpad, offs);
+  if (cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p.fn, p.NW * 32, p.smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return false;
+  }
+  const long long n_tiles = (c.n_rows + 31) / 32;
+  long long want = (n_tiles + 2ll * p.NW - 1) / (2ll * p.NW);  // >= two tiles per warp before another SM is used
+  if (want < 1) want = 1;
+  p.grid = static_cast<int>(want < h->num_sms ? want : h->num_sms);
+  out = p;
+  return true;
+}
+
+// Which narrow shapes take ring mode 2 (tools/shape_sweep_ldg.sh, same-box A/B, profiles/README round 2): every D <= 48 and
+// D = 63, 64 — there it runs at 98-109 % of the HBM copy peak against 58-94 % for the shared-memory rings (power-of-two
+// strides conflict in shared memory, rows of few columns leave the rings latency-bound), and L2-resident sizes gain
+// 1.3-1.9x. For 49 <= D <= 62 the CTA-wide ring is as fast or faster (cfg 2, D = 54: 16.1 us per step against 19.0).
+// EDHMC_RING: unset = that rule; 2 = ring mode 2 wherever eligible; 1 / 0 = row-major plans only (A/B runs).
+static int make_plan(edhmc_handle* h) {
+  if (int rc = make_plan_rows(h)) return rc;
+  h->plan_rows = h->plan;
+  int ring = -1;
+  if (const char* e = getenv("EDHMC_RING")) ring = atoi(e);
+  const int D = h->cfg.n_features;
+  const bool want = ring == 2 || (ring < 0 && (D <= 48 || D >= 63));
+  Plan pl;
+  if (want && !h->interleave && make_plan_ldg(h, pl)) h->plan = pl;
+  return 0;
+}
+
+static void fill_args(edhmc_handle* h, KArgs& a, const Plan* pp = nullptr) {
   memset(&a, 0, sizeof(a));
   const edhmc_cfg& c = h->cfg;
   a.X = h->X;
@@ -515,7 +585,10 @@ static void fill_args(edhmc_handle* h, KArgs& a) {
   a.prior_scale = h->d_prior_scale;
   a.prior_kind = h->d_prior_kind;
   a.prior_const = h->prior_const;
-  const Plan& p = h->plan;
+  const Plan& p = pp ? *pp : h->plan;
+  a.Xt = h->d_xt;
+  a.Yt = h->d_yt;
+  a.n_tiles = h->n_tiles;
   a.Kact = p.Kact;
   a.J = p.J;
   a.RT = p.RT;
@@ -821,6 +894,8 @@ int edhmc_destroy(edhmc_t* h) {
   h_free(h, h->d_bar);
   h_free(h, h->d_ll_part);
   h_free(h, h->d_ll_theta);
+  if (h->d_xt) cudaFree(h->d_xt);
+  if (h->d_yt) cudaFree(h->d_yt);
   h_free(h, h->d_ll_group);
   h_free(h, h->d_ticket);
   h_free(h, h->d_sums);
@@ -871,7 +946,7 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
   h->X = X;
   h->y = y;
   h->y_dtype = h->cfg.y_dtype;
-  if (h->plan.RM == 1 && h->cfg.y_dtype != EDHMC_Y_U8 && reinterpret_cast<uintptr_t>(y) % 16 != 0) {
+  if (h->plan_rows.RM == 1 && h->cfg.y_dtype != EDHMC_Y_U8 && reinterpret_cast<uintptr_t>(y) % 16 != 0) {
     h->no_cta_ring = true;  // the CTA-wide ring bulk-copies y: fall back to the per-warp rings
     if (int rc = make_plan(h)) return rc;
   }
@@ -881,6 +956,33 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
     CUDA_TRY(cudaGetLastError());
     h->y = h->y_owned;
     h->y_dtype = EDHMC_Y_I32;
+  }
+  if (h->plan.RM == 2) {
+    // ring mode 2 reads its own column-pair-major copy of X / y (stream_ldg.cuh): re-lay once per bind
+    const long long n_tiles = (h->cfg.n_rows + 31) / 32;
+    if (n_tiles != h->n_tiles || (!h->d_xt && n_tiles > 0)) {
+      if (h->d_xt) cudaFree(h->d_xt);
+      if (h->d_yt) cudaFree(h->d_yt);
+      h->d_xt = nullptr;
+      h->d_yt = nullptr;
+      h->n_tiles = n_tiles;
+      if (n_tiles > 0) {
+        const size_t xb = static_cast<size_t>(n_tiles) * h->plan.Kact * 32 * sizeof(float2);
+        if (cudaMalloc(reinterpret_cast<void**>(&h->d_xt), xb) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&h->d_yt), static_cast<size_t>(n_tiles) * 32 * sizeof(float)) != cudaSuccess) {
+          cudaGetLastError();
+          if (h->d_xt) cudaFree(h->d_xt);
+          h->d_xt = nullptr;
+          h->n_tiles = 0;
+          h->plan = h->plan_rows;  // not enough memory for the copy: stream the caller's X through the shared-memory ring
+        }
+      }
+    }
+    if (h->plan.RM == 2 && n_tiles > 0) {
+      k_relay_tiles<<<h->num_sms * 8, 256, 0, stream>>>(X, h->cfg.n_rows, h->cfg.ldx, h->cfg.n_features, h->y, h->y_dtype,
+                                                       h->plan.Kact, n_tiles, h->d_xt, h->d_yt);
+      CUDA_TRY(cudaGetLastError());
+    }
   }
   h->bound = true;
   // data changed: the cached log joint / gradient no longer apply
@@ -905,7 +1007,8 @@ int edhmc_bind_data(edhmc_t* h, const float* X, const void* y, int check_finite,
 }
 
 static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int gate, long long gsi, cudaStream_t stream,
-                       int want_lp = 1) {
+                       int want_lp = 1, const Plan* pp = nullptr) {
+  const Plan& pl = pp ? *pp : h->plan;
   KArgs aa = a;
   aa.mode = 1;
   aa.gate = gate;
@@ -913,7 +1016,7 @@ static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int 
   aa.par0 = static_cast<int>(gsi & 1);
   aa.theta_in = theta;
   void* params[] = {&aa};
-  CUDA_TRY(cudaLaunchKernel(h->plan.fn, dim3(h->plan.grid), dim3(h->plan.NW * 32), params, h->plan.smem, stream));
+  CUDA_TRY(cudaLaunchKernel(pl.fn, dim3(pl.grid), dim3(pl.NW * 32), params, pl.smem, stream));
   ++h->launches_last;
   return 0;
 }
@@ -1409,10 +1512,21 @@ int edhmc_sgmcmc_run(edhmc_t* h, int32_t kind, float* params, int64_t ldp, int64
   h->passes_last = n_iter;
   h->plan_in_use = EDHMC_PLAN_STEPWISE;
   const int64_t nb = batch_rows > 0 ? h->cfg.n_rows / batch_rows : 1;
+  // mini-batches are row windows of the caller's X: they take the row-major plan (ring mode 2 reads whole 32-row tiles of
+  // its own copy)
+  const Plan* pp = batch_rows > 0 ? &h->plan_rows : &h->plan;
+  KArgs arows;
+  if (batch_rows > 0) {
+    fill_args(h, arows, pp);
+    arows.params = a.params;
+    arows.ldp = a.ldp;
+    arows.t0 = a.t0;
+    arows.n_iter = a.n_iter;
+  }
   for (int64_t it = 0; it < n_iter; ++it) {
     const int64_t t = t0 + it;
     const int64_t t_prev = t > 0 ? t - 1 : 0;
-    KArgs ab = a;
+    KArgs ab = batch_rows > 0 ? arows : a;
     if (batch_rows > 0) {  // mini-batch: a contiguous slice of the bound rows
       const int64_t lo = (t % nb) * batch_rows;
       ab.X = a.X + lo * a.ldx;
@@ -1420,7 +1534,7 @@ int edhmc_sgmcmc_run(edhmc_t* h, int32_t kind, float* params, int64_t ldp, int64
       ab.n_rows = batch_rows;
     }
     int rc;
-    if ((rc = launch_pass(h, ab, params + t_prev * ldp, 0, t, stream))) return rc;
+    if ((rc = launch_pass(h, ab, params + t_prev * ldp, 0, t, stream, 1, pp))) return rc;
     if ((rc = allreduce_sums(h, stream))) return rc;
     k_sg_update<<<1, kChainThreads, 0, stream>>>(a, g, it);
     CUDA_TRY(cudaGetLastError());

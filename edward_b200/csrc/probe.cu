@@ -72,6 +72,60 @@ __global__ void __launch_bounds__(128, 1) k_probe_tma(const unsigned char* __res
   }
 }
 
+// mode 2..4: what a one-lane-per-row GEMV pass costs when X is laid out in column-pair-major 32-row tiles
+// ([tile][27 pairs][32 rows][2 floats], 6,912 bytes per tile for D = 54) and read straight into registers with coalesced
+// LDG.64 — no shared-memory staging. Same arithmetic per row as the sampler's pass (dot, sigmoid residual, gradient FMA).
+template <int NW, bool TSM>
+__global__ void __launch_bounds__(NW * 32, 1) k_probe_gemv(const float2* __restrict__ xt, long long ntiles, int iters, float* sink) {
+  __shared__ float2 th_s[27];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 27) th_s[threadIdx.x] = make_float2(0.001f * (threadIdx.x + 1), -0.002f * (threadIdx.x + 1));
+  __syncthreads();
+  float2 th[TSM ? 1 : 27];
+  if (!TSM) {
+#pragma unroll
+    for (int i = 0; i < 27; ++i) th[i] = th_s[i];
+  }
+  float2 g[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) g[i] = make_float2(0.f, 0.f);
+  const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long t0 = blockIdx.x * per, t1 = (t0 + per < ntiles) ? t0 + per : ntiles;
+  const long long cnt = t1 > t0 ? t1 - t0 : 0;
+  for (int it = 0; it < iters; ++it) {
+    for (long long k = warp; k < cnt; k += NW) {
+      const long long t = (it & 1) ? (t1 - 1 - k) : (t0 + k);
+      const float2* p = xt + t * (27 * 32) + lane;
+      float2 x[27];
+#pragma unroll
+      for (int i = 0; i < 27; ++i) x[i] = __ldcg(p + i * 32);
+      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 27; ++i) {
+        const float2 w = TSM ? th_s[i] : th[i];
+        if (i & 1)
+          a1 = __ffma2_rn(x[i], w, a1);
+        else
+          a0 = __ffma2_rn(x[i], w, a0);
+      }
+      const float eta = (a0.x + a0.y) + (a1.x + a1.y);
+      float e, inv;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * fabsf(eta)));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.0f + e));
+      const float q = e * inv;
+      const float yv = (x[0].x > 0.0f) ? 1.0f : 0.0f;
+      const float r = (eta >= 0.0f) ? (yv - 1.0f) + q : yv - q;
+      const float2 r2 = make_float2(r, r);
+#pragma unroll
+      for (int i = 0; i < 27; ++i) g[i] = __ffma2_rn(r2, x[i], g[i]);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 27; ++i) s += g[i].x + g[i].y;
+  if (s == 123.456f) *sink = s;
+}
+
 }  // namespace edhmc
 
 extern "C" int edhmc_probe_read(const void* buf, int64_t bytes, int32_t iters, int32_t mode, void* sink, void* stream_) {
@@ -81,7 +135,21 @@ extern "C" int edhmc_probe_read(const void* buf, int64_t bytes, int32_t iters, i
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return EDHMC_ERR_CUDA;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (mode == 0) {
+  if (mode >= 2) {
+    const long long ntiles = bytes / 6912;
+    const float2* xt = static_cast<const float2*>(buf);
+    float* sk = static_cast<float*>(sink);
+    if (mode == 2)
+      k_probe_gemv<8, false><<<sms, 256, 0, stream>>>(xt, ntiles, iters, sk);
+    else if (mode == 3)
+      k_probe_gemv<12, true><<<sms, 384, 0, stream>>>(xt, ntiles, iters, sk);
+    else if (mode == 4)
+      k_probe_gemv<16, true><<<sms, 512, 0, stream>>>(xt, ntiles, iters, sk);
+    else if (mode == 5)
+      k_probe_gemv<8, true><<<sms, 256, 0, stream>>>(xt, ntiles, iters, sk);
+    else
+      return EDHMC_ERR_INVALID;
+  } else if (mode == 0) {
     k_probe_ldg<<<sms * 2, 1024, 0, stream>>>(static_cast<const float4*>(buf), bytes / 16, iters, static_cast<float*>(sink));
   } else {
     const int smem = kProbeStages * kProbeChunk;

@@ -1,0 +1,156 @@
+// stream_ldg.cuh — the streaming pass WITHOUT shared-memory staging (ring mode 2), for narrow rows (D <= 64).
+//
+// Ring mode 1 moves every byte of X through shared memory twice (TMA write, then LDS): at cfg 2 that is 14k of the
+// 22k cycles of a pass on the 128 B/clk shared-memory port, and neither more warps nor more lanes per row helped
+// (profiles/README round 2). Here X is re-laid ONCE at bind time (k_relay_tiles) into column-pair-major 32-row tiles,
+//
+//     Xt[tile][pair i < Kact][row r < 32] = float2(X[32*tile + r][2i], X[32*tile + r][2i+1])     (zero padded)
+//     Yt[tile][r]                         = float(y[32*tile + r])
+//
+// so that lane r of a warp reads ITS row with Kact coalesced LDG.64 (256 contiguous bytes per warp instruction) straight
+// into registers: one lane per row as before — the same dot / link / gradient arithmetic as row_group<1, 2, K> — but no
+// TMA, no mbarrier, no ring bookkeeping, and the bytes cross the L1/shared-memory array once. theta is read from shared
+// memory (broadcast LDS.64), which leaves room for 12 warps per SM; the probe kernel of this access pattern
+// (edhmc_probe_read modes 2-5, tools/probe_gemv.py) streams cfg 2 in 8.3 us per pass with 12 warps against 10.2 us with 8.
+//
+// Rows: a CTA owns a contiguous range of tiles, warp w of it the tiles w, w + NW, ...; odd passes walk them backwards
+// (zig-zag, L2 reuse). Padded rows of the last tile are masked (their residual and log-likelihood are zero).
+#pragma once
+#include "stream.cuh"
+
+namespace edhmc {
+
+// Re-lay of X / y into the tile layout above (once per edhmc_bind_data). One thread per (tile, pair, row) element.
+static __global__ void __launch_bounds__(256) k_relay_tiles(const float* __restrict__ X, long long n_rows, long long ldx, int D,
+                                                     const void* __restrict__ y, int y_dtype, int Kact, long long n_tiles,
+                                                     float2* __restrict__ Xt, float* __restrict__ Yt) {
+  const long long total = n_tiles * Kact * 32;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(e & 31);
+    const long long q = e >> 5;
+    const int i = static_cast<int>(q % Kact);
+    const long long t = q / Kact;
+    const long long row = t * 32 + r;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (row < n_rows) {
+      const float* src = X + row * ldx + 2 * i;
+      v.x = src[0];  // 2i < D always (Kact = ceil(D / 2))
+      if (2 * i + 1 < D) v.y = src[1];
+    }
+    Xt[e] = v;
+    if (i == 0) {
+      float yv = 0.0f;
+      if (row < n_rows)
+        yv = y_dtype == 1 ? reinterpret_cast<const float*>(y)[row] : static_cast<float>(reinterpret_cast<const int*>(y)[row]);
+      Yt[row] = yv;
+    }
+  }
+}
+
+// Tiles a warp keeps in flight per round: rows of few columns are batched so that every lane has ~24 LDG.64 outstanding
+// whatever D is (a warp with one 8-column tile in flight has 1 KB outstanding and is bound by the L2 / HBM latency:
+// 16M x 8 ran at 47 % of the HBM peak with J = 1).
+template <int K>
+struct LdgBatch {
+  static constexpr int J = K >= 14 ? 1 : (K >= 10 ? 2 : (K >= 8 ? 3 : (K >= 6 ? 4 : 6)));
+};
+
+template <int K, int NW, int FAM, int LPM>
+__device__ __forceinline__ void stream_pass_ldg_tiles(const float2* __restrict__ Xt, const float* __restrict__ Yt, int Kact,
+                                                      long long t0, long long cnt, bool backward, long long n_rows,
+                                                      const float2* __restrict__ theta2, float bias, float lik_scale,
+                                                      float2* __restrict__ gout, float* gbout, double* lpout) {
+  constexpr int J = LdgBatch<K>::J;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2 g[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) g[i] = make_float2(0.0f, 0.0f);
+  float gb = 0.0f;
+  double lp = 0.0;
+  const long long stride_t = static_cast<long long>(Kact) * 32;
+  for (long long k0 = static_cast<long long>(warp) * J; k0 < cnt; k0 += NW * J) {
+    float2 x[J][K];
+    float yv[J];
+    long long row[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const bool live = J == 1 || k0 + j < cnt;
+      const long long t = backward ? (t0 + cnt - 1 - (k0 + j)) : (t0 + k0 + j);
+      const float2* p = Xt + t * stride_t + lane;
+#pragma unroll
+      for (int i = 0; i < K; ++i) x[j][i] = (live && i < Kact) ? __ldcg(p + i * 32) : make_float2(0.0f, 0.0f);
+      yv[j] = live ? __ldcg(Yt + t * 32 + lane) : 0.0f;
+      row[j] = live ? t * 32 + lane : n_rows;
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const float2 w = theta2[i];  // broadcast LDS.64 (entries >= D are zero)
+        if (i & 1)
+          a1 = fma2(x[j][i], w, a1);
+        else
+          a0 = fma2(x[j][i], w, a0);
+      }
+      const float eta = ((a0.x + a0.y) + (a1.x + a1.y)) + bias;
+      float lpv = 0.0f, rv;
+      if (LPM)
+        row_terms(FAM, eta, yv[j], lik_scale, lpv, rv);
+      else if (FAM == 0)
+        rv = bernoulli_resid_fast(eta, yv[j]);
+      else
+        rv = row_resid(FAM, eta, yv[j], lik_scale);
+      if (row[j] >= n_rows) {  // padded rows of the last tile, absent tiles of the last round
+        lpv = 0.0f;
+        rv = 0.0f;
+      }
+      if (LPM) lp += static_cast<double>(lpv);
+      gb += rv;
+      const float2 r2 = make_float2(rv, rv);
+#pragma unroll
+      for (int i = 0; i < K; ++i) g[i] = fma2(r2, x[j][i], g[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < K; ++i) gout[i] = g[i];
+  *gbout = gb;
+  *lpout = lp;
+}
+
+// One pass of this CTA over its tiles (ring mode 2). Same contract as stream_pass / stream_pass_cta: on return
+// cta_acc[0..P] holds the CTA's float64 sums, reduced in a fixed order; ends with a __syncthreads().
+template <int K, int NW>
+__device__ __forceinline__ void stream_pass_ldg(const KArgs& a, const SmemLayout& sm, float bias, bool want_lp, bool backward) {
+  const long long per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const long long t0 = blockIdx.x * per;
+  long long cnt = a.n_tiles - t0;
+  if (cnt > per) cnt = per;
+  if (cnt < 0) cnt = 0;
+  const float2* theta2 = reinterpret_cast<const float2*>(sm.theta_s);
+  float2 g[K];
+  float gb;
+  double lp;
+  const int fam = a.family;
+  if (want_lp) {
+    if (fam == 0)
+      stream_pass_ldg_tiles<K, NW, 0, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+    else if (fam == 1)
+      stream_pass_ldg_tiles<K, NW, 1, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+    else
+      stream_pass_ldg_tiles<K, NW, 2, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+  } else {
+    if (fam == 0)
+      stream_pass_ldg_tiles<K, NW, 0, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+    else if (fam == 1)
+      stream_pass_ldg_tiles<K, NW, 1, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+    else
+      stream_pass_ldg_tiles<K, NW, 2, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+  }
+  PlanRegs pr_unused = {};
+  int wt_unused = 0, ring_unused = 0;
+  pass_reduce<1, 2, K, NW, true>(a, pr_unused, wt_unused, ring_unused, sm, g, gb, lp, false, false, 0u, 0ull);
+}
+
+}  // namespace edhmc
