@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kMcChainsPerCta, 1) k_mc_pass_simple(const McA
     __syncthreads();
     for (int i = tid; i < 32 * D; i += kMcChainsPerCta) {
       const int m = i / D, d = i - m * D;
-      xs[m][d] = m < nr ? a.X[(base + m) * a.ldx + d] : 0.0f;
+      xs[m][d] = m < nr ? (d < a.Dx ? a.X[(base + m) * a.ldx + d] : 1.0f) : 0.0f;  // d == Dx: the bias latent's column of ones
     }
     if (tid < 32) ys[tid] = tid < nr ? ld_y(a.y, a.y_dtype, base + tid) : 0.0f;
     __syncthreads();
@@ -160,7 +160,7 @@ __global__ void k_mc_pretile(const McArgs a, float* xt, float* yt) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int d = kc * 4 + e;
-      const float v = (row < a.n_rows && d < a.D) ? a.X[row * a.ldx + d] : 0.0f;
+      const float v = (row < a.n_rows && d < a.D) ? (d < a.Dx ? a.X[row * a.ldx + d] : 1.0f) : 0.0f;  // d == Dx: bias column
       split_tf32(v, hp[e], lq[e]);
     }
     float* base = xt + static_cast<size_t>(t) * 2 * plane + static_cast<size_t>(kc) * (kT3Pitch / 4) + m * 4;

@@ -13,7 +13,7 @@ namespace edhmc {
 
 constexpr int kMcChainsPerCta = 128;  // chains per CTA: one TMEM lane / one thread per chain
 constexpr int kMcTileRows = 128;      // rows of X per tensor-core tile
-constexpr int kMcMaxD = 64;           // features supported by the many-chain pass kernels
+constexpr int kMcMaxD = 64;           // latents (features + bias) supported by the many-chain pass kernels
 
 struct McArgs {
   // problem
@@ -21,7 +21,8 @@ struct McArgs {
   const void* y;
   long long n_rows;
   long long ldx;
-  int D;
+  int D;   // latents per chain: the columns of X plus, with a bias latent, one column of ones appended by the pre-tiling
+  int Dx;  // columns physically present in X (D - 1 with a bias latent, else D)
   int Dp;  // D rounded up to a multiple of 8 (MMA K granularity for tf32)
   int family;
   int y_dtype;

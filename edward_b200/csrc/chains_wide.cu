@@ -57,7 +57,7 @@ __global__ void k_mcw_pretile_xk(const McwArgs a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int d = kg * 4 + e;
-      const float v = (row < a.n_rows && d < a.D) ? a.X[row * a.ldx + d] : 0.0f;
+      const float v = (row < a.n_rows && d < a.D) ? (d < a.Dx ? a.X[row * a.ldx + d] : 1.0f) : 0.0f;  // d == Dx: bias column
       split_tf32(v, hp[e], lq[e]);
     }
     float* base = a.xk + static_cast<size_t>(t) * 2 * plane + (static_cast<size_t>(kg) * kMwRowTile + m) * 4;
@@ -86,7 +86,7 @@ __global__ void k_mcw_pretile_xt(const McwArgs a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const long long row = rg * 4 + e;
-      const float v = (row < a.n_rows && d < a.D) ? a.X[row * a.ldx + d] : 0.0f;
+      const float v = (row < a.n_rows && d < a.D) ? (d < a.Dx ? a.X[row * a.ldx + d] : 1.0f) : 0.0f;  // d == Dx: bias column
       split_tf32(v, hp[e], lq[e]);
     }
     float* base = a.xt + static_cast<size_t>(ft) * 2 * plane + (static_cast<size_t>(rg) * a.NB2 + f) * 4;

@@ -25,7 +25,8 @@ struct McwArgs {
   const void* y;
   long long n_rows;
   long long ldx;
-  int D;
+  int D;   // latents per chain (columns of X + the bias latent's column of ones, appended by the pre-tiling)
+  int Dx;  // columns physically present in X
   int family;
   int y_dtype;
   float lik_scale;

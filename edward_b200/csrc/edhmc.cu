@@ -662,7 +662,6 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   if (cfg->n_chains > 1) {
     if (cfg->n_chains % kMcChainsPerCta != 0)
       return fail(EDHMC_ERR_INVALID, "n_chains must be a multiple of %d, got %d", kMcChainsPerCta, cfg->n_chains);
-    if (cfg->has_bias) return fail(EDHMC_ERR_INVALID, "vectorised chains do not support a bias latent yet");
   }
   const int P = cfg->n_features + (cfg->has_bias ? 1 : 0);
   double pc = 0.0;
@@ -761,7 +760,7 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   }
   if (cfg->n_chains > 1) {
     h->C = cfg->n_chains;
-    h->mc_Dp = (cfg->n_features + 7) / 8 * 8;
+    h->mc_Dp = (P + 7) / 8 * 8;  // a bias latent is one more column (of ones) of the pre-tiled operand
     const long long ntiles = (cfg->n_rows + kMcTileRows - 1) / kMcTileRows;
     long long nrg = h->num_sms / (h->C / kMcChainsPerCta);
     if (nrg < 1) nrg = 1;
@@ -769,7 +768,7 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
     h->mc_nrg = static_cast<int>(nrg);
     // pass implementation: 3 = pre-tiled pipelined tcgen05 (default), 0 = CUDA cores (cross-check)
     h->mc_use_tc = 3;
-    h->mc_wide = cfg->n_features > kMcMaxD;
+    h->mc_wide = P > kMcMaxD;
     if (const char* e = getenv("EDHMC_MC_IMPL")) {
       if (strcmp(e, "wide") == 0) h->mc_wide = true;
       if (strcmp(e, "simple") == 0) h->mc_use_tc = 0;
@@ -779,7 +778,8 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
     if (h->mc_wide) {
       McwArgs& w = h->mcw;
       w.n_rows = cfg->n_rows;
-      w.D = cfg->n_features;
+      w.D = P;
+      w.Dx = cfg->n_features;
       w.C = h->C;
       mcw_plan(w, h->num_sms);
       const McwSizes z = mcw_sizes(w);
@@ -804,7 +804,7 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
       ALLOC(h->mc_xt, xtb + 4096);
       ALLOC(h->mc_yt, ytb + 256);
     }
-    const size_t cd = static_cast<size_t>(h->C) * cfg->n_features * sizeof(float);
+    const size_t cd = static_cast<size_t>(h->C) * P * sizeof(float);
     ALLOC(h->mc_z, cd);
     ALLOC(h->mc_r, cd);
     ALLOC(h->mc_g, cd);
@@ -1551,7 +1551,8 @@ static void fill_mc_args(edhmc_handle* h, McArgs& a) {
   a.y = h->y;
   a.n_rows = c.n_rows;
   a.ldx = c.ldx;
-  a.D = c.n_features;
+  a.D = h->P;
+  a.Dx = c.n_features;
   a.Dp = h->mc_Dp;
   a.family = c.family;
   a.y_dtype = h->y_dtype;
@@ -1773,6 +1774,7 @@ int edhmc_chains_plan_probe(int64_t n_rows, int32_t n_features, int32_t n_chains
   memset(&w, 0, sizeof(w));
   w.n_rows = n_rows;
   w.D = n_features;
+  w.Dx = n_features;
   w.C = n_chains;
   mcw_plan(w, num_sms);
   const int64_t v[8] = {w.nct, w.Kp1, w.nrt, w.nft, w.NB2, w.g1, w.splits, w.Dp2};

@@ -115,8 +115,6 @@ def test_chain_argument_checks():
   X, y = _data(100, 8, 0)
   with pytest.raises(_C.EdhmcError):
     engine.GLMSampler(engine.GLMSpec(8), X, y, n_chains=100)   # not a multiple of 128
-  with pytest.raises(_C.EdhmcError):
-    engine.GLMSampler(engine.GLMSpec(8, has_bias=True), X, y, n_chains=128)  # no bias latent with vectorised chains
 
 
 # ---- wide models / the two-GEMM path (chains_wide.cu): n_features > 64, or forced with EDHMC_MC_IMPL=wide ----
@@ -162,6 +160,67 @@ def test_wide_chain_run_matches_independent_oracle_runs(D, impl, monkeypatch):
   for c in [0, 1, 64, 127]:
     p64 = np.zeros((T, D))
     p64[0] = z0[c]
+    infos, nacc = o.run(X, y, p64, r0[:, c], u[:, c], eps, L, spec)
+    forked = False
+    for i, info in enumerate(infos):
+      assert abs(tr[i, c, 1] - info.logp_new) <= REL_LOGP * abs(info.logp_new) + 1e-6, (c, i)
+      if bool(tr[i, c, 6] > 0.5) != info.accept:
+        assert info.margin < TIE_EPS, (c, i, info)
+        ties += 1
+        forked = True
+        break
+      assert np.max(np.abs(got[i, c] - p64[i])) <= REL_POS * max(np.max(np.abs(p64[i])), 1e-3), (c, i)
+    if not forked:
+      assert n_acc[c] == nacc
+  assert ties <= 1
+  s.close()
+
+
+# ---- bias latent: one more column (of ones) of the pre-tiled operands, so both tensor-core paths and the CUDA-core twin
+#      take models with an intercept (cfg 1's shape: Bernoulli(logits=ed.dot(X, w) + b), examples/...:60-62) ----
+@pytest.mark.parametrize("N,D,C,impl", [(1000, 7, 128, "simple"), (1000, 7, 128, "tc"), (4133, 53, 256, "tc"), (3000, 63, 128, "tc"),
+                                        (900, 64, 128, "tc"), (2111, 200, 128, "tc")])
+def test_chain_logp_grad_with_bias_latent(N, D, C, impl, monkeypatch):
+  from edward_b200 import engine
+  X, y = _data(N, D, N + D)
+  monkeypatch.setenv("EDHMC_MC_IMPL", impl)
+  P = D + 1
+  ps = np.full(P, 1.5, np.float32)
+  s = engine.GLMSampler(engine.GLMSpec(D, True, prior_scale=ps), X, y, n_chains=C)
+  rng = np.random.default_rng(5)
+  theta = (0.3 * rng.standard_normal((C, P)) / np.sqrt(D)).astype(np.float32)
+  lp, g = s.logp_grad_chains(theta)
+  lp, g = lp.cpu().numpy(), g.cpu().numpy()
+  spec = o.GLMSpec(D, True, prior_scale=ps)
+  for c in list(range(0, C, 41)) + [C - 1]:
+    lp64 = float(o.log_joint(X, y, theta[c], spec))
+    g64 = o.grad_log_joint(X, y, theta[c], spec)
+    assert abs(lp[c] - lp64) <= REL_LOGP * abs(lp64), (impl, c, lp[c], lp64)
+    assert np.max(np.abs(g[c] - g64)) / np.max(np.abs(g64)) <= REL_GRAD, (impl, c)
+  s.close()
+
+
+@pytest.mark.parametrize("D,impl", [(20, "tc"), (100, "tc")])
+def test_chain_run_with_bias_latent_matches_independent_oracle_runs(D, impl, monkeypatch):
+  import torch
+  from edward_b200 import engine
+  N, C, T, L, eps = 2000, 128, 5, 4, 0.02
+  P = D + 1
+  X, y = _data(N, D, 13)
+  monkeypatch.setenv("EDHMC_MC_IMPL", impl)
+  s = engine.GLMSampler(engine.GLMSpec(D, True), X, y, n_chains=C)
+  rng = np.random.Generator(np.random.Philox(key=7))
+  r0 = rng.standard_normal((T, C, P), dtype=np.float32)
+  u = np.clip(rng.random((T, C), dtype=np.float32), 1e-7, 1 - 1e-7).astype(np.float32)
+  params = torch.zeros(T, C, P, device="cuda")
+  tr = s.set_chain_trace(T)
+  s.run_chains(params, 0, T, eps, L, r0=torch.tensor(r0), u=torch.tensor(u))
+  n_acc, _ = s.read_chain_state()
+  got, tr = params.cpu().numpy(), tr.cpu().numpy()
+  spec = o.GLMSpec(D, True)
+  ties = 0
+  for c in [0, 5, 64, 127]:
+    p64 = np.zeros((T, P))
     infos, nacc = o.run(X, y, p64, r0[:, c], u[:, c], eps, L, spec)
     forked = False
     for i, info in enumerate(infos):
