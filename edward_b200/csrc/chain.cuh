@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   {
     const int par0 = single ? (a.par0 & 1) : static_cast<int>((a.t0 * a.L - (in_init ? 1 : 0)) & 1);
     ring.cpass = par0;
+    if constexpr (RM == 2) ldg_load_resident<NW>(a, sm);
     if constexpr (RM == 1)
       ring.par0 = par0;
     else if constexpr (RM == 0)

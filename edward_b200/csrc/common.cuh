@@ -83,6 +83,7 @@ struct KArgs {
   const float2* Xt;  // [n_tiles][Kact][32] float2
   const float* Yt;   // [n_tiles][32]
   long long n_tiles;
+  int n_res;          // tiles per CTA kept resident in shared memory for the whole launch (persistent plan only)
   // ---- launch mode ----
   int mode;               // 0: run n_iter transitions (cooperative launch); 1: one data pass at theta_in
   int gate;               // mode 1: return immediately unless sc->need_init

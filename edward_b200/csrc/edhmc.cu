@@ -132,6 +132,7 @@ struct Plan {
   int grid = 0;
   int WPG = 0;  // ring mode 1: warps per group
   int RM = 0;  // ring mode: 0 = one ring per warp (stream.cuh), 1 = one ring per CTA (stream_cta.cuh, narrow rows)
+  int n_res = 0;  // ring mode 2: 32-row tiles per CTA kept resident in shared memory during a persistent launch
   size_t smem = 0;
   const void* fn = nullptr;
 };
@@ -532,8 +533,34 @@ static bool make_plan_ldg(edhmc_handle* h, Plan& out) {
   p.wpad = 2 * K;
   p.fn = lookup_kernel(1, 2, K, p.NW, 2);
   if (!p.fn) return false;
+  const long long n_tiles = (c.n_rows + 31) / 32;
+  long long want = (n_tiles + 2ll * p.NW - 1) / (2ll * p.NW);  // >= two tiles per warp before another SM is used
+  if (want < 1) want = 1;
+  p.grid = static_cast<int>(want < h->num_sms ? want : h->num_sms);
   size_t offs[8];
-  p.smem = smem_layout_bytes(1, 0, 0, h->P, p.wpad, offs);
+  // Shared memory that is not needed for staging keeps the first tiles of the CTA's range resident for the whole
+  // persistent launch (stream_ldg.cuh, ldg_load_resident): EDHMC_RESIDENT=0 switches it off (A/B runs).
+  {
+    const size_t fixed = smem_layout_bytes(1, 0, 0, h->P, p.wpad, offs);
+    const size_t tile_bytes = static_cast<size_t>(chunks) * 256 + 128;
+    const size_t budget = static_cast<size_t>(h->smem_optin) > fixed + 2048 ? static_cast<size_t>(h->smem_optin) - fixed - 2048 : 0;
+    long long r = static_cast<long long>(budget / tile_bytes);
+    const long long per = (n_tiles + p.grid - 1) / p.grid;
+    if (r > per) r = per;
+    // worth it only when a sizeable part of X stays on chip (same-box A/B, profiles/README round 2: L2-resident shapes gain
+    // 5-13 %, HBM-bound ones with < 7 % of their tiles resident lose 0-13 % to the per-tile branch)
+    if (r * 10 < per) r = 0;
+    if (const char* e = getenv("EDHMC_RESIDENT")) {
+      const long long lim = atoll(e);
+      if (lim >= 0 && r > lim) r = lim;
+    }
+    p.n_res = static_cast<int>(r);
+    if (p.n_res > 0) {
+      p.S = 1;
+      p.stage_floats = static_cast<int>(r * (tile_bytes / 4));
+    }
+  }
+  p.smem = smem_layout_bytes(1, p.S, p.stage_floats, h->P, p.wpad, offs);
   if (cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)) != cudaSuccess) {
     cudaGetLastError();
     return false;
@@ -543,10 +570,6 @@ static bool make_plan_ldg(edhmc_handle* h, Plan& out) {
     cudaGetLastError();
     return false;
   }
-  const long long n_tiles = (c.n_rows + 31) / 32;
-  long long want = (n_tiles + 2ll * p.NW - 1) / (2ll * p.NW);  // >= two tiles per warp before another SM is used
-  if (want < 1) want = 1;
-  p.grid = static_cast<int>(want < h->num_sms ? want : h->num_sms);
   out = p;
   return true;
 }
@@ -589,6 +612,7 @@ static void fill_args(edhmc_handle* h, KArgs& a, const Plan* pp = nullptr) {
   a.Xt = h->d_xt;
   a.Yt = h->d_yt;
   a.n_tiles = h->n_tiles;
+  a.n_res = p.RM == 2 ? p.n_res : 0;
   a.Kact = p.Kact;
   a.J = p.J;
   a.RT = p.RT;
@@ -1011,6 +1035,7 @@ static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int 
   const Plan& pl = pp ? *pp : h->plan;
   KArgs aa = a;
   aa.mode = 1;
+  aa.n_res = 0;  // one pass per launch: nothing to keep resident
   aa.gate = gate;
   aa.single_lp = want_lp;
   aa.par0 = static_cast<int>(gsi & 1);

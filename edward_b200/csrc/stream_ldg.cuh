@@ -56,10 +56,21 @@ struct LdgBatch {
   static constexpr int J = K >= 14 ? 1 : (K >= 10 ? 2 : (K >= 8 ? 3 : (K >= 6 ? 4 : 6)));
 };
 
+// J == 1 (K >= 14 pairs per row): two tiles per warp, double-buffered IN REGISTERS — the loads of the warp's next tile are
+// issued before the current one is consumed. With a single buffer all warps of a CTA fall into lock-step (every pass
+// starts them together): they request 83 KB at once, wait ~2,000 cycles for the SM's 64 B/clk L2 port to deliver it, then
+// compute together while the port idles (measured: 2.0k cycles per round in the sampler against 1.57k in the free-running
+// probe). Same tile order per warp as the single-buffered loop would have (k = warp, warp + NW, ...).
+// Measured and rejected (profiles/README round 2): two tiles per warp double-buffered in registers (8 warps for K >= 24, 12
+// below) — slower on every shape (4M x 32: 100.5 -> 86.7 % of the HBM copy peak, 3M x 64: 103 -> 57 %, cfg 2 18.6 us per step
+// against 17.6 for the loop below with resident tiles). A conditionally loaded register array ends up in local memory; with
+// unconditional (clamped) loads the arrays stay in registers but the 255-register variants lose more to spilled chain state
+// and 8 warps than the second buffer gains.
 template <int K, int NW, int FAM, int LPM>
 __device__ __forceinline__ void stream_pass_ldg_tiles(const float2* __restrict__ Xt, const float* __restrict__ Yt, int Kact,
                                                       long long t0, long long cnt, bool backward, long long n_rows,
                                                       const float2* __restrict__ theta2, float bias, float lik_scale,
+                                                      const float* __restrict__ res, int n_res,
                                                       float2* __restrict__ gout, float* gbout, double* lpout) {
   constexpr int J = LdgBatch<K>::J;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -77,10 +88,18 @@ __device__ __forceinline__ void stream_pass_ldg_tiles(const float2* __restrict__
     for (int j = 0; j < J; ++j) {
       const bool live = J == 1 || k0 + j < cnt;
       const long long t = backward ? (t0 + cnt - 1 - (k0 + j)) : (t0 + k0 + j);
-      const float2* p = Xt + t * stride_t + lane;
+      const long long rel = t - t0;
+      if (live && rel < n_res) {  // resident tile (warp-uniform): shared memory, conflict-free LDS.64
+        const float2* p = reinterpret_cast<const float2*>(res) + rel * stride_t + lane;
 #pragma unroll
-      for (int i = 0; i < K; ++i) x[j][i] = (live && i < Kact) ? __ldcg(p + i * 32) : make_float2(0.0f, 0.0f);
-      yv[j] = live ? __ldcg(Yt + t * 32 + lane) : 0.0f;
+        for (int i = 0; i < K; ++i) x[j][i] = (i < Kact) ? p[i * 32] : make_float2(0.0f, 0.0f);
+        yv[j] = res[static_cast<long long>(n_res) * stride_t * 2 + rel * 32 + lane];
+      } else {
+        const float2* p = Xt + t * stride_t + lane;
+#pragma unroll
+        for (int i = 0; i < K; ++i) x[j][i] = (live && i < Kact) ? __ldcg(p + i * 32) : make_float2(0.0f, 0.0f);
+        yv[j] = live ? __ldcg(Yt + t * 32 + lane) : 0.0f;
+      }
       row[j] = live ? t * 32 + lane : n_rows;
     }
 #pragma unroll
@@ -119,6 +138,31 @@ __device__ __forceinline__ void stream_pass_ldg_tiles(const float2* __restrict__
   *lpout = lp;
 }
 
+// Resident tiles: X does not change during a persistent launch, so the first a.n_res tiles of the CTA's range are copied
+// ONCE per launch into the shared memory that ring mode 2 does not need for staging (~210 KB per SM: 30 of cfg 2's 123
+// tiles per SM, 31 MB of X over the GPU) and are read from there in every pass — they never cross the SM's L2 port again,
+// and an L2-sized X (cfg 2: 127.8 MB against 126 MB of L2) shrinks to a working set that fits the L2 with room to spare.
+// Layout: [n_res][Kact][32] float2, then [n_res][32] float (y). The order in which a warp visits its tiles does not
+// depend on where a tile lives, so the sums are bit-identical to a launch without resident tiles (stepwise plan).
+template <int NW>
+__device__ __forceinline__ void ldg_load_resident(const KArgs& a, const SmemLayout& sm) {
+  if (a.n_res <= 0) return;
+  const long long per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const long long t0 = blockIdx.x * per;
+  long long cnt = a.n_tiles - t0;
+  if (cnt > per) cnt = per;
+  if (cnt < 0) cnt = 0;
+  const int n_res = static_cast<int>(cnt < a.n_res ? cnt : a.n_res);
+  const long long stride_t = static_cast<long long>(a.Kact) * 32;  // float2 per tile
+  const float4* src = reinterpret_cast<const float4*>(a.Xt + t0 * stride_t);  // tiles start 256-byte aligned
+  float4* dst = reinterpret_cast<float4*>(sm.ring);
+  const long long n4 = static_cast<long long>(n_res) * stride_t / 2;
+  for (long long i = threadIdx.x; i < n4; i += NW * 32) dst[i] = __ldcg(src + i);
+  float* dy = sm.ring + static_cast<long long>(n_res) * stride_t * 2;
+  for (int i = threadIdx.x; i < n_res * 32; i += NW * 32) dy[i] = __ldcg(a.Yt + t0 * 32 + i);
+  __syncthreads();
+}
+
 // One pass of this CTA over its tiles (ring mode 2). Same contract as stream_pass / stream_pass_cta: on return
 // cta_acc[0..P] holds the CTA's float64 sums, reduced in a fixed order; ends with a __syncthreads().
 template <int K, int NW>
@@ -129,24 +173,26 @@ __device__ __forceinline__ void stream_pass_ldg(const KArgs& a, const SmemLayout
   if (cnt > per) cnt = per;
   if (cnt < 0) cnt = 0;
   const float2* theta2 = reinterpret_cast<const float2*>(sm.theta_s);
+  const float* res = sm.ring;
+  const int n_res = static_cast<int>(cnt < a.n_res ? cnt : a.n_res);
   float2 g[K];
   float gb;
   double lp;
   const int fam = a.family;
   if (want_lp) {
     if (fam == 0)
-      stream_pass_ldg_tiles<K, NW, 0, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 0, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
     else if (fam == 1)
-      stream_pass_ldg_tiles<K, NW, 1, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 1, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
     else
-      stream_pass_ldg_tiles<K, NW, 2, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 2, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
   } else {
     if (fam == 0)
-      stream_pass_ldg_tiles<K, NW, 0, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 0, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
     else if (fam == 1)
-      stream_pass_ldg_tiles<K, NW, 1, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 1, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
     else
-      stream_pass_ldg_tiles<K, NW, 2, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 2, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
   }
   PlanRegs pr_unused = {};
   int wt_unused = 0, ring_unused = 0;
