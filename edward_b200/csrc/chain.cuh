@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   if (single && a.gate && !a.sc->need_init) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_last;
+  __shared__ uint32_t s_tmem;  // ring mode 2: base address of the tensor memory allocation
   __shared__ int s_init0;  // leader protocol: 1 if this launch starts with the initial evaluation pass
   // The chain scalars live in shared memory BETWEEN the serial sections: every thread reloads them after a data pass
   // and thread 0 stores them back before the next one, so none of them occupies a register across the tile loop (with
@@ -331,9 +332,19 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   float* zc = g + ppad;
   float* gc = zc + ppad;
 
+  uint32_t tm_base = kNoTmem;
   if constexpr (RM == 2) {
     for (int i = tid; i < a.wpad; i += kThreads) sm.theta_s[i] = 0.0f;  // no ring, no barriers: theta only
+    const bool tm_use = a.tm_on != 0 && a.mode == 0;
+    if (tm_use) {  // tensor memory for resident tiles (stream_ldg.cuh); released after the pass loop on every exit path
+      if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+      tc_fence_before();
+    }
     __syncthreads();
+    if (tm_use) {
+      tc_fence_after();
+      tm_base = s_tmem;
+    }
   } else if constexpr (RM == 1) {
     smem_setup_cta(sm, a, ngroups);
   } else {
@@ -453,7 +464,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   {
     const int par0 = single ? (a.par0 & 1) : static_cast<int>((a.t0 * a.L - (in_init ? 1 : 0)) & 1);
     ring.cpass = par0;
-    if constexpr (RM == 2) ldg_load_resident<NW>(a, sm);
+    if constexpr (RM == 2) ldg_load_resident<K, NW>(a, sm, tm_base);
     if constexpr (RM == 1)
       ring.par0 = par0;
     else if constexpr (RM == 0)
@@ -541,7 +552,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
     EDHMC_TL(0, clock64());
     EDHMC_TL(6, global_timer_ns());
     if constexpr (RM == 2) {
-      stream_pass_ldg<K, NW>(a, sm, bias, want_lp, a.zigzag && (ring.cpass & 1));
+      stream_pass_ldg<K, NW>(a, sm, bias, want_lp, a.zigzag && (ring.cpass & 1), tm_base);
       ++ring.cpass;
     } else if constexpr (RM == 1) {
       stream_pass_cta<G, V, K, NW>(a, pr, wt, ring, sm, bias, policy, want_lp);
@@ -719,6 +730,16 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
     EDHMC_TL(5, clock64());
   }
 
+  if constexpr (RM == 2) {
+    if (tm_base != kNoTmem) {  // uniform over the CTA; also reached when a peer wait timed out
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tm_base, 512);
+      }
+    }
+  }
   if (aborted) return;
   load_chain(n_passes);
   if (!single && blockIdx.x == 0) {

@@ -84,6 +84,9 @@ struct KArgs {
   const float* Yt;   // [n_tiles][32]
   long long n_tiles;
   int n_res;          // tiles per CTA kept resident in shared memory for the whole launch (persistent plan only)
+  int n_tm;           // tiles per CTA that a persistent launch parks in tensor memory (they are the last of the CTA's range
+                      // in either plan: the tile order must not depend on the plan)
+  int tm_on;          // 1: this launch allocates tensor memory and reads those tiles from there
   // ---- launch mode ----
   int mode;               // 0: run n_iter transitions (cooperative launch); 1: one data pass at theta_in
   int gate;               // mode 1: return immediately unless sc->need_init

@@ -133,6 +133,7 @@ struct Plan {
   int WPG = 0;  // ring mode 1: warps per group
   int RM = 0;  // ring mode: 0 = one ring per warp (stream.cuh), 1 = one ring per CTA (stream_cta.cuh, narrow rows)
   int n_res = 0;  // ring mode 2: 32-row tiles per CTA kept resident in shared memory during a persistent launch
+  int n_tm = 0;   // ring mode 2: 32-row tiles per CTA parked in tensor memory during a persistent launch
   size_t smem = 0;
   const void* fn = nullptr;
 };
@@ -543,21 +544,30 @@ static bool make_plan_ldg(edhmc_handle* h, Plan& out) {
   {
     const size_t fixed = smem_layout_bytes(1, 0, 0, h->P, p.wpad, offs);
     const size_t tile_bytes = static_cast<size_t>(chunks) * 256 + 128;
-    const size_t budget = static_cast<size_t>(h->smem_optin) > fixed + 2048 ? static_cast<size_t>(h->smem_optin) - fixed - 2048 : 0;
-    long long r = static_cast<long long>(budget / tile_bytes);
     const long long per = (n_tiles + p.grid - 1) / p.grid;
-    if (r > per) r = per;
+    // tensor memory (one tile per warp and round only: K >= 14): 4 lane quarters x (512 / columns per row) slots
+    long long tm = K >= 14 ? 4ll * (512 / ((2 * K + 7) / 8 * 8)) : 0;
+    if (tm > per) tm = per;
+    size_t budget = static_cast<size_t>(h->smem_optin) > fixed + 2048 ? static_cast<size_t>(h->smem_optin) - fixed - 2048 : 0;
+    budget = budget > static_cast<size_t>(tm) * 128 ? budget - static_cast<size_t>(tm) * 128 : 0;  // y of the TMEM tiles
+    long long r = static_cast<long long>(budget / tile_bytes);
+    if (r > per - tm) r = per - tm;
     // worth it only when a sizeable part of X stays on chip (same-box A/B, profiles/README round 2: L2-resident shapes gain
     // 5-13 %, HBM-bound ones with < 7 % of their tiles resident lose 0-13 % to the per-tile branch)
-    if (r * 10 < per) r = 0;
+    if ((r + tm) * 10 < per) r = tm = 0;
     if (const char* e = getenv("EDHMC_RESIDENT")) {
       const long long lim = atoll(e);
       if (lim >= 0 && r > lim) r = lim;
     }
+    if (const char* e = getenv("EDHMC_TMEM")) {
+      const long long lim = atoll(e);
+      if (lim >= 0 && tm > lim) tm = lim;
+    }
     p.n_res = static_cast<int>(r);
-    if (p.n_res > 0) {
+    p.n_tm = static_cast<int>(tm);
+    if (p.n_res > 0 || p.n_tm > 0) {
       p.S = 1;
-      p.stage_floats = static_cast<int>(r * (tile_bytes / 4));
+      p.stage_floats = static_cast<int>(r * (tile_bytes / 4) + tm * 32);
     }
   }
   p.smem = smem_layout_bytes(1, p.S, p.stage_floats, h->P, p.wpad, offs);
@@ -577,7 +587,8 @@ static bool make_plan_ldg(edhmc_handle* h, Plan& out) {
 // Which narrow shapes take ring mode 2 (tools/shape_sweep_ldg.sh, same-box A/B, profiles/README round 2): every D <= 48 and
 // D = 63, 64 — there it runs at 98-109 % of the HBM copy peak against 58-94 % for the shared-memory rings (power-of-two
 // strides conflict in shared memory, rows of few columns leave the rings latency-bound), and L2-resident sizes gain
-// 1.3-1.9x. For 49 <= D <= 62 the CTA-wide ring is as fast or faster (cfg 2, D = 54: 16.1 us per step against 19.0).
+// 1.3-1.9x. For 49 <= D <= 62 the CTA-wide ring is as fast or faster when X streams from HBM; ring mode 2 is taken there
+// when at least 30 % of the CTA's tiles stay resident in shared / tensor memory (see below).
 // EDHMC_RING: unset = that rule; 2 = ring mode 2 wherever eligible; 1 / 0 = row-major plans only (A/B runs).
 static int make_plan(edhmc_handle* h) {
   if (int rc = make_plan_rows(h)) return rc;
@@ -585,9 +596,18 @@ static int make_plan(edhmc_handle* h) {
   int ring = -1;
   if (const char* e = getenv("EDHMC_RING")) ring = atoi(e);
   const int D = h->cfg.n_features;
-  const bool want = ring == 2 || (ring < 0 && (D <= 48 || D >= 63));
   Plan pl;
-  if (want && !h->interleave && make_plan_ldg(h, pl)) h->plan = pl;
+  if (ring != 2 && ring >= 0) return 0;
+  if (h->interleave || !make_plan_ldg(h, pl)) return 0;
+  bool want = ring == 2 || D <= 48 || D >= 63;
+  if (!want) {
+    // 49 <= D <= 62: the CTA-wide ring streams faster from the L2 / HBM, ring mode 2 wins once a good part of X stays in
+    // shared and tensor memory for the whole launch (cfg 2: 65 of 123 tiles per SM, 14.6 against 16.1 us per step)
+    const long long n_tiles = (h->cfg.n_rows + 31) / 32;
+    const long long per = (n_tiles + pl.grid - 1) / pl.grid;
+    want = 10ll * (pl.n_res + pl.n_tm) >= 3 * per;  // 1M x 54 (31 % resident): 108 vs 104 % of the HBM copy peak; 1M x 60 (27 %): 95 vs 102 %
+  }
+  if (want) h->plan = pl;
   return 0;
 }
 
@@ -613,6 +633,8 @@ static void fill_args(edhmc_handle* h, KArgs& a, const Plan* pp = nullptr) {
   a.Yt = h->d_yt;
   a.n_tiles = h->n_tiles;
   a.n_res = p.RM == 2 ? p.n_res : 0;
+  a.n_tm = p.RM == 2 ? p.n_tm : 0;
+  a.tm_on = a.n_tm > 0 ? 1 : 0;
   a.Kact = p.Kact;
   a.J = p.J;
   a.RT = p.RT;
@@ -1036,6 +1058,7 @@ static int launch_pass(edhmc_handle* h, const KArgs& a, const float* theta, int 
   KArgs aa = a;
   aa.mode = 1;
   aa.n_res = 0;  // one pass per launch: nothing to keep resident
+  aa.tm_on = 0;  // (n_tm stays: the tile order is the same in both plans)
   aa.gate = gate;
   aa.single_lp = want_lp;
   aa.par0 = static_cast<int>(gsi & 1);

@@ -17,6 +17,7 @@
 // (zig-zag, L2 reuse). Padded rows of the last tile are masked (their residual and log-likelihood are zero).
 #pragma once
 #include "stream.cuh"
+#include "tc.cuh"
 
 namespace edhmc {
 
@@ -56,21 +57,97 @@ struct LdgBatch {
   static constexpr int J = K >= 14 ? 1 : (K >= 10 ? 2 : (K >= 8 ? 3 : (K >= 6 ? 4 : 6)));
 };
 
-// J == 1 (K >= 14 pairs per row): two tiles per warp, double-buffered IN REGISTERS — the loads of the warp's next tile are
-// issued before the current one is consumed. With a single buffer all warps of a CTA fall into lock-step (every pass
-// starts them together): they request 83 KB at once, wait ~2,000 cycles for the SM's 64 B/clk L2 port to deliver it, then
-// compute together while the port idles (measured: 2.0k cycles per round in the sampler against 1.57k in the free-running
-// probe). Same tile order per warp as the single-buffered loop would have (k = warp, warp + NW, ...).
 // Measured and rejected (profiles/README round 2): two tiles per warp double-buffered in registers (8 warps for K >= 24, 12
 // below) — slower on every shape (4M x 32: 100.5 -> 86.7 % of the HBM copy peak, 3M x 64: 103 -> 57 %, cfg 2 18.6 us per step
 // against 17.6 for the loop below with resident tiles). A conditionally loaded register array ends up in local memory; with
 // unconditional (clamped) loads the arrays stay in registers but the 255-register variants lose more to spilled chain state
 // and 8 warps than the second buffer gains.
+// Tensor-memory tiles. The sampler issues no tcgen05.mma, so the SM's 256 KB of tensor memory (128 lanes x 512 columns of
+// 32 bits) is free: a persistent launch parks further 32-row tiles there — TMEM lane = row of the tile, 2K consecutive
+// columns = the row — and reads a row back with tcgen05.ld.32x32b straight into the registers the arithmetic uses. A warp
+// can only reach the 32 lanes of its quarter (warp % 4), so TMEM tile tt lives in quarter tt % 4, slot tt / 4, and is
+// handled, in every pass and in both directions, by the warps of that quarter (slot % (NW / 4) == warp / 4); y of those
+// tiles sits in shared memory behind the resident tiles. cfg 2: 36 tiles (1,152 rows, 249 KB) per SM next to the 29 in
+// shared memory — 53 % of X never leaves the SM. Only for K >= 14 (one tile per warp and round).
+template <int K>
+struct TmemTiles {
+  static constexpr int kCols = (2 * K + 7) / 8 * 8;  // column stride of a slot
+  static constexpr int kSlots = 512 / kCols;         // slots per lane quarter
+  static constexpr int kMax = LdgBatch<K>::J == 1 ? 4 * kSlots : 0;
+};
+
+template <int K, int FAM, int LPM>
+__device__ __forceinline__ void ldg_row_math(const float2 (&x)[K], float yv, bool valid_row, const float2* __restrict__ theta2,
+                                             float bias, float lik_scale, float2 (&g)[K], float& gb, double& lp) {
+  float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const float2 w = theta2[i];  // broadcast LDS.64 (entries >= D are zero)
+    if (i & 1)
+      a1 = fma2(x[i], w, a1);
+    else
+      a0 = fma2(x[i], w, a0);
+  }
+  const float eta = ((a0.x + a0.y) + (a1.x + a1.y)) + bias;
+  float lpv = 0.0f, rv;
+  if (LPM)
+    row_terms(FAM, eta, yv, lik_scale, lpv, rv);
+  else if (FAM == 0)
+    rv = bernoulli_resid_fast(eta, yv);
+  else
+    rv = row_resid(FAM, eta, yv, lik_scale);
+  if (!valid_row) {  // padded rows of the last tile
+    lpv = 0.0f;
+    rv = 0.0f;
+  }
+  if (LPM) lp += static_cast<double>(lpv);
+  gb += rv;
+  const float2 r2 = make_float2(rv, rv);
+#pragma unroll
+  for (int i = 0; i < K; ++i) g[i] = fma2(r2, x[i], g[i]);
+}
+
+// The tiles of the CTA's range that a launch with tensor-memory tiles keeps there: the LAST n_tm of its cnt tiles. The
+// same tiles are visited by the same warps in the same order when they are read from global memory instead (tm_base ==
+// kNoTmem: stepwise plan, one pass per launch), so both plans add the same numbers in the same order.
+constexpr uint32_t kNoTmem = 0xFFFFFFFFu;
+template <int K, int NW, int FAM, int LPM>
+__device__ __forceinline__ void ldg_tmem_tiles(const float2* __restrict__ Xt, const float* __restrict__ Yt, int Kact, long long tile0,
+                                               int n_tm, uint32_t tm_base, const float* __restrict__ tm_y, long long n_rows,
+                                               const float2* __restrict__ theta2, float bias, float lik_scale, float2 (&g)[K],
+                                               float& gb, double& lp) {
+  if constexpr (TmemTiles<K>::kMax > 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = warp & 3;
+    const long long stride_t = static_cast<long long>(Kact) * 32;
+    for (int slot = warp >> 2; 4 * slot + q < n_tm; slot += NW / 4) {
+      const int tt = 4 * slot + q;
+      float2 x[K];
+      float yv;
+      if (tm_base != kNoTmem) {
+        uint32_t v[2 * K];
+        tmem_ld_cols<2 * K>(tm_base + (static_cast<uint32_t>(q * 32) << 16) + slot * TmemTiles<K>::kCols, v);
+        yv = tm_y[tt * 32 + lane];
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < K; ++i) x[i] = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      } else {
+        const float2* p = Xt + (tile0 + tt) * stride_t + lane;
+#pragma unroll
+        for (int i = 0; i < K; ++i) x[i] = (i < Kact) ? __ldcg(p + i * 32) : make_float2(0.0f, 0.0f);
+        yv = __ldcg(Yt + (tile0 + tt) * 32 + lane);
+      }
+      ldg_row_math<K, FAM, LPM>(x, yv, (tile0 + tt) * 32 + lane < n_rows, theta2, bias, lik_scale, g, gb, lp);
+    }
+  }
+}
+
 template <int K, int NW, int FAM, int LPM>
 __device__ __forceinline__ void stream_pass_ldg_tiles(const float2* __restrict__ Xt, const float* __restrict__ Yt, int Kact,
                                                       long long t0, long long cnt, bool backward, long long n_rows,
                                                       const float2* __restrict__ theta2, float bias, float lik_scale,
-                                                      const float* __restrict__ res, int n_res,
+                                                      const float* __restrict__ res, int n_res, int n_tm, uint32_t tm_base,
+                                                      const float* __restrict__ tm_y,
                                                       float2* __restrict__ gout, float* gbout, double* lpout) {
   constexpr int J = LdgBatch<K>::J;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -132,68 +209,109 @@ __device__ __forceinline__ void stream_pass_ldg_tiles(const float2* __restrict__
       for (int i = 0; i < K; ++i) g[i] = fma2(r2, x[j][i], g[i]);
     }
   }
+  // `cnt` above excludes the tensor-memory tiles, which follow it in the CTA's range
+  ldg_tmem_tiles<K, NW, FAM, LPM>(Xt, Yt, Kact, t0 + cnt, n_tm, tm_base, tm_y, n_rows, theta2, bias, lik_scale, g, gb, lp);
 #pragma unroll
   for (int i = 0; i < K; ++i) gout[i] = g[i];
   *gbout = gb;
   *lpout = lp;
 }
 
-// Resident tiles: X does not change during a persistent launch, so the first a.n_res tiles of the CTA's range are copied
-// ONCE per launch into the shared memory that ring mode 2 does not need for staging (~210 KB per SM: 30 of cfg 2's 123
-// tiles per SM, 31 MB of X over the GPU) and are read from there in every pass — they never cross the SM's L2 port again,
-// and an L2-sized X (cfg 2: 127.8 MB against 126 MB of L2) shrinks to a working set that fits the L2 with room to spare.
-// Layout: [n_res][Kact][32] float2, then [n_res][32] float (y). The order in which a warp visits its tiles does not
-// depend on where a tile lives, so the sums are bit-identical to a launch without resident tiles (stepwise plan).
-template <int NW>
-__device__ __forceinline__ void ldg_load_resident(const KArgs& a, const SmemLayout& sm) {
-  if (a.n_res <= 0) return;
+// Resident tiles: X does not change during a persistent launch, so part of the CTA's range is copied ONCE per launch into
+// on-chip memory that ring mode 2 does not otherwise need and is read from there in every pass: the first n_res tiles into
+// shared memory (~210 KB per SM), the last n_tm tiles into tensor memory (256 KB per SM, see TmemTiles). Those rows never
+// cross the SM's L2 port again, and an L2-sized X (cfg 2: 127.8 MB against 126 MB of L2) shrinks to a working set that
+// fits the L2 with room to spare. Shared-memory layout: [n_res][Kact][32] float2, [n_res][32] float (y), [n_tm][32] float
+// (y of the tensor-memory tiles). The order in which a warp visits its tiles does not depend on where a tile lives, so
+// the sums are bit-identical to a launch that reads everything from global memory (stepwise plan).
+struct LdgRange {
+  long long t0;    // first tile of the CTA
+  long long cnt;   // tiles visited by the main loop (shared-memory-resident ones first)
+  int n_res, n_tm;
+};
+template <int K>
+__device__ __forceinline__ LdgRange ldg_range(const KArgs& a) {
+  LdgRange r;
   const long long per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
-  const long long t0 = blockIdx.x * per;
-  long long cnt = a.n_tiles - t0;
+  r.t0 = blockIdx.x * per;
+  long long cnt = a.n_tiles - r.t0;
   if (cnt > per) cnt = per;
   if (cnt < 0) cnt = 0;
-  const int n_res = static_cast<int>(cnt < a.n_res ? cnt : a.n_res);
+  const long long tm_cap = TmemTiles<K>::kMax < a.n_tm ? TmemTiles<K>::kMax : a.n_tm;
+  r.n_tm = static_cast<int>(cnt < tm_cap ? cnt : tm_cap);
+  r.cnt = cnt - r.n_tm;
+  r.n_res = static_cast<int>(r.cnt < a.n_res ? r.cnt : a.n_res);
+  return r;
+}
+
+template <int K, int NW>
+__device__ __forceinline__ void ldg_load_resident(const KArgs& a, const SmemLayout& sm, uint32_t tm_base) {
+  if (a.n_res <= 0 && tm_base == kNoTmem) return;
+  const LdgRange r = ldg_range<K>(a);
   const long long stride_t = static_cast<long long>(a.Kact) * 32;  // float2 per tile
-  const float4* src = reinterpret_cast<const float4*>(a.Xt + t0 * stride_t);  // tiles start 256-byte aligned
-  float4* dst = reinterpret_cast<float4*>(sm.ring);
-  const long long n4 = static_cast<long long>(n_res) * stride_t / 2;
-  for (long long i = threadIdx.x; i < n4; i += NW * 32) dst[i] = __ldcg(src + i);
-  float* dy = sm.ring + static_cast<long long>(n_res) * stride_t * 2;
-  for (int i = threadIdx.x; i < n_res * 32; i += NW * 32) dy[i] = __ldcg(a.Yt + t0 * 32 + i);
+  if (a.n_res > 0) {
+    const float4* src = reinterpret_cast<const float4*>(a.Xt + r.t0 * stride_t);  // tiles start 256-byte aligned
+    float4* dst = reinterpret_cast<float4*>(sm.ring);
+    const long long n4 = static_cast<long long>(r.n_res) * stride_t / 2;
+    for (long long i = threadIdx.x; i < n4; i += NW * 32) dst[i] = __ldcg(src + i);
+    float* dy = sm.ring + static_cast<long long>(r.n_res) * stride_t * 2;
+    for (int i = threadIdx.x; i < r.n_res * 32; i += NW * 32) dy[i] = __ldcg(a.Yt + r.t0 * 32 + i);
+  }
+  if constexpr (TmemTiles<K>::kMax > 0) {
+    if (tm_base != kNoTmem) {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int q = warp & 3;
+      float* tm_y = sm.ring + static_cast<long long>(r.n_res) * (stride_t * 2 + 32);
+      const long long tile0 = r.t0 + r.cnt;
+      for (int slot = warp >> 2; 4 * slot + q < r.n_tm; slot += NW / 4) {
+        const int tt = 4 * slot + q;
+        const float2* p = a.Xt + (tile0 + tt) * stride_t + lane;
+        uint32_t v[2 * K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const float2 xv = (i < a.Kact) ? __ldcg(p + i * 32) : make_float2(0.0f, 0.0f);
+          v[2 * i] = __float_as_uint(xv.x);
+          v[2 * i + 1] = __float_as_uint(xv.y);
+        }
+        tmem_st_cols<2 * K>(tm_base + (static_cast<uint32_t>(q * 32) << 16) + slot * TmemTiles<K>::kCols, v);
+        tm_y[tt * 32 + lane] = __ldcg(a.Yt + (tile0 + tt) * 32 + lane);
+      }
+      tmem_wait_st();  // a warp only ever reads back the tiles it stored itself
+    }
+  }
   __syncthreads();
 }
 
 // One pass of this CTA over its tiles (ring mode 2). Same contract as stream_pass / stream_pass_cta: on return
 // cta_acc[0..P] holds the CTA's float64 sums, reduced in a fixed order; ends with a __syncthreads().
 template <int K, int NW>
-__device__ __forceinline__ void stream_pass_ldg(const KArgs& a, const SmemLayout& sm, float bias, bool want_lp, bool backward) {
-  const long long per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
-  const long long t0 = blockIdx.x * per;
-  long long cnt = a.n_tiles - t0;
-  if (cnt > per) cnt = per;
-  if (cnt < 0) cnt = 0;
+__device__ __forceinline__ void stream_pass_ldg(const KArgs& a, const SmemLayout& sm, float bias, bool want_lp, bool backward,
+                                                uint32_t tm_base) {
+  const LdgRange r = ldg_range<K>(a);
   const float2* theta2 = reinterpret_cast<const float2*>(sm.theta_s);
   const float* res = sm.ring;
-  const int n_res = static_cast<int>(cnt < a.n_res ? cnt : a.n_res);
+  const float* tm_y = sm.ring + static_cast<long long>(r.n_res) * (static_cast<long long>(a.Kact) * 64 + 32);
   float2 g[K];
   float gb;
   double lp;
   const int fam = a.family;
+#define EDHMC_LDG_ARGS a.Xt, a.Yt, a.Kact, r.t0, r.cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, r.n_res, r.n_tm, tm_base, tm_y, g, &gb, &lp
   if (want_lp) {
     if (fam == 0)
-      stream_pass_ldg_tiles<K, NW, 0, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 0, 1>(EDHMC_LDG_ARGS);
     else if (fam == 1)
-      stream_pass_ldg_tiles<K, NW, 1, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 1, 1>(EDHMC_LDG_ARGS);
     else
-      stream_pass_ldg_tiles<K, NW, 2, 1>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 2, 1>(EDHMC_LDG_ARGS);
   } else {
     if (fam == 0)
-      stream_pass_ldg_tiles<K, NW, 0, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 0, 0>(EDHMC_LDG_ARGS);
     else if (fam == 1)
-      stream_pass_ldg_tiles<K, NW, 1, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 1, 0>(EDHMC_LDG_ARGS);
     else
-      stream_pass_ldg_tiles<K, NW, 2, 0>(a.Xt, a.Yt, a.Kact, t0, cnt, backward, a.n_rows, theta2, bias, a.lik_scale, res, n_res, g, &gb, &lp);
+      stream_pass_ldg_tiles<K, NW, 2, 0>(EDHMC_LDG_ARGS);
   }
+#undef EDHMC_LDG_ARGS
   PlanRegs pr_unused = {};
   int wt_unused = 0, ring_unused = 0;
   pass_reduce<1, 2, K, NW, true>(a, pr_unused, wt_unused, ring_unused, sm, g, gb, lp, false, false, 0u, 0ull);

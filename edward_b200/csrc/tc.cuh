@@ -52,6 +52,56 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+// Narrower shapes of the same 32x32b access (lane = TMEM lane of the warp's quarter, N consecutive 32-bit columns per lane):
+// used by the single-chain sampler, which parks rows of X in TMEM for a whole persistent launch (stream_ldg.cuh).
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(v[0]), "r"(v[1]) : "memory");
+}
+// N (even) consecutive columns as a ladder of x16 / x8 / x4 / x2 accesses
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]) {
+  static_assert(N % 2 == 0, "even column counts only");
+  constexpr int n16 = N / 16, r16 = N - 16 * n16;
+#pragma unroll
+  for (int i = 0; i < n16; ++i) tmem_ld16(taddr + 16 * i, &v[16 * i]);
+  if constexpr ((r16 & 8) != 0) tmem_ld8(taddr + 16 * n16, &v[16 * n16]);
+  if constexpr ((r16 & 4) != 0) tmem_ld4(taddr + 16 * n16 + (r16 & 8), &v[16 * n16 + (r16 & 8)]);
+  if constexpr ((r16 & 2) != 0) tmem_ld2(taddr + 16 * n16 + (r16 & 12), &v[16 * n16 + (r16 & 12)]);
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[N]) {
+  static_assert(N % 2 == 0, "even column counts only");
+  constexpr int n16 = N / 16, r16 = N - 16 * n16;
+#pragma unroll
+  for (int i = 0; i < n16; ++i) tmem_st16(taddr + 16 * i, &v[16 * i]);
+  if constexpr ((r16 & 8) != 0) tmem_st8(taddr + 16 * n16, &v[16 * n16]);
+  if constexpr ((r16 & 4) != 0) tmem_st4(taddr + 16 * n16 + (r16 & 8), &v[16 * n16 + (r16 & 8)]);
+  if constexpr ((r16 & 2) != 0) tmem_st2(taddr + 16 * n16 + (r16 & 12), &v[16 * n16 + (r16 & 12)]);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

@@ -124,10 +124,12 @@ def test_persistent_and_stepwise_plans_bit_identical_on_ldg_tiles():
 
 
 def test_plan_rule_picks_ldg_tiles_for_the_measured_shapes():
-  """make_plan (csrc/edhmc.cu): ring mode 2 for D <= 48 and D = 63, 64; the CTA-wide ring for 49 <= D <= 62 (cfg 2)."""
+  """make_plan (csrc/edhmc.cu): ring mode 2 for D <= 48 and D = 63, 64; for 49 <= D <= 62 ring mode 2 when at least 30 % of
+  a CTA's tiles stay resident in shared / tensor memory (cfg 2), else the CTA-wide ring."""
   with _ring(None):
-    for D, want in ((8, 2), (32, 2), (48, 2), (54, 1), (60, 1), (64, 2), (100, None)):
-      X, y, spec = _mk(5000, D, False, o.BERNOULLI_LOGIT, seed=D)
+    for D, N, want in ((8, 5000, 2), (32, 5000, 2), (48, 5000, 2), (54, 5000, 2), (54, 581012, 2), (54, 2000000, 1),
+                       (60, 1000000, 1), (64, 5000, 2), (100, 5000, None)):
+      X, y, spec = _mk(N, D, False, o.BERNOULLI_LOGIT, seed=D)
       s = _sampler(X, y, spec)
       rm = s.plan_info()["ring_mode"]
       s.close()
