@@ -1832,7 +1832,7 @@ int edhmc_chains_plan_probe(int64_t n_rows, int32_t n_features, int32_t n_chains
 
 int edhmc_plan_info(edhmc_t* h, int64_t* out, int32_t cap) {
   if (!h || !out) return fail(EDHMC_ERR_INVALID, "null argument");
-  const int64_t v[11] = {h->plan.grid,
+  const int64_t v[13] = {h->plan.grid,
                          h->plan.NW,
                          h->plan.S,
                          h->plan.RT,
@@ -1842,8 +1842,10 @@ int edhmc_plan_info(edhmc_t* h, int64_t* out, int32_t cap) {
                          h->plan_in_use,
                          h->passes_last,
                          h->launches_last,
-                         h->plan.RM};
-  int n = cap < 11 ? cap : 11;
+                         h->plan.RM,
+                         h->plan.RM == 2 ? h->plan.n_res : 0,
+                         h->plan.RM == 2 ? h->plan.n_tm : 0};
+  int n = cap < 13 ? cap : 13;
   for (int i = 0; i < n; ++i) out[i] = v[i];
   return n;
 }

@@ -327,10 +327,11 @@ class GLMSampler:
   def plan_info(self) -> dict:
     if self.dtype == torch.float64:
       return {"plan_in_use": _C.PLAN_STEPWISE, "dtype": "f64"}
-    out = (C.c_int64 * 11)()
-    n = _C.check(self.lib.edhmc_plan_info(self._h, out, 11))
+    out = (C.c_int64 * 13)()
+    n = _C.check(self.lib.edhmc_plan_info(self._h, out, 13))
     keys = ["grid_ctas", "warps_per_cta", "ring_stages", "tile_rows", "lanes_per_row", "vec_width", "smem_bytes",
-            "plan_in_use", "passes_last_run", "launches_last_run", "ring_mode"]
+            "plan_in_use", "passes_last_run", "launches_last_run", "ring_mode", "smem_resident_tiles_per_cta",
+            "tmem_resident_tiles_per_cta"]
     return {k: int(out[i]) for i, k in enumerate(keys[:n])}
 
   def close(self):

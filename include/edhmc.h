@@ -258,7 +258,9 @@ int edhmc_probe_read(const void* buf, int64_t bytes, int32_t iters, int32_t mode
 
 /* Introspection for benches/tests: fills up to `cap` int64 values:
  * {grid_ctas, warps_per_cta, ring_stages, tile_rows, lanes_per_row, vec_width, smem_bytes,
- *  plan_in_use, passes_last_run, launches_last_run, ring_mode (0: one TMA ring per warp, 1: one ring per CTA, 2: re-laid 32-row tiles read with LDG)}.
+ *  plan_in_use, passes_last_run, launches_last_run, ring_mode (0: one TMA ring per warp, 1: one ring per CTA, 2: re-laid
+ *  32-row tiles read with LDG), and for ring mode 2 the 32-row tiles per CTA that a persistent launch keeps resident in
+ *  shared memory and in tensor memory}.
  * Returns the number written. */
 int edhmc_plan_info(edhmc_t* h, int64_t* out_host, int32_t cap);
 

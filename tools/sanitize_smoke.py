@@ -19,7 +19,9 @@ def data(N, D):
   return X, y
 
 
-for (N, D, bias) in [(1000, 54, False), (777, 5, True), (300, 130, False), (4096, 64, False), (513, 1000, False)]:
+# (D <= 64 takes ring mode 2: re-laid tiles, shared-memory- and tensor-memory-resident tiles on the persistent plan)
+for (N, D, bias) in [(1000, 54, False), (777, 5, True), (300, 130, False), (4096, 64, False), (513, 1000, False), (20011, 16, True),
+                     (9000, 32, False), (70001, 54, False)]:
   X, y = data(N, D)
   for plan in (_C.PLAN_PERSISTENT, _C.PLAN_STEPWISE):
     s = engine.GLMSampler(engine.GLMSpec(D, has_bias=bias), X, y, device=dev, plan=plan)
