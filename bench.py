@@ -323,7 +323,8 @@ def timeline_of(torch, s, run_once, n_passes=48):
   else:
     d = {
         "unit": "SM cycles (clock64), median over CTAs and passes 8..%d of one launch" % (n_passes - 1),
-        "protocol": "grid barrier, every CTA reads every CTA's partials",
+        "protocol": ("flag-in-data partials -> group sums -> every CTA sums the groups and integrates (grid_barrier_* = publish -> totals)"
+                     if t.shape[1] > 1 and np.any(t[:, 1:, 21]) else "grid barrier, every CTA reads every CTA's partials"),
         "pass_tiles_and_cta_reduce": float(np.median(t[:, :, 1] - t[:, :, 0])),
         "publish_partials": float(np.median(t[:, :, 2] - t[:, :, 1])),
         "grid_barrier_wait_median": float(np.median(t[:, :, 3] - t[:, :, 2])),

@@ -521,8 +521,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
   // leader protocol (see ll_reduce_partials): the host selects it for one GPU and P+1 <= kWideCols
   // (a.leader is set only for the persistent plan on one GPU with a narrow model and more than one CTA). Nothing of it
   // is kept in registers across the data pass: the flag comes from the constant bank, in_init0 from shared memory.
+  // a.leader == 2 ("flat"): the partials and group sums travel the same way, but EVERY CTA polls the group sums and runs
+  // the O(P) integrator itself on its own copy of the chain state (as the grid-barrier protocol does), so the next position
+  // needs no broadcast: one L2 round trip (leader -> workers) less per leapfrog step. Only CTA 0 writes global state.
 #define EDHMC_LEAD (a.leader != 0)
-#define EDHMC_WORKER (a.leader != 0 && blockIdx.x != 0)
+#define EDHMC_WORKER (a.leader == 1 && blockIdx.x != 0)
   if (tid == 0) s_init0 = in_init ? 1 : 0;
   __syncthreads();
   for (long long pass = 0; pass < n_passes; ++pass) {
@@ -714,7 +717,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_hmc(const KArgs a) {
       }
     }
     EDHMC_TL(23, clock64());
-    if (EDHMC_LEAD && pass + 1 < n_passes) {
+    if (a.leader == 1 && pass + 1 < n_passes) {
       // the position of pass + 1 to the workers; each thread sends the latents it has just written itself
       const unsigned int seq_next = a.ll_seq0 + static_cast<unsigned int>(pass) + 2u;
       uint2* dst = a.ll_theta + static_cast<size_t>((pass + 1) & 1) * kLlCopies * P;

@@ -176,7 +176,8 @@ struct edhmc_handle {
   uint4* d_ll_group = nullptr;  // leader protocol: sums of groups of kLlGroup CTAs [2][ceil(num_sms / kLlGroup)][P+1]
   uint2* d_ll_theta = nullptr;  // leader protocol: flag-in-data position [2][P]
   unsigned int ll_seq = 1;      // sequence numbers handed out so far
-  int leader = 1;               // EDHMC_LEADER=0 keeps the grid-barrier protocol on one GPU (same-box A/B)
+  int leader = 2;               // 2: flag-in-data partials + group sums, every CTA integrates (default); 1: CTA 0 integrates and
+                                // broadcasts the position; 0: grid barrier, every CTA reads every partial (EDHMC_LEADER, same-box A/B)
   size_t partials_cap = 0;
   unsigned long long* d_bar = nullptr;
   unsigned int* d_ticket = nullptr;
@@ -531,7 +532,7 @@ static bool make_plan_ldg(edhmc_handle* h, Plan& out) {
   p.RT = 32;
   p.S = 0;
   p.stage_floats = 0;
-  p.wpad = 2 * K;
+  p.wpad = (2 * K + 3) / 4 * 4;  // theta is read with LDS.128
   p.fn = lookup_kernel(1, 2, K, p.NW, 2);
   if (!p.fn) return false;
   const long long n_tiles = (c.n_rows + 31) / 32;
@@ -1274,7 +1275,7 @@ int edhmc_run(edhmc_t* h, float* params, int64_t ldp, int64_t T, int64_t t0, int
     a.mode = 0;
     if (h->leader && h->d_ll_part && a.nranks == 1 && h->plan.grid > 1 && h->plan.grid <= h->num_sms &&
         h->plan.grid <= kLlGroup * kLlMaxGroups && n_iter * n_steps < (1ll << 30)) {
-      a.leader = 1;
+      a.leader = h->leader >= 2 ? 2 : 1;
       a.ll_part = h->d_ll_part;
       a.ll_theta = h->d_ll_theta;
       a.ll_group = h->d_ll_group;

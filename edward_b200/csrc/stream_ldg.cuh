@@ -80,13 +80,12 @@ template <int K, int FAM, int LPM>
 __device__ __forceinline__ void ldg_row_math(const float2 (&x)[K], float yv, bool valid_row, const float2* __restrict__ theta2,
                                              float bias, float lik_scale, float2 (&g)[K], float& gb, double& lp) {
   float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+  const float4* theta4 = reinterpret_cast<const float4*>(theta2);
 #pragma unroll
-  for (int i = 0; i < K; ++i) {
-    const float2 w = theta2[i];  // broadcast LDS.64 (entries >= D are zero)
-    if (i & 1)
-      a1 = fma2(x[i], w, a1);
-    else
-      a0 = fma2(x[i], w, a0);
+  for (int i = 0; i < K; i += 2) {
+    const float4 w = theta4[i >> 1];  // broadcast LDS.128: two pairs per shared-memory wavefront (entries >= D are zero)
+    a0 = fma2(x[i], make_float2(w.x, w.y), a0);
+    if (i + 1 < K) a1 = fma2(x[i + 1], make_float2(w.z, w.w), a1);
   }
   const float eta = ((a0.x + a0.y) + (a1.x + a1.y)) + bias;
   float lpv = 0.0f, rv;
@@ -182,13 +181,12 @@ __device__ __forceinline__ void stream_pass_ldg_tiles(const float2* __restrict__
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+      const float4* theta4 = reinterpret_cast<const float4*>(theta2);
 #pragma unroll
-      for (int i = 0; i < K; ++i) {
-        const float2 w = theta2[i];  // broadcast LDS.64 (entries >= D are zero)
-        if (i & 1)
-          a1 = fma2(x[j][i], w, a1);
-        else
-          a0 = fma2(x[j][i], w, a0);
+      for (int i = 0; i < K; i += 2) {
+        const float4 w = theta4[i >> 1];  // broadcast LDS.128: two pairs per shared-memory wavefront (entries >= D are zero)
+        a0 = fma2(x[j][i], make_float2(w.x, w.y), a0);
+        if (i + 1 < K) a1 = fma2(x[j][i + 1], make_float2(w.z, w.w), a1);
       }
       const float eta = ((a0.x + a0.y) + (a1.x + a1.y)) + bias;
       float lpv = 0.0f, rv;
