@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _C
+from . import graph as _graph
 
 
 @dataclass
@@ -206,6 +207,7 @@ class GLMSampler:
       fn = self.lib.edhmc_run_f64 if self.dtype == torch.float64 else self.lib.edhmc_run
       _C.check(fn(self._h, params.data_ptr(), int(params.stride(0)), int(params.shape[0]), int(t0),
                   int(n_iter), float(step_size), int(n_steps), r0p, up, _stream_ptr(self.dev)))
+    _graph.bump_device_epoch()  # the sample store changed: host mirrors of its variables are stale
 
   # ---- SGLD / SGHMC on the same gradient kernel (sgld.py:52-87, sghmc.py:58-96) -----------------
   def sgmcmc_run(self, kind: str, params: torch.Tensor, t0: int, n_iter: int, step_size: float, friction: float = 0.1,
@@ -233,6 +235,7 @@ class GLMSampler:
                                          int(n_iter), float(step_size), float(friction), float(lik_factor), pf,
                                          velocity.data_ptr() if velocity is not None else None, nz, int(batch_rows),
                                          _stream_ptr(self.dev)))
+    _graph.bump_device_epoch()
 
   # ---- C vectorised chains (extension) ---------------------------------------------------------
   def logp_grad_chains(self, theta):
@@ -265,6 +268,7 @@ class GLMSampler:
     with torch.cuda.device(self.dev):
       _C.check(self.lib.edhmc_run_chains(self._h, params.data_ptr(), int(params.shape[0]), int(t0), int(n_iter),
                                          float(step_size), int(n_steps), r0p, up, _stream_ptr(self.dev)))
+    _graph.bump_device_epoch()
 
   def read_chain_state(self):
     n = (C.c_int64 * self.n_chains)()

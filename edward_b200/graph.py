@@ -198,6 +198,21 @@ class Placeholder(Tensor):
     return np.asarray(feed[id(self)], self.dtype.np)
 
 
+# Host mirrors of device-resident variables are cached between device writes: every launch that can write a sample
+# store (engine.GLMSampler.run / sgmcmc_run / run_chains, Variable.load / rebind, checkpoint restore) bumps this epoch.
+# The reference's example draws 100 single rows from the Empirical store every 10 iterations
+# (examples/bayesian_logistic_regression.py:91-96); without the mirror each draw is a host-device round trip.
+_device_epoch = [0]
+
+
+def bump_device_epoch():
+  _device_epoch[0] += 1
+
+
+def device_epoch():
+  return _device_epoch[0]
+
+
 class Variable(Tensor):
   """Mutable tensor. Until a sampler adopts it, it lives on the host; `ed.HMC.initialize` re-homes the
   Empirical parameter variables into device memory (`rebind`) so that the sample store stays on the
@@ -219,6 +234,7 @@ class Variable(Tensor):
     self.name = name
     self.trainable = trainable
     self._storage = None  # torch tensor (device) once adopted by a sampler
+    self._mirror, self._mirror_epoch = None, -1  # host copy of _storage, valid while the device epoch is unchanged
     self._host = self.initial_value.copy()
     super(Variable, self).__init__(self.initial_value.shape, dtype)
     if collections is None or len(collections) > 0:
@@ -231,14 +247,24 @@ class Variable(Tensor):
     cur = self.numpy()  # the CURRENT contents: after an earlier adoption they live on the device, not in _host
     storage.copy_(torch.as_tensor(np.ascontiguousarray(cur)).to(storage.device, storage.dtype).reshape(storage.shape))
     self._storage = storage
+    bump_device_epoch()
 
   def value_tensor(self):
     """Device tensor if adopted, else None."""
     return self._storage
 
+  def host_view(self):
+    """Current contents as a host array that must not be modified (shared with the mirror cache)."""
+    if self._storage is None:
+      return self._host
+    if self._mirror_epoch != _device_epoch[0]:
+      self._mirror = self._storage.detach().cpu().numpy().reshape(tuple(self.shape)).astype(self.dtype.np, copy=False)
+      self._mirror_epoch = _device_epoch[0]
+    return self._mirror
+
   def numpy(self):
     if self._storage is not None:
-      return self._storage.detach().cpu().numpy().reshape(tuple(self.shape)).astype(self.dtype.np)
+      return self.host_view().copy()
     return self._host
 
   def load(self, value):
@@ -246,6 +272,7 @@ class Variable(Tensor):
     if self._storage is not None:
       import torch
       self._storage.copy_(torch.as_tensor(value).to(self._storage.device, self._storage.dtype).reshape(self._storage.shape))
+      bump_device_epoch()
     else:
       self._host = value.copy()
 

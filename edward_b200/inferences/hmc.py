@@ -226,6 +226,7 @@ class HMC(MonteCarlo):
     if tuple(params.shape) != tuple(self._packed.shape):
       raise ValueError("checkpoint params have shape %s, expected %s" % (params.shape, tuple(self._packed.shape)))
     self._packed.copy_(torch.as_tensor(params).to(self._packed.device))
+    _g.bump_device_epoch()
     self._sampler.reset()
     self._n_accept_base = int(state["n_accept"])
     self._t = int(state["t"])

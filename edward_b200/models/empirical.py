@@ -67,9 +67,11 @@ class Empirical(RandomVariable):
     if len(self._params.shape) == 0:
       return np.tile(_g.evaluate(self._params), sample_shape)
     idx = np.random.randint(0, self._n, size=n)
-    if t is not None:
+    if t is not None and n > 4096:
       import torch
-      rows = t[torch.as_tensor(idx, device=t.device)].cpu().numpy()
+      rows = t[torch.as_tensor(idx, device=t.device)].cpu().numpy()  # large draws: gather on the device
+    elif t is not None:
+      rows = self._params.host_view()[idx]  # host mirror, refreshed after the next device write (graph.device_epoch)
     else:
       rows = _g.evaluate(self._params)[idx]
     return rows.reshape(tuple(sample_shape) + tuple(self.event_shape)).astype(self.dtype.np)
