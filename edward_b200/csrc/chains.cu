@@ -615,7 +615,7 @@ __global__ void k_mc_check(const McArgs a) {  // one block of 256 threads
   if (threadIdx.x == 0) s_need = !*a.valid;
   __syncthreads();
   const long long t_prev = a.t0 > 0 ? a.t0 - 1 : 0;
-  const size_t n = static_cast<size_t>(a.C) * a.D;
+  const size_t n = static_cast<size_t>(a.Cu) * a.D;  // the caller's chains are the first Cu rows of zcur
   bool mismatch = false;
   for (size_t i = threadIdx.x; i < n; i += blockDim.x)
     if (__float_as_uint(a.params[t_prev * n + i]) != __float_as_uint(a.zcur[i])) mismatch = true;
@@ -653,7 +653,7 @@ __device__ __forceinline__ void mc_finish_transition(const McArgs& a, int c, lon
       a.zcur[cd] = a.z[cd];
       a.gcur[cd] = a.g[cd];
     }
-    a.params[(static_cast<size_t>(t) * a.C + c) * a.D + d] = accept ? a.z[cd] : a.zcur[cd];
+    a.params[(static_cast<size_t>(t) * a.Cu + c) * a.D + d] = accept ? a.z[cd] : a.zcur[cd];
   }
   if (d == 0) {
     if (accept) {
@@ -661,7 +661,7 @@ __device__ __forceinline__ void mc_finish_transition(const McArgs& a, int c, lon
       a.n_accept[c] += 1;
     }
     if (a.trace) {
-      double* tr = a.trace + (static_cast<size_t>(it) * a.C + c) * 8;
+      double* tr = a.trace + (static_cast<size_t>(it) * a.Cu + c) * 8;
       tr[0] = logp_cur;
       tr[1] = logp_new;
       tr[2] = k_old;
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(kMcChainThreads) k_mc_begin(const McArgs a, lo
   const size_t cd = static_cast<size_t>(c) * a.D + d;
   float rv = 0.0f;
   if (d < a.D) {
-    rv = a.r0 ? a.r0[(static_cast<size_t>(it) * a.C + c) * a.D + d] : philox_normal(a.seed + 0x9E3779B97F4A7C15ull * (c + 1), t, d);
+    rv = a.r0 ? a.r0[(static_cast<size_t>(it) * a.Cu + c) * a.D + d] : philox_normal(a.seed + 0x9E3779B97F4A7C15ull * (c + 1), t, d);
     float zz = a.zcur[cd];
     float rr = rv;
     const float gg = a.gcur[cd];
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(kMcChainThreads) k_mc_begin(const McArgs a, lo
   }
   const double k_old = 0.5 * chain_sum(static_cast<double>(__fmul_rn(rv, rv)), sh);
   if (d == 0) {
-    const float u = a.u ? a.u[static_cast<size_t>(it) * a.C + c] : philox_uniform(a.seed + 0x9E3779B97F4A7C15ull * (c + 1), t);
+    const float u = a.u ? a.u[static_cast<size_t>(it) * a.Cu + c] : philox_uniform(a.seed + 0x9E3779B97F4A7C15ull * (c + 1), t);
     a.k_old[c] = k_old;
     a.log_u[c] = static_cast<double>(logf(u));
   }
@@ -785,19 +785,19 @@ cudaError_t mc_launch_check(const McArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 cudaError_t mc_launch_init_finish(const McArgs& a, cudaStream_t s) {
-  k_mc_init_finish<<<a.C, kMcChainThreads, 0, s>>>(a);
+  k_mc_init_finish<<<a.Cu, kMcChainThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t mc_launch_begin(const McArgs& a, long long it, cudaStream_t s) {
-  k_mc_begin<<<a.C, kMcChainThreads, 0, s>>>(a, it);
+  k_mc_begin<<<a.Cu, kMcChainThreads, 0, s>>>(a, it);
   return cudaGetLastError();
 }
 cudaError_t mc_launch_leap(const McArgs& a, long long it, int step, cudaStream_t s) {
-  k_mc_leap<<<a.C, kMcChainThreads, 0, s>>>(a, it, step);
+  k_mc_leap<<<a.Cu, kMcChainThreads, 0, s>>>(a, it, step);
   return cudaGetLastError();
 }
 cudaError_t mc_launch_logp_grad_finish(const McArgs& a, const float* theta, double* logp, float* grad, cudaStream_t s) {
-  k_mc_logp_grad_finish<<<a.C, kMcChainThreads, 0, s>>>(a, theta, logp, grad);
+  k_mc_logp_grad_finish<<<a.Cu, kMcChainThreads, 0, s>>>(a, theta, logp, grad);
   return cudaGetLastError();
 }
 

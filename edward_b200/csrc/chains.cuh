@@ -30,7 +30,9 @@ struct McArgs {
   const float* prior_loc;    // [D]
   const float* prior_scale;  // [D]
   double prior_const;
-  int C;           // chains (multiple of 128)
+  int C;           // chains the pass kernels run: the caller's count rounded up to a multiple of 128 (padding chains sit at
+                   // theta = 0 in the handle's own state arrays and are never read back)
+  int Cu;          // the caller's chains: extent / stride of every caller-owned array (params, r0, u, trace, theta, logp, grad)
   int n_rowgroups;  // CTAs along the rows
   int seg_mode;     // development: 0 = float64 flush, 1 = synchronisation only, 2 = store only
   int seg_tiles;    // tensor-core pass: 64-row tiles accumulated in TMEM before a float64 flush (0 = default)

@@ -407,7 +407,7 @@ __device__ __forceinline__ double mcw_finish_gradient(const McwArgs& a, int c, c
 // steps over the C*D elements: compare (any mismatch raises a.valid[2]), then re-seed zcur and publish need_init.
 __global__ void k_mcw_check_compare(const McwArgs a) {
   const long long t_prev = a.t0 > 0 ? a.t0 - 1 : 0;
-  const size_t n = static_cast<size_t>(a.C) * a.D;
+  const size_t n = static_cast<size_t>(a.Cu) * a.D;  // the caller's chains are the first Cu rows of zcur
   bool mismatch = false;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
     if (__float_as_uint(a.params[t_prev * n + i]) != __float_as_uint(a.zcur[i])) mismatch = true;
@@ -416,7 +416,7 @@ __global__ void k_mcw_check_compare(const McwArgs a) {
 __global__ void k_mcw_check_apply(const McwArgs a) {
   const int need = (!a.valid[0] || a.valid[2]) ? 1 : 0;
   const long long t_prev = a.t0 > 0 ? a.t0 - 1 : 0;
-  const size_t n = static_cast<size_t>(a.C) * a.D;
+  const size_t n = static_cast<size_t>(a.Cu) * a.D;  // the caller's chains are the first Cu rows of zcur
   if (need)
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
       a.zcur[i] = a.params[t_prev * n + i];
@@ -453,7 +453,7 @@ __device__ __forceinline__ void mcw_finish_transition(const McwArgs& a, int c, l
       a.zcur[cd] = a.z[cd];
       a.gcur[cd] = a.g[cd];
     }
-    a.params[(static_cast<size_t>(t) * a.C + c) * a.D + d] = accept ? a.z[cd] : a.zcur[cd];
+    a.params[(static_cast<size_t>(t) * a.Cu + c) * a.D + d] = accept ? a.z[cd] : a.zcur[cd];
   }
   if (threadIdx.x == 0) {
     if (accept) {
@@ -461,7 +461,7 @@ __device__ __forceinline__ void mcw_finish_transition(const McwArgs& a, int c, l
       a.n_accept[c] += 1;
     }
     if (a.trace) {
-      double* tr = a.trace + (static_cast<size_t>(it) * a.C + c) * 8;
+      double* tr = a.trace + (static_cast<size_t>(it) * a.Cu + c) * 8;
       tr[0] = logp_cur;
       tr[1] = logp_new;
       tr[2] = k_old;
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(kMwChainThreads) k_mcw_begin(const McwArgs a, 
   double ks = 0.0;
   for (int d = threadIdx.x; d < a.D; d += kMwChainThreads) {
     const size_t cd = static_cast<size_t>(c) * a.D + d;
-    const float rv = a.r0 ? a.r0[(static_cast<size_t>(it) * a.C + c) * a.D + d] : philox_normal(cseed, t, d);
+    const float rv = a.r0 ? a.r0[(static_cast<size_t>(it) * a.Cu + c) * a.D + d] : philox_normal(cseed, t, d);
     float zz = a.zcur[cd];
     float rr = rv;
     const float gg = a.gcur[cd];
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kMwChainThreads) k_mcw_begin(const McwArgs a, 
   }
   const double k_old = 0.5 * mcw_chain_sum(ks, sh);
   if (threadIdx.x == 0) {
-    const float u = a.u ? a.u[static_cast<size_t>(it) * a.C + c] : philox_uniform(cseed, t);
+    const float u = a.u ? a.u[static_cast<size_t>(it) * a.Cu + c] : philox_uniform(cseed, t);
     a.k_old[c] = k_old;
     a.log_u[c] = static_cast<double>(logf(u));
   }
@@ -626,19 +626,19 @@ cudaError_t mcw_launch_check(const McwArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 cudaError_t mcw_launch_init_finish(const McwArgs& a, cudaStream_t s) {
-  k_mcw_init_finish<<<a.C, kMwChainThreads, 0, s>>>(a);
+  k_mcw_init_finish<<<a.Cu, kMwChainThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t mcw_launch_begin(const McwArgs& a, long long it, cudaStream_t s) {
-  k_mcw_begin<<<a.C, kMwChainThreads, 0, s>>>(a, it);
+  k_mcw_begin<<<a.Cu, kMwChainThreads, 0, s>>>(a, it);
   return cudaGetLastError();
 }
 cudaError_t mcw_launch_leap(const McwArgs& a, long long it, int step, cudaStream_t s) {
-  k_mcw_leap<<<a.C, kMwChainThreads, 0, s>>>(a, it, step);
+  k_mcw_leap<<<a.Cu, kMwChainThreads, 0, s>>>(a, it, step);
   return cudaGetLastError();
 }
 cudaError_t mcw_launch_logp_grad_finish(const McwArgs& a, const float* theta, double* logp, float* grad, cudaStream_t s) {
-  k_mcw_logp_grad_finish<<<a.C, kMwChainThreads, 0, s>>>(a, theta, logp, grad);
+  k_mcw_logp_grad_finish<<<a.Cu, kMwChainThreads, 0, s>>>(a, theta, logp, grad);
   return cudaGetLastError();
 }
 

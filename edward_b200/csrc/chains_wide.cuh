@@ -33,7 +33,8 @@ struct McwArgs {
   const float* prior_loc;
   const float* prior_scale;
   double prior_const;
-  int C;
+  int C;   // chains the GEMMs run (the caller's count rounded up to a multiple of 128)
+  int Cu;  // the caller's chains: extent / stride of every caller-owned array
   // tiling
   int nct;          // chain tiles of 128
   int Kp1;          // D rounded up to kMwKC

@@ -201,7 +201,10 @@ struct edhmc_handle {
   bool shared_comm = false;  // comm / peer tables belong to g_shared[device]
   long long spin_limit = 0;
   // many chains
-  int C = 0, mc_nrg = 0, mc_use_tc = 0, mc_Dp = 0;
+  int C = 0;     // the caller's chains
+  int Cpad = 0;  // rounded up to whole 128-chain tiles: what the pass kernels run and the handle's state arrays hold
+  float* mc_theta_pad = nullptr;  // [Cpad][P] staging of a caller's theta when C is not a multiple of 128
+  int mc_nrg = 0, mc_use_tc = 0, mc_Dp = 0;
   float *mc_z = nullptr, *mc_r = nullptr, *mc_g = nullptr, *mc_zcur = nullptr, *mc_gcur = nullptr;
   double *mc_part_g = nullptr, *mc_logp = nullptr, *mc_kold = nullptr, *mc_logu = nullptr, *mc_part_lp = nullptr;
   long long* mc_nacc = nullptr;
@@ -706,10 +709,6 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   if (!cfg->prior_loc_host || !cfg->prior_scale_host) return fail(EDHMC_ERR_INVALID, "prior arrays are required");
   for (int i = 0; i < 3; ++i)
     if (cfg->reserved[i] != 0) return fail(EDHMC_ERR_INVALID, "reserved fields must be zero");
-  if (cfg->n_chains > 1) {
-    if (cfg->n_chains % kMcChainsPerCta != 0)
-      return fail(EDHMC_ERR_INVALID, "n_chains must be a multiple of %d, got %d", kMcChainsPerCta, cfg->n_chains);
-  }
   const int P = cfg->n_features + (cfg->has_bias ? 1 : 0);
   double pc = 0.0;
   for (int i = 0; i < P; ++i) {
@@ -807,9 +806,10 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
   }
   if (cfg->n_chains > 1) {
     h->C = cfg->n_chains;
+    h->Cpad = (h->C + kMcChainsPerCta - 1) / kMcChainsPerCta * kMcChainsPerCta;
     h->mc_Dp = (P + 7) / 8 * 8;  // a bias latent is one more column (of ones) of the pre-tiled operand
     const long long ntiles = (cfg->n_rows + kMcTileRows - 1) / kMcTileRows;
-    long long nrg = h->num_sms / (h->C / kMcChainsPerCta);
+    long long nrg = h->num_sms / (h->Cpad / kMcChainsPerCta);
     if (nrg < 1) nrg = 1;
     if (nrg > ntiles) nrg = ntiles > 0 ? ntiles : 1;
     h->mc_nrg = static_cast<int>(nrg);
@@ -827,7 +827,8 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
       w.n_rows = cfg->n_rows;
       w.D = P;
       w.Dx = cfg->n_features;
-      w.C = h->C;
+      w.C = h->Cpad;
+      w.Cu = h->C;
       mcw_plan(w, h->num_sms);
       const McwSizes z = mcw_sizes(w);
       ALLOC(w.xk, z.xk);
@@ -851,23 +852,30 @@ int edhmc_create(edhmc_t** out, const edhmc_cfg* cfg) {
       ALLOC(h->mc_xt, xtb + 4096);
       ALLOC(h->mc_yt, ytb + 256);
     }
-    const size_t cd = static_cast<size_t>(h->C) * P * sizeof(float);
+    const size_t cd = static_cast<size_t>(h->Cpad) * P * sizeof(float);
     ALLOC(h->mc_z, cd);
     ALLOC(h->mc_r, cd);
     ALLOC(h->mc_g, cd);
     ALLOC(h->mc_zcur, cd);
     ALLOC(h->mc_gcur, cd);
-    ALLOC(h->mc_logp, h->C * sizeof(double));
-    ALLOC(h->mc_kold, h->C * sizeof(double));
-    ALLOC(h->mc_logu, h->C * sizeof(double));
-    ALLOC(h->mc_nacc, h->C * sizeof(long long));
+    ALLOC(h->mc_logp, h->Cpad * sizeof(double));
+    ALLOC(h->mc_kold, h->Cpad * sizeof(double));
+    ALLOC(h->mc_logu, h->Cpad * sizeof(double));
+    ALLOC(h->mc_nacc, h->Cpad * sizeof(long long));
     ALLOC(h->mc_flags, 4 * sizeof(int));
-    ALLOC(h->mc_part_g, static_cast<size_t>(h->mc_nrg) * h->C * h->mc_Dp * sizeof(double));
-    ALLOC(h->mc_part_lp, static_cast<size_t>(h->mc_nrg) * h->C * sizeof(double));
+    ALLOC(h->mc_part_g, static_cast<size_t>(h->mc_nrg) * h->Cpad * h->mc_Dp * sizeof(double));
+    ALLOC(h->mc_part_lp, static_cast<size_t>(h->mc_nrg) * h->Cpad * sizeof(double));
     cudaMemset(h->mc_zcur, 0, cd);
     cudaMemset(h->mc_gcur, 0, cd);
-    cudaMemset(h->mc_logp, 0, h->C * sizeof(double));
-    cudaMemset(h->mc_nacc, 0, h->C * sizeof(long long));
+    cudaMemset(h->mc_logp, 0, h->Cpad * sizeof(double));
+    cudaMemset(h->mc_nacc, 0, h->Cpad * sizeof(long long));
+    cudaMemset(h->mc_z, 0, cd);  // the padding chains (C not a multiple of 128) stay at theta = 0 for good
+    cudaMemset(h->mc_r, 0, cd);
+    cudaMemset(h->mc_g, 0, cd);
+    if (h->Cpad != h->C) {
+      ALLOC(h->mc_theta_pad, cd);
+      cudaMemset(h->mc_theta_pad, 0, cd);
+    }
     cudaMemset(h->mc_flags, 0, 4 * sizeof(int));
     if (h->mc_use_tc) {
       cudaError_t e = mc_prepare_tc();
@@ -954,6 +962,7 @@ int edhmc_destroy(edhmc_t* h) {
   h_free(h, h->d64_g);
   h_free(h, h->d64_partials);
   h_free(h, h->y_owned);
+  h_free(h, h->mc_theta_pad);
   h_free(h, h->mc_z);
   h_free(h, h->mc_r);
   h_free(h, h->mc_g);
@@ -1386,7 +1395,7 @@ int edhmc_reset(edhmc_t* h, void* stream_) {
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   CUDA_TRY(cudaMemsetAsync(h->d_sc, 0, sizeof(ChainScalars), stream));
   if (h->C > 1) {
-    CUDA_TRY(cudaMemsetAsync(h->mc_nacc, 0, h->C * sizeof(long long), stream));
+    CUDA_TRY(cudaMemsetAsync(h->mc_nacc, 0, h->Cpad * sizeof(long long), stream));
     CUDA_TRY(cudaMemsetAsync(h->mc_flags, 0, 4 * sizeof(int), stream));
   }
   return 0;
@@ -1609,7 +1618,8 @@ static void fill_mc_args(edhmc_handle* h, McArgs& a) {
   a.prior_loc = h->d_prior_loc;
   a.prior_scale = h->d_prior_scale;
   a.prior_const = h->prior_const;
-  a.C = h->C;
+  a.C = h->Cpad;
+  a.Cu = h->C;
   a.n_rowgroups = h->mc_nrg;
   if (const char* e = getenv("EDHMC_MC_SEG_MODE")) a.seg_mode = atoi(e);
   if (const char* e = getenv("EDHMC_MC_SEG")) a.seg_tiles = atoi(e);  // development: TMEM accumulation length (tiles)
@@ -1636,7 +1646,7 @@ static void fill_mc_args(edhmc_handle* h, McArgs& a) {
 }
 
 static void fill_mcw_args(edhmc_handle* h, McwArgs& a) {
-  a = h->mcw;  // tiling + buffers
+  a = h->mcw;  // tiling + buffers (C = Cpad, Cu = the caller's chains)
   const edhmc_cfg& c = h->cfg;
   a.X = h->X;
   a.y = h->y;
@@ -1770,12 +1780,17 @@ int edhmc_logp_grad_chains(edhmc_t* h, const float* theta, double* logp, float* 
   if (!h->bound) return fail(EDHMC_ERR_STATE, "edhmc_bind_data has not been called");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const float* theta_pass = theta;  // what the pass kernels read: whole 128-chain tiles
+  if (h->mc_theta_pad) {
+    CUDA_TRY(cudaMemcpyAsync(h->mc_theta_pad, theta, static_cast<size_t>(h->C) * h->P * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    theta_pass = h->mc_theta_pad;
+  }
   if (h->mc_wide) {
     McwArgs w;
     fill_mcw_args(h, w);
     h->launches_last = 0;
     h->passes_last = 1;
-    if (int rc = mcw_pass(h, w, theta, 0, stream)) return rc;
+    if (int rc = mcw_pass(h, w, theta_pass, 0, stream)) return rc;
     CUDA_TRY(mcw_launch_logp_grad_finish(w, theta, logp, grad, stream));
     ++h->launches_last;
     return 0;
@@ -1783,7 +1798,7 @@ int edhmc_logp_grad_chains(edhmc_t* h, const float* theta, double* logp, float* 
   McArgs a;
   fill_mc_args(h, a);
   if (int rc = mc_ensure_pretiled(h, a, stream)) return rc;
-  CUDA_TRY(mc_launch_pass(a, theta, h->mc_use_tc, 0, stream));
+  CUDA_TRY(mc_launch_pass(a, theta_pass, h->mc_use_tc, 0, stream));
   CUDA_TRY(mc_launch_logp_grad_finish(a, theta, logp, grad, stream));
   h->launches_last = 2;
   h->passes_last = 1;
@@ -1817,14 +1832,14 @@ int edhmc_chains_plan_probe(int64_t n_rows, int32_t n_features, int32_t n_chains
   if (!out8) return fail(EDHMC_ERR_INVALID, "null argument");
   if (n_rows < 1 || n_features < 1 || n_features > kMaxFeatures || num_sms < 1)
     return fail(EDHMC_ERR_INVALID, "bad n_rows / n_features / num_sms");
-  if (n_chains < kMcChainsPerCta || n_chains % kMcChainsPerCta != 0)
-    return fail(EDHMC_ERR_INVALID, "n_chains must be a multiple of %d, got %d", kMcChainsPerCta, n_chains);
+  if (n_chains < 2) return fail(EDHMC_ERR_INVALID, "n_chains must be >= 2, got %d", n_chains);
   McwArgs w;
   memset(&w, 0, sizeof(w));
   w.n_rows = n_rows;
   w.D = n_features;
   w.Dx = n_features;
-  w.C = n_chains;
+  w.C = (n_chains + kMcChainsPerCta - 1) / kMcChainsPerCta * kMcChainsPerCta;
+  w.Cu = n_chains;
   mcw_plan(w, num_sms);
   const int64_t v[8] = {w.nct, w.Kp1, w.nrt, w.nft, w.NB2, w.g1, w.splits, w.Dp2};
   for (int i = 0; i < 8; ++i) out8[i] = v[i];

@@ -93,7 +93,8 @@ typedef struct edhmc_cfg {
   int32_t device;          /* CUDA device ordinal */
   int32_t plan;            /* edhmc_plan */
   int32_t debug;           /* 1: check log-joint/gradient for NaN/Inf after every run (inference.py:279-281) */
-  int32_t n_chains;        /* 0 or 1: one chain (the reference). C > 1: C vectorised chains (extension; C % 128 == 0,
+  int32_t n_chains;        /* 0 or 1: one chain (the reference). C > 1: C vectorised chains (extension; any C — the kernels run whole
+                              128-chain tiles, the padding chains are internal;
                               n_features + bias <= 64 on the one-kernel path, wider models on the two-GEMM path)
                               served by edhmc_run_chains / edhmc_logp_grad_chains */
   int32_t dtype;           /* edhmc_dtype */

@@ -131,4 +131,5 @@ def test_wide_chain_tiling_probe():
     assert p["Kp1"] % 16 == 0 and p["Kp1"] >= d and p["nrt"] * 128 >= n
     assert 1 <= p["g1"] <= max(1, p["nrt"]) and p["nct"] * p["g1"] <= 148
     assert p["splits"] >= 1 and p["nct"] * p["nft"] * p["splits"] <= max(148, p["nct"] * p["nft"])
-  assert L.edhmc_chains_plan_probe(100, 8, 100, 148, out) == _C.ERR_INVALID
+  assert probe(100, 8, 100)["nct"] == 1 and probe(1000, 200, 130)["nct"] == 2  # any chain count: whole 128-chain tiles
+  assert L.edhmc_chains_plan_probe(100, 8, 1, 148, out) == _C.ERR_INVALID

@@ -113,8 +113,10 @@ def test_tc_and_simple_paths_agree_and_match_single_chain_kernel(monkeypatch):
 def test_chain_argument_checks():
   from edward_b200 import _C, engine
   X, y = _data(100, 8, 0)
-  with pytest.raises(_C.EdhmcError):
-    engine.GLMSampler(engine.GLMSpec(8), X, y, n_chains=100)   # not a multiple of 128
+  s = engine.GLMSampler(engine.GLMSpec(8), X, y, n_chains=100)   # any chain count: the kernels pad to whole 128-chain tiles
+  with pytest.raises(TypeError):
+    s.run_chains(__import__("torch").zeros(2, 128, 8, device="cuda"), 0, 2, 0.01, 2)  # params must be [T, 100, 8]
+  s.close()
 
 
 # ---- wide models / the two-GEMM path (chains_wide.cu): n_features > 64, or forced with EDHMC_MC_IMPL=wide ----
@@ -234,4 +236,48 @@ def test_chain_run_with_bias_latent_matches_independent_oracle_runs(D, impl, mon
     if not forked:
       assert n_acc[c] == nacc
   assert ties <= 1
+  s.close()
+
+
+# ---- chain counts that are not multiples of 128: the pass kernels run whole 128-chain tiles, the padding chains live in
+#      the handle's own state arrays only; every caller-owned array has exactly C chains ----
+@pytest.mark.parametrize("N,D,C,impl", [(1000, 54, 100, "tc"), (1000, 54, 100, "simple"), (3000, 20, 130, "tc"), (900, 8, 2, "tc"),
+                                        (1500, 200, 200, "tc"), (1000, 54, 70, "wide")])
+def test_chain_counts_not_multiple_of_128(N, D, C, impl, monkeypatch):
+  import torch
+  X, y = _data(N, D, N + C)
+  s = _sampler(X, y, D, C, impl, monkeypatch)
+  rng = np.random.Generator(np.random.Philox(key=C))
+  theta = (0.3 * rng.standard_normal((C, D)) / np.sqrt(D)).astype(np.float32)
+  lp, g = s.logp_grad_chains(theta)
+  lp, g = lp.cpu().numpy(), g.cpu().numpy()
+  assert lp.shape == (C,) and g.shape == (C, D)
+  spec = o.GLMSpec(D)
+  for c in sorted({0, C // 2, C - 1}):
+    lp64 = float(o.log_joint(X, y, theta[c], spec))
+    g64 = o.grad_log_joint(X, y, theta[c], spec)
+    assert abs(lp[c] - lp64) <= REL_LOGP * abs(lp64), (c, lp[c], lp64)
+    assert np.max(np.abs(g[c] - g64)) / np.max(np.abs(g64)) <= REL_GRAD, c
+  T, L, eps = 4, 3, 0.02
+  r0 = rng.standard_normal((T, C, D), dtype=np.float32)
+  u = np.clip(rng.random((T, C), dtype=np.float32), 1e-7, 1 - 1e-7).astype(np.float32)
+  params = torch.zeros(T, C, D, device="cuda")
+  tr = s.set_chain_trace(T)
+  s.run_chains(params, 0, T, eps, L, r0=torch.tensor(r0), u=torch.tensor(u))
+  n_acc, _ = s.read_chain_state()
+  assert len(n_acc) == C
+  got, tr = params.cpu().numpy(), tr.cpu().numpy()
+  for c in sorted({0, C - 1}):
+    p64 = np.zeros((T, D))
+    infos, nacc = o.run(X, y, p64, r0[:, c], u[:, c], eps, L, spec)
+    forked = False
+    for i, info in enumerate(infos):
+      assert abs(tr[i, c, 1] - info.logp_new) <= REL_LOGP * abs(info.logp_new) + 1e-6, (c, i)
+      if bool(tr[i, c, 6] > 0.5) != info.accept:
+        assert info.margin < TIE_EPS, (c, i, info)
+        forked = True
+        break
+      assert np.max(np.abs(got[i, c] - p64[i])) <= REL_POS * max(np.max(np.abs(p64[i])), 1e-3), (c, i)
+    if not forked:
+      assert n_acc[c] == nacc
   s.close()
