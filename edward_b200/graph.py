@@ -258,7 +258,8 @@ class Variable(Tensor):
     if self._storage is None:
       return self._host
     if self._mirror_epoch != _device_epoch[0]:
-      self._mirror = self._storage.detach().cpu().numpy().reshape(tuple(self.shape)).astype(self.dtype.np, copy=False)
+      m = self._storage.detach().cpu().numpy().reshape(tuple(self.shape)).astype(self.dtype.np, copy=False)
+      self._mirror = m.copy() if self._storage.device.type == "cpu" else m  # (.cpu() of a CPU tensor aliases it)
       self._mirror_epoch = _device_epoch[0]
     return self._mirror
 

@@ -201,3 +201,31 @@ def test_progbar_output_format():
   assert " 1/50 [  2%]" in out and "ETA:" in out
   assert "50/50 [100%]" in out and "Elapsed:" in out and "Acceptance Rate: 0.250" in out
   assert out.endswith("\n")
+
+
+def test_host_mirror_of_adopted_variables_follows_the_device_epoch():
+  """graph.Variable.host_view: one device-to-host copy per device-write epoch. A CPU torch tensor stands in for the
+  device store here; engine.GLMSampler.run / sgmcmc_run / run_chains, Variable.load / rebind and checkpoint restore bump
+  the epoch on the real path."""
+  import torch
+  ed, tf, Bernoulli, Empirical, Normal, Poisson = _imports()
+  from edward_b200 import graph as g
+  v = tf.Variable(tf.zeros([6, 2]))
+  assert v.host_view() is v._host                       # not adopted: the host array itself
+  store = torch.arange(12, dtype=torch.float32).reshape(6, 2)
+  v.rebind(store)                                       # adoption copies the current contents (zeros) in
+  assert torch.equal(store, torch.zeros(6, 2))
+  a = v.host_view()
+  assert v.host_view() is a                             # cached
+  store += 1.0                                          # a "kernel" writes the store ...
+  assert np.all(v.host_view() == 0.0)                   # ... the mirror is stale until the launch site bumps the epoch
+  g.bump_device_epoch()
+  assert np.all(v.host_view() == 1.0) and v.host_view() is not a
+  v.load(np.full((6, 2), 3.0, np.float32))              # load() writes through and bumps
+  assert np.all(v.numpy() == 3.0) and torch.equal(store, torch.full((6, 2), 3.0))
+  out = v.numpy()
+  out[:] = -1.0                                         # numpy() hands out a copy
+  assert np.all(v.host_view() == 3.0)
+  q = Empirical(params=v)
+  s = q.sample(5).eval()                                # draws rows from the mirror
+  assert s.shape == (5, 2) and np.all(s == 3.0)
