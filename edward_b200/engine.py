@@ -69,7 +69,9 @@ class GLMSampler:
     P = spec.n_params
     loc = np.zeros(P, np.float32) if spec.prior_loc is None else np.ascontiguousarray(spec.prior_loc, np.float32).reshape(P)
     scale = np.ones(P, np.float32) if spec.prior_scale is None else np.ascontiguousarray(spec.prior_scale, np.float32).reshape(P)
-    self.X = self._to_device(X, dtype)
+    # the uploads are asynchronous when the caller's arrays are pinned: handle creation and planning below overlap with them
+    # (bind_data's finite check, or the explicit synchronize at the end, completes them before __init__ returns)
+    self.X = self._to_device(X, dtype, non_blocking=True)
     if self.X.dim() != 2 or self.X.shape[1] != spec.n_features:
       raise TypeError("X must have shape [N, %d], got %s" % (spec.n_features, tuple(self.X.shape)))
     if self.X.stride(1) != 1 or self.X.data_ptr() % 16 != 0:
@@ -79,7 +81,7 @@ class GLMSampler:
     if yt.dtype not in ymap:
       # the reference casts observed data to the random variable's dtype (inference.py:88-95)
       yt = yt.to(torch.int32 if spec.family != _C.NORMAL_IDENTITY else dtype)
-    self.y = yt.to(self.dev).contiguous()
+    self.y = yt.to(self.dev, non_blocking=True).contiguous()
     if self.y.dim() != 1 or self.y.shape[0] != self.X.shape[0]:
       raise TypeError("y must have shape [%d], got %s" % (self.X.shape[0], tuple(self.y.shape)))
     self.n_rows = int(self.X.shape[0])
@@ -108,12 +110,14 @@ class GLMSampler:
       bind = self.lib.edhmc_bind_data_f64 if f64 else self.lib.edhmc_bind_data
       _C.check(bind(self._h, self.X.data_ptr(), self.y.data_ptr(), 1 if check_finite else 0,
                                         _stream_ptr(self.dev)))
+    if not check_finite:
+      torch.cuda.current_stream(self.dev).synchronize()  # the caller may reuse its host arrays once we return
     self._trace = None
     self.nranks = 1
 
-  def _to_device(self, a, dtype):
+  def _to_device(self, a, dtype, non_blocking=False):
     t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
-    return t.to(device=self.dev, dtype=dtype)
+    return t.to(device=self.dev, dtype=dtype, non_blocking=non_blocking)
 
   # ---- row shards (extension) -----------------------------------------------------------------
   def init_comm(self, nranks: int, rank: int, group=None, peers=None):
