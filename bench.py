@@ -841,7 +841,8 @@ def main():
                  "chains": 1, "plan": {1: "persistent", 2: "stepwise"}[info["plan_in_use"]],
                  "parallelism": ("rows sharded over %d GPUs, %s" % (world, "one persistent launch per GPU, in-kernel all-reduce of [grad, logp] through peer inboxes over NVLink each leapfrog step"
                                   if info["plan_in_use"] == 1 else "NCCL all-reduce per leapfrog step")) if world > 1 else "1 GPU",
-                 "l2": "L2 flushed between steps (512 MiB write); within a step X (%.1f MB) is re-streamed every leapfrog step" % (4e-6 * (r_hi - r_lo) * D),
+                 "l2": ("L2 flushed between steps (512 MiB write); within a step X (%.1f MB) is re-streamed every leapfrog step" % (4e-6 * (r_hi - r_lo) * D))
+                       + (" — except the rows a persistent launch keeps in shared / tensor memory (roofline.on_chip)" if info.get("ring_mode") == 2 else ""),
                  "rng": "device Philox", "grid_ctas": info["grid_ctas"], "ring_stages": info["ring_stages"], "tile_rows": info["tile_rows"],
                  "ring_mode": info.get("ring_mode"), "warps_per_cta": info["warps_per_cta"]},
       "rows_steps_per_s": value * N,
