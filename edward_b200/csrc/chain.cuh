@@ -3,9 +3,13 @@
 // k_hmc<G,V,K> is the one kernel that touches X. It has two launch modes:
 //   mode 0 (persistent plan, cooperative launch): runs ALL transitions of an edhmc_run. Every CTA carries
 //     a redundant copy of the O(P) chain state in shared memory and performs the same integrator / accept
-//     arithmetic on the same all-CTA totals, so the only grid-wide communication per leapfrog step is one
-//     barrier + one read of the per-CTA partial sums. The TMA rings keep streaming the next pass's tiles
-//     while that happens.
+//     arithmetic on the same all-CTA totals, so the only grid-wide communication per leapfrog step is the
+//     exchange of the per-CTA partial sums: on one GPU with a narrow model as fence-free flag-in-data entries
+//     (partials -> sums of 16-CTA groups -> every CTA; "flat" protocol, a.leader == 2), otherwise one grid
+//     barrier + (row shards) the in-kernel all-reduce over peer memory. The data pass between two exchanges
+//     is one of three layouts chosen by the host (RM): a TMA ring per warp, a TMA ring per CTA, or — narrow
+//     rows — re-laid tiles read with LDG, with as many rows as fit parked in shared and tensor memory for
+//     the whole launch (stream_ldg.cuh).
 //   mode 1 (stepwise plan): one data pass at a given theta; the last CTA to finish folds the partials
 //     into a.sums. Single-CTA chain kernels (below) and, when rows are sharded over GPUs, an NCCL
 //     all-reduce of a.sums run between passes.
